@@ -1,0 +1,334 @@
+"""ctypes front-end of the CPU oracle -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.  The product (krylov.jl_b200/) never
+does.  The solver entry points follow Krylov.jl v0.10.8 (src/cg.jl,
+src/gmres.jl, src/bicgstab.jl, src/minres.jl); the problem generators are
+literal SciPy transcriptions of test/get_div_grad.jl and test/test_utils.jl.
+
+Parity pinning: scalar helpers + solver end states are checked against the
+reference's own known-answer tests (tests/test_oracle_kat.py).  Per-iteration
+residual histories on the benchmark configs: parity unpinned (no Julia here).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import scipy.sparse as sp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class Stats(C.Structure):
+    _fields_ = [("niter", C.c_int), ("solved", C.c_int), ("inconsistent", C.c_int),
+                ("indefinite", C.c_int), ("npcCount", C.c_int), ("nres", C.c_int),
+                ("nAres", C.c_int), ("error", C.c_int), ("status", C.c_char * 96)]
+
+
+class Opts(C.Structure):
+    _fields_ = [("atol", C.c_double), ("rtol", C.c_double), ("itmax", C.c_int), ("history", C.c_int),
+                ("radius", C.c_double), ("linesearch", C.c_int), ("lambda_", C.c_double),
+                ("etol", C.c_double), ("conlim", C.c_double), ("window", C.c_int), ("memory", C.c_int),
+                ("restart", C.c_int), ("reorthogonalization", C.c_int), ("ldiv", C.c_int),
+                ("hist_cap", C.c_int)]
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/libkrylov_oracle.so with the committed Makefile."""
+    so = os.path.join(_HERE, "libkrylov_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("krylov_oracle.c", "krylov_oracle_impl.h", "Makefile")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        for suf in ("f64", "f32"):
+            getattr(_LIB, f"oracle_dot_{suf}").restype = C.c_double if suf == "f64" else C.c_float
+    return _LIB
+
+
+def _suf(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float64:
+        return "f64", C.c_double
+    if dtype == np.float32:
+        return "f32", C.c_float
+    raise TypeError(f"oracle supports float32/float64, got {dtype}")
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _csr(A, dtype):
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    return (A.shape[0], np.ascontiguousarray(A.indptr, dtype=np.int32),
+            np.ascontiguousarray(A.indices, dtype=np.int32), np.ascontiguousarray(A.data, dtype=dtype))
+
+
+def _vec(v, dtype):
+    return None if v is None else np.ascontiguousarray(v, dtype=dtype)
+
+
+def _opts(n, kw, default_hist):
+    o = Opts()
+    o.atol = kw.pop("atol", math.nan)
+    o.rtol = kw.pop("rtol", math.nan)
+    o.itmax = kw.pop("itmax", 0)
+    o.history = int(kw.pop("history", True))
+    o.radius = kw.pop("radius", 0.0)
+    o.linesearch = int(kw.pop("linesearch", False))
+    o.lambda_ = kw.pop("lambda_", 0.0)
+    o.etol = kw.pop("etol", math.nan)
+    o.conlim = kw.pop("conlim", math.nan)
+    o.window = kw.pop("window", 0)
+    o.memory = kw.pop("memory", 0)
+    o.restart = int(kw.pop("restart", False))
+    o.reorthogonalization = int(kw.pop("reorthogonalization", False))
+    o.ldiv = int(kw.pop("ldiv", False))
+    itmax = o.itmax if o.itmax > 0 else 2 * n
+    o.hist_cap = kw.pop("hist_cap", min(itmax + 2, default_hist))
+    if kw:
+        raise TypeError(f"unknown options {sorted(kw)}")
+    return o
+
+
+def _result(st, x, res, extra=None):
+    out = dict(niter=st.niter, solved=bool(st.solved), inconsistent=bool(st.inconsistent),
+               indefinite=bool(st.indefinite), npcCount=st.npcCount, error=st.error,
+               status=st.status.decode("utf-8"), residuals=res[:min(st.nres, len(res))].copy())
+    if extra:
+        out.update(extra)
+    return x, out
+
+
+def cg(A, b, x0=None, M=None, dtype=np.float64, **kw):
+    """cg! (src/cg.jl:120-291).  M: None or the diagonal of a Diagonal preconditioner."""
+    suf, _ = _suf(dtype)
+    n, rp, ci, va = _csr(A, dtype)
+    b, x0, M = _vec(b, dtype), _vec(x0, dtype), _vec(M, dtype)
+    o = _opts(n, kw, 1 << 22)
+    x = np.zeros(n, dtype)
+    res = np.zeros(o.hist_cap, dtype)
+    npc = np.zeros(n, dtype)
+    st = Stats()
+    getattr(lib(), f"oracle_cg_{suf}")(n, _p(rp), _p(ci), _p(va), _p(b), _p(x0), _p(M), C.byref(o),
+                                        _p(x), _p(res), _p(npc), C.byref(st))
+    return _result(st, x, res, dict(npc_dir=npc))
+
+
+def bicgstab(A, b, c=None, x0=None, M=None, N=None, dtype=np.float64, **kw):
+    """bicgstab! (src/bicgstab.jl:125-277)."""
+    suf, _ = _suf(dtype)
+    n, rp, ci, va = _csr(A, dtype)
+    b, c, x0, M, N = (_vec(v, dtype) for v in (b, c, x0, M, N))
+    o = _opts(n, kw, 1 << 22)
+    x = np.zeros(n, dtype)
+    res = np.zeros(o.hist_cap, dtype)
+    st = Stats()
+    getattr(lib(), f"oracle_bicgstab_{suf}")(n, _p(rp), _p(ci), _p(va), _p(b), _p(c), _p(x0), _p(M), _p(N),
+                                              C.byref(o), _p(x), _p(res), C.byref(st))
+    return _result(st, x, res)
+
+
+def gmres(A, b, x0=None, M=None, N=None, dtype=np.float64, **kw):
+    """gmres! (src/gmres.jl:121-384)."""
+    suf, _ = _suf(dtype)
+    n, rp, ci, va = _csr(A, dtype)
+    b, x0, M, N = (_vec(v, dtype) for v in (b, x0, M, N))
+    o = _opts(n, kw, 1 << 22)
+    x = np.zeros(n, dtype)
+    res = np.zeros(o.hist_cap, dtype)
+    st = Stats()
+    getattr(lib(), f"oracle_gmres_{suf}")(n, _p(rp), _p(ci), _p(va), _p(b), _p(x0), _p(M), _p(N),
+                                           C.byref(o), _p(x), _p(res), C.byref(st))
+    return _result(st, x, res)
+
+
+def minres(A, b, x0=None, M=None, dtype=np.float64, **kw):
+    """minres! (src/minres.jl:164-485)."""
+    suf, _ = _suf(dtype)
+    n, rp, ci, va = _csr(A, dtype)
+    b, x0, M = _vec(b, dtype), _vec(x0, dtype), _vec(M, dtype)
+    o = _opts(n, kw, 1 << 22)
+    x = np.zeros(n, dtype)
+    res, ares, acond = (np.zeros(o.hist_cap, dtype) for _ in range(3))
+    npc = np.zeros(n, dtype)
+    st = Stats()
+    getattr(lib(), f"oracle_minres_{suf}")(n, _p(rp), _p(ci), _p(va), _p(b), _p(x0), _p(M), C.byref(o),
+                                            _p(x), _p(res), _p(ares), _p(acond), _p(npc), C.byref(st))
+    k = min(st.nAres, o.hist_cap)
+    return _result(st, x, res, dict(Aresiduals=ares[:k].copy(), Acond=acond[:k].copy(), npc_dir=npc))
+
+
+def spmv(A, x, dtype=np.float64):
+    suf, _ = _suf(dtype)
+    n, rp, ci, va = _csr(A, dtype)
+    x = _vec(x, dtype)
+    y = np.zeros(n, dtype)
+    getattr(lib(), f"oracle_spmv_{suf}")(n, _p(rp), _p(ci), _p(va), _p(x), _p(y))
+    return y
+
+
+def dot(x, y, dtype=np.float64):
+    suf, _ = _suf(dtype)
+    x, y = _vec(x, dtype), _vec(y, dtype)
+    return float(getattr(lib(), f"oracle_dot_{suf}")(len(x), _p(x), _p(y)))
+
+
+def sym_givens(a, b, dtype=np.float64):
+    suf, ct = _suf(dtype)
+    c, s, r = ct(), ct(), ct()
+    getattr(lib(), f"oracle_sym_givens_{suf}")(ct(a), ct(b), C.byref(c), C.byref(s), C.byref(r))
+    return c.value, s.value, r.value
+
+
+def roots_quadratic(q2, q1, q0, nitref=1, dtype=np.float64):
+    suf, ct = _suf(dtype)
+    r1, r2 = ct(), ct()
+    rc = getattr(lib(), f"oracle_roots_quadratic_{suf}")(ct(q2), ct(q1), ct(q0), nitref, C.byref(r1), C.byref(r2))
+    if rc:
+        raise ArithmeticError("The quadratic `q` doesn't have real roots.")
+    return r1.value, r2.value
+
+
+def to_boundary(x, d, radius, flip=False, xNorm2=0.0, dNorm2=0.0, M=None, ldiv=False, dtype=np.float64):
+    suf, ct = _suf(dtype)
+    x, d, M = _vec(x, dtype), _vec(d, dtype), _vec(M, dtype)
+    z = np.zeros_like(x)
+    s1, s2 = ct(), ct()
+    rc = getattr(lib(), f"oracle_to_boundary_{suf}")(len(x), _p(x), _p(d), _p(z), ct(radius), int(flip),
+                                                     ct(xNorm2), ct(dNorm2), _p(M), int(ldiv),
+                                                     C.byref(s1), C.byref(s2))
+    if rc:
+        raise ArithmeticError({1: "radius must be positive", 2: "zero direction",
+                               3: "outside of the trust region"}.get(rc, "no real roots"))
+    return s1.value, s2.value
+
+
+# --------------------------------------------------------------------------
+# Problem generators: literal transcriptions of the reference's test helpers.
+# --------------------------------------------------------------------------
+
+def eye(n):
+    """eye(n) = sparse(I, n, n)  (test/get_div_grad.jl:2)."""
+    return sp.identity(n, format="csc")
+
+
+def ddx(n):
+    """1-D staggered-grid difference, n x (n+1)  (test/get_div_grad.jl:21-25)."""
+    e = np.ones(n)
+    rows = np.concatenate([np.arange(n), np.arange(n)])
+    cols = np.concatenate([np.arange(n), np.arange(1, n + 1)])
+    return sp.csc_matrix((np.concatenate([-e, e]), (rows, cols)), shape=(n, n + 1))
+
+
+def get_div_grad(n1, n2, n3):
+    """Div * Div'  (test/get_div_grad.jl:8-19) -- literal Kronecker construction."""
+    D1 = sp.kron(eye(n3), sp.kron(eye(n2), ddx(n1)))
+    D2 = sp.kron(eye(n3), sp.kron(ddx(n2), eye(n1)))
+    D3 = sp.kron(ddx(n3), sp.kron(eye(n2), eye(n1)))
+    Div = sp.hstack([D1, D2, D3], format="csc")
+    A = sp.csr_matrix(Div @ Div.T)
+    A.sort_indices()
+    return A
+
+
+def sparse_laplacian(n=16):
+    """test/test_utils.jl:153-157"""
+    return get_div_grad(n, n, n), np.ones(n ** 3)
+
+
+def symmetric_definite(n=10):
+    """test/test_utils.jl:18-23"""
+    A = sp.diags([np.ones(n - 1), 4 * np.ones(n), np.ones(n - 1)], [-1, 0, 1], format="csr")
+    return A, A @ np.arange(1, n + 1, dtype=float)
+
+
+def symmetric_indefinite(n=10, shift=0):
+    """test/test_utils.jl:26-31"""
+    A = sp.diags([np.ones(n - 1), np.ones(n), np.ones(n - 1)], [-1, 0, 1], format="csr") - shift * sp.identity(n)
+    A = sp.csr_matrix(A)
+    return A, A @ np.arange(1, n + 1, dtype=float)
+
+
+def kron_unsymmetric(n=64):
+    """test/test_utils.jl:160-169"""
+    T = sp.diags([-np.ones(n - 1), 3.0 * np.ones(n), -2.0 * np.ones(n - 1)], [-1, 0, 1], format="csr")
+    Id = sp.identity(n, format="csr")
+    A = sp.kron(T, Id) + sp.kron(Id, T)
+    Id2 = Id  # the reference re-uses the same n x n identity in the second step
+    A = sp.kron(A, Id2) + sp.kron(Id2, A)
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    return A, A @ np.ones(A.shape[0])
+
+
+def almost_singular(n=16):
+    """test/test_utils.jl:172-177"""
+    A = sp.csr_matrix(get_div_grad(n, n, n) - 5 * sp.identity(n ** 3))
+    return A, A @ np.ones(n ** 3)
+
+
+def cartesian_poisson(n=50, m=50):
+    """test/test_utils.jl:294-299 + test/get_div_grad.jl:179-222"""
+    dx, dy = 1.0 / (n + 1), 1.0 / (m + 1)
+    xs = np.array([i * dx for i in range(1, n + 1)])
+    ys = np.array([j * dy for j in range(1, m + 1)])
+    A = sp.lil_matrix((n * m, n * m))
+    for i in range(n):
+        for j in range(m):
+            k = i + j * n
+            A[k, k] = -2.0 / (dx * dx) - 2.0 / (dy * dy)
+            if i >= 1:
+                A[k, k - 1] = 1.0 / (dx * dx)
+            if i <= n - 2:
+                A[k, k + 1] = 1.0 / (dx * dx)
+            if j >= 1:
+                A[k, k - n] = 1.0 / (dy * dy)
+            if j <= m - 2:
+                A[k, k + n] = 1.0 / (dy * dy)
+    b = np.zeros(n * m)
+    for i in range(n):
+        for j in range(m):
+            b[i + j * n] = -2.0 * math.pi * math.pi * math.sin(math.pi * xs[i]) * math.sin(math.pi * ys[j])
+    return sp.csr_matrix(A), b
+
+
+def square_preconditioned(n=10):
+    """test/test_utils.jl:302-307; returns (A, b, diag(M^-1))."""
+    A = sp.csr_matrix(np.ones((n, n)) + (n - 1) * np.eye(n))
+    return A, 10.0 * np.arange(1, n + 1, dtype=float), np.full(n, 1.0 / n)
+
+
+def zero_rhs(n=10, seed=0):
+    """test/test_utils.jl:319-323 (rand matrix, b = 0)."""
+    return sp.csr_matrix(np.random.default_rng(seed).random((n, n))), np.zeros(n)
+
+
+def square_inconsistent(n=10):
+    """test/test_utils.jl (Diagonal(ones) with A[1,1]=0, b=ones)."""
+    d = np.ones(n)
+    d[0] = 0.0
+    A = sp.csr_matrix(sp.diags(d))
+    return A, np.ones(n)
+
+
+def singular_consistent(n=10):
+    """test/test_utils.jl:181-186"""
+    A = np.array([[float(i * j) for j in range(1, n + 1)] for i in range(1, n + 1)]) + 5 * np.eye(n)
+    A[:, 0] = 1.0  # chained broadcast assignment: every target gets one(FC)
+    A[:, 1] = 1.0
+    A[1, :] = 1.0
+    A[0, :] = 1.0
+    return sp.csr_matrix(A), A @ np.ones(n)
