@@ -1,0 +1,250 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (contract: task statement section 4).
+
+Metric (BASELINE.json): CG iterations/s on the 3-D 7-point Poisson matrix
+get_div_grad(N,N,N), N = 215 (n = 9 938 375, nnz = 69 291 275), Float64, b = ones,
+and the achieved fraction of the HBM roofline.
+
+A "step" is one cg!(ws, A, b; atol=0, rtol=0, itmax=ITERS) solve = ITERS fused
+iterations (2 kernel launches each).  `value` is timed with CUDA events on the
+workspace's own stream with A and b resident in HBM; `e2e` times the same solve
+through the reference-facing C ABI (krylov_solve / krylov_get_x) with pinned HOST
+buffers for b and x.  The matrix (871 MB) is far larger than L2 (126 MB), so
+every iteration streams it from HBM: no explicit L2 flush is needed.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload poisson215]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "krylov.jl_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (N, iterations per step)
+    "poisson215": (215, 100),     # BASELINE config 2  (n ~ 1e7)
+    "poisson464": (464, 50),      # BASELINE config 5  (n ~ 1e8)
+    "poisson32": (32, 79),        # BASELINE config 1  (CPU-runnable reference case)
+}
+FALLBACK_HBM_GBS = 6650.0         # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def algorithmic_bytes_cg(n, nnz, v=8, i=4):
+    """B_cg = nnz(v+i) + (n+1)i + 9nv per fused CG iteration."""
+    return nnz * (v + i) + (n + 1) * i + 9 * n * v
+
+
+def hbm_peak():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_problem(N, torch, device, k_lo=0, k_hi=None):
+    from krylov_b200.problems import div_grad_csr
+    rp, ci, va = div_grad_csr(N, xp=torch, device=device, k_lo=k_lo, k_hi=k_hi)
+    return rp, ci, va
+
+
+def cpu_leg(N, iters, threads, budget_s=20.0):
+    """Times the CPU restatement of the same loop (oracle/, kind 'port') on a bounded sample of the workload:
+    the same matrix, fewer iterations (sized for ~10-30 s)."""
+    from krylov_b200.problems import div_grad_csr
+    from oracle import oracle as O
+    rp, ci, va = div_grad_csr(N)
+    b = np.ones(N ** 3)
+    t, _, _ = O.cg_timed(rp, ci, va, b, 2, threads)           # calibrate
+    per_it = max(t / 2, 1e-6)
+    k = int(max(3, min(iters, budget_s / per_it)))
+    t, _, rn = O.cg_timed(rp, ci, va, b, k, threads)
+    return dict(value=k / t, unit="CG iterations/s", cores=threads, kind="port",
+                sample=f"{k} iterations of cg.jl:195-268 on get_div_grad({N},{N},{N}), b=ones, {threads} thread(s), "
+                       f"{t:.2f} s wall"), k, t
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  Julia is not in this image, so the timed code is the
+    oracle port (oracle/krylov_oracle.c), threaded over all host cores it can use."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, iters = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    n, nnz = N ** 3, 7 * N ** 3 - 6 * N ** 2
+    total_it, total_t = 0, 0.0
+    leg = None
+    for s in range(args.warmup + args.steps):
+        leg, k, t = cpu_leg(N, iters, threads, budget_s=max(2.0, 60.0 / max(1, args.warmup + args.steps)))
+        if s >= args.warmup:
+            total_it += k; total_t += t
+    v = total_it / total_t
+    line = dict(metric="CG iterations/s", value=v, unit="it/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * total_t / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=f"cg! on get_div_grad({N},{N},{N}) Float64 CSR, b=ones, fixed iterations", n=n, nnz=nnz,
+                            note="Julia absent: CPU restatement (oracle port) of src/cg.jl:195-268, OpenMP over host cores"),
+                cpu_baseline=dict(leg, value=v),
+                e2e=dict(value=v, unit="it/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("KB200_WORKLOAD", "poisson215"), choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import krylov_b200 as kb
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from krylov_b200 import dist
+        return dist.bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler)
+    if kb.device_count() < 1:
+        raise SystemExit("bench.py needs a B200: libkrylov_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    N, iters = WORKLOADS[args.workload]
+    n, nnz = N ** 3, 7 * N ** 3 - 6 * N ** 2
+    t0 = time.perf_counter()
+    rp, ci, va = build_problem(N, torch, dev)
+    assert int(va.numel()) == nnz
+    gen_s = time.perf_counter() - t0
+    b = torch.ones(n, dtype=torch.float64, device=dev)
+
+    # ---- device-resident arm (value) --------------------------------------
+    ws = kb.CgWorkspace(n, n, np.float64, device="cuda")
+    t0 = time.perf_counter()
+    ws.set_operator((rp, ci, va))
+    upload_s = time.perf_counter() - t0
+    stream = torch.cuda.ExternalStream(kb.lib().krylov_b200_stream(ws._h), device=dev)
+    solve_kw = dict(atol=0.0, rtol=0.0, itmax=iters)
+    for _ in range(args.warmup):
+        ws.solve(None, b, **solve_kw)
+    assert ws.stats.niter == iters, ws.stats
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ws.launches
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        ws.solve(None, b, **solve_kw)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = ws.launches - l0
+    ms = e0.elapsed_time(e1)
+    its = args.steps * iters
+    value = its / (ms * 1e-3)
+    B = algorithmic_bytes_cg(n, nnz)
+    peak, peak_src = hbm_peak()
+    achieved = B * its / (ms * 1e-3) / 1e9
+    rnorm = ws.stats  # noqa: F841
+
+    # ---- end-to-end arm: C ABI with pinned host buffers ---------------------
+    wsh = kb.CgWorkspace(n, n, np.float64, device="host")
+    wsh.share_operator(ws)
+    bh = torch.ones(n, dtype=torch.float64).pin_memory()
+    xh = torch.empty(n, dtype=torch.float64).pin_memory()
+    bh_np, xh_np = bh.numpy(), xh.numpy()
+    import ctypes as C
+    for _ in range(max(1, args.warmup - 1)):
+        wsh.solve(None, bh_np, **solve_kw)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        wsh.solve(None, bh_np, **solve_kw)                                   # H2D of b inside
+        kb.lib().krylov_get_x(wsh._h, C.c_void_p(xh.data_ptr()), n)          # D2H of x inside
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e = dict(value=its / e2e_s, unit="it/s", h2d_bytes_per_step=n * 8, d2h_bytes_per_step=n * 8,
+               ms_per_step=1e3 * e2e_s / args.steps)
+
+    line = dict(metric="CG iterations/s", value=value, unit="it/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+                data="synthetic",
+                config=dict(workload=f"cg! fused (2 launches/iter) on get_div_grad({N},{N},{N}) Float64 int32-CSR, b=ones, "
+                                     f"atol=rtol=0, itmax={iters} per step", n=n, nnz=nnz, iters_per_step=iters,
+                            l2="inputs larger than L2 (matrix 0.87 GB vs 126 MB): no flush needed",
+                            matrix_upload_s=round(upload_s, 3), matrix_generate_s=round(gen_s, 3)),
+                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                              peak_source=peak_src, bytes_per_iteration=B,
+                              note="unit = one fused CG iteration (cg_k1 + cg_k2); B_cg from SURVEY.md 8(d)"),
+                clocks=clocks, e2e=e2e, gpu_launches=int(launches))
+    if not args.no_cpu:
+        try:
+            leg, _, _ = cpu_leg(N, iters, 1, budget_s=15.0)
+            line["cpu_baseline"] = leg
+        except Exception as ex:  # the CPU leg must never cost the GPU number
+            line["cpu_baseline"] = dict(value=None, unit="it/s", cores=1, kind="port", sample=f"failed: {ex}")
+    print(json.dumps(line))
+    ws.free(); wsh.free()
+
+
+if __name__ == "__main__":
+    main()

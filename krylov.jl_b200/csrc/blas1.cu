@@ -1,0 +1,232 @@
+// blas1.cu -- device implementations of Krylov.jl's vector primitives
+// (src/krylov_utils.jl:309-349): kdot/kdotr, knorm, kscal!, kdiv!, kcopy!,
+// kscalcopy!, kdivcopy!, kaxpy!, kaxpby!, kfill!.
+//
+// All kernels are HBM-bound streaming passes: grid = whole CTAs per SM,
+// grid-stride loops with 4 independent elements in flight per thread.
+// Element updates use non-contracted mul/add so they agree bit-for-bit with
+// the reference's `y[i] += s*x[i]` (Julia does not fuse); reductions are
+// deterministic two-stage tree sums finalised by the last CTA on the device.
+#include "kb_internal.h"
+
+#include <chrono>
+
+namespace kb {
+
+double now_seconds() {
+  using namespace std::chrono;
+  return duration_cast<duration<double>>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------------------
+void Ctx::init(int dev) {
+  device = dev;
+  KB_CUDA(cudaSetDevice(dev));
+  KB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  own_stream = true;
+  KB_CUDA(cudaMalloc(&partials, sizeof(double) * kMaxPartials * 4));
+  KB_CUDA(cudaMalloc((void**)&tickets, sizeof(unsigned) * 8));
+  KB_CUDA(cudaMemset(tickets, 0, sizeof(unsigned) * 8));
+  KB_CUDA(cudaMalloc(&dscal, sizeof(double) * 16));
+  KB_CUDA(cudaMemset(dscal, 0, sizeof(double) * 16));
+  KB_CUDA(cudaHostAlloc(&hscal, sizeof(double) * 16, cudaHostAllocDefault));
+}
+
+void Ctx::destroy() {
+  if (partials) cudaFree(partials);
+  if (tickets) cudaFree(tickets);
+  if (dscal) cudaFree(dscal);
+  if (hscal) cudaFreeHost(hscal);
+  if (own_stream && stream) cudaStreamDestroy(stream);
+  partials = nullptr; tickets = nullptr; dscal = nullptr; hscal = nullptr; stream = nullptr;
+}
+
+template <class T> T* dev_alloc(size_t n) {
+  void* p = nullptr;
+  KB_CUDA(cudaMalloc(&p, n * sizeof(T) + 64));   // 64 B tail pad: TMA tiles may over-read up to 16 B
+  return (T*)p;
+}
+void dev_free(void* p) { if (p) cudaFree(p); }
+template double* dev_alloc<double>(size_t);
+template float* dev_alloc<float>(size_t);
+template int* dev_alloc<int>(size_t);
+template char* dev_alloc<char>(size_t);
+
+// ---------------------------------------------------------------------------
+// Elementwise kernels
+// ---------------------------------------------------------------------------
+enum EwOp { EW_AXPY, EW_AXPBY, EW_SCAL, EW_COPY, EW_SCALCOPY, EW_DIVCOPY, EW_FILL, EW_DIAGMUL, EW_DIAGDIV };
+
+template <class T, int OP>
+__global__ void __launch_bounds__(kBlock) ew_kernel(int n, T s, T t, const T* x, const T* d, T* y) {
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // 4 independent elements per trip keep enough loads in flight per thread.
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    T xv[4], yv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int j = i + u * stride;
+      if (OP != EW_FILL && OP != EW_SCAL) xv[u] = x[j];
+      if (OP == EW_AXPY || OP == EW_AXPBY || OP == EW_SCAL) yv[u] = y[j];
+      if (OP == EW_DIAGMUL || OP == EW_DIAGDIV) yv[u] = d[j];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int j = i + u * stride;
+      T r;
+      if (OP == EW_AXPY) r = add_rn(yv[u], mul_rn(s, xv[u]));
+      else if (OP == EW_AXPBY) r = add_rn(mul_rn(s, xv[u]), mul_rn(t, yv[u]));
+      else if (OP == EW_SCAL) r = mul_rn(s, yv[u]);
+      else if (OP == EW_COPY) r = xv[u];
+      else if (OP == EW_SCALCOPY) r = mul_rn(s, xv[u]);
+      else if (OP == EW_DIVCOPY) r = div_rn(xv[u], s);
+      else if (OP == EW_FILL) r = s;
+      else if (OP == EW_DIAGMUL) r = mul_rn(yv[u], xv[u]);
+      else r = div_rn(xv[u], yv[u]);
+      y[j] = r;
+    }
+  }
+  for (; i < n; i += stride) {
+    T r;
+    if (OP == EW_AXPY) r = add_rn(y[i], mul_rn(s, x[i]));
+    else if (OP == EW_AXPBY) r = add_rn(mul_rn(s, x[i]), mul_rn(t, y[i]));
+    else if (OP == EW_SCAL) r = mul_rn(s, y[i]);
+    else if (OP == EW_COPY) r = x[i];
+    else if (OP == EW_SCALCOPY) r = mul_rn(s, x[i]);
+    else if (OP == EW_DIVCOPY) r = div_rn(x[i], s);
+    else if (OP == EW_FILL) r = s;
+    else if (OP == EW_DIAGMUL) r = mul_rn(d[i], x[i]);
+    else r = div_rn(x[i], d[i]);
+    y[i] = r;
+  }
+}
+
+template <class T, int OP>
+static void ew_launch(Ctx& c, int n, T s, T t, const T* x, const T* d, T* y) {
+  if (n <= 0) return;
+  const int grid = stream_grid(n, 4, 8);
+  ew_kernel<T, OP><<<grid, kBlock, 0, c.stream>>>(n, s, t, x, d, y);
+  KB_CUDA(cudaGetLastError());
+  c.launches++;
+}
+
+template <class T> void k_axpy(Ctx& c, int n, T s, const T* x, T* y) { ew_launch<T, EW_AXPY>(c, n, s, T(0), x, nullptr, y); }
+template <class T> void k_axpby(Ctx& c, int n, T s, const T* x, T t, T* y) { ew_launch<T, EW_AXPBY>(c, n, s, t, x, nullptr, y); }
+template <class T> void k_scal(Ctx& c, int n, T s, T* x) { ew_launch<T, EW_SCAL>(c, n, s, T(0), nullptr, nullptr, x); }
+template <class T> void k_copy(Ctx& c, int n, T* y, const T* x) {
+  if (n > 0 && y != x) KB_CUDA(cudaMemcpyAsync(y, x, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, c.stream));
+}
+template <class T> void k_scalcopy(Ctx& c, int n, T* y, T s, const T* x) { ew_launch<T, EW_SCALCOPY>(c, n, s, T(0), x, nullptr, y); }
+template <class T> void k_divcopy(Ctx& c, int n, T* y, const T* x, T s) { ew_launch<T, EW_DIVCOPY>(c, n, s, T(0), x, nullptr, y); }
+template <class T> void k_fill(Ctx& c, int n, T* x, T v) {
+  if (n <= 0) return;
+  if (v == T(0)) { KB_CUDA(cudaMemsetAsync(x, 0, sizeof(T) * (size_t)n, c.stream)); return; }
+  ew_launch<T, EW_FILL>(c, n, v, T(0), nullptr, nullptr, x);
+}
+template <class T> void k_diagmul(Ctx& c, int n, T* y, const T* d, const T* x, bool ldiv) {
+  if (ldiv) ew_launch<T, EW_DIAGDIV>(c, n, T(0), T(0), x, d, y);
+  else ew_launch<T, EW_DIAGMUL>(c, n, T(0), T(0), x, d, y);
+}
+
+// ---------------------------------------------------------------------------
+// Reductions
+// ---------------------------------------------------------------------------
+template <class T, int K>
+__global__ void __launch_bounds__(kBlock) dot_kernel(int n, const T* __restrict__ a, const T* __restrict__ b,
+                                                     const T* __restrict__ u, const T* __restrict__ v, T* part,
+                                                     unsigned* ticket, T* out, int do_sqrt) {
+  __shared__ T sm[32];
+  const int stride = gridDim.x * blockDim.x;
+  T acc[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) acc[k] = T(0);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    T av[4], bv[4], uv[4], vv[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      av[q] = a[i + q * stride]; bv[q] = b[i + q * stride];
+      if (K > 1) { uv[q] = u[i + q * stride]; vv[q] = v[i + q * stride]; }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      acc[0] += av[q] * bv[q];
+      if (K > 1) acc[K - 1] += uv[q] * vv[q];
+    }
+  }
+  for (; i < n; i += stride) {
+    acc[0] += a[i] * b[i];
+    if (K > 1) acc[K - 1] += u[i] * v[i];
+  }
+  T mine[K], tot[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    mine[k] = block_sum(acc[k], sm);
+  }
+  if (grid_sum_last<T, K>(mine, part, ticket, sm, tot)) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < K; k++) out[k] = do_sqrt ? sqrt_rn(tot[k]) : tot[k];
+    }
+  }
+}
+
+template <class T>
+static T* slot_ptr(Ctx& c, int slot) { return reinterpret_cast<T*>(reinterpret_cast<double*>(c.dscal) + slot); }
+
+template <class T>
+static void dot_launch(Ctx& c, int n, const T* a, const T* b, int slot, int do_sqrt) {
+  const int grid = n > 0 ? stream_grid(n, 4, 4) : 1;
+  dot_kernel<T, 1><<<grid, kBlock, 0, c.stream>>>(n, a, b, nullptr, nullptr, (T*)c.partials, c.tickets, slot_ptr<T>(c, slot), do_sqrt);
+  KB_CUDA(cudaGetLastError());
+  c.launches++;
+}
+
+template <class T>
+static T read_slot(Ctx& c, int slot) {
+  KB_CUDA(cudaMemcpyAsync(reinterpret_cast<double*>(c.hscal) + slot, reinterpret_cast<double*>(c.dscal) + slot,
+                          sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  c.sync();
+  return *reinterpret_cast<T*>(reinterpret_cast<double*>(c.hscal) + slot);
+}
+
+template <class T> void k_dot_dev(Ctx& c, int n, const T* x, const T* y, int slot) { dot_launch<T>(c, n, x, y, slot, 0); }
+template <class T> T k_dot(Ctx& c, int n, const T* x, const T* y) {
+  dot_launch<T>(c, n, x, y, 0, 0);
+  return read_slot<T>(c, 0);
+}
+template <class T> T k_nrm2(Ctx& c, int n, const T* x) {
+  dot_launch<T>(c, n, x, x, 0, 1);
+  return read_slot<T>(c, 0);
+}
+template <class T> void k_dot2(Ctx& c, int n, const T* a, const T* b, const T* u, const T* v, T* r1, T* r2) {
+  const int grid = n > 0 ? stream_grid(n, 4, 4) : 1;
+  // two adjacent T outputs live in slot 0 (out[0], out[1])
+  dot_kernel<T, 2><<<grid, kBlock, 0, c.stream>>>(n, a, b, u, v, (T*)c.partials, c.tickets, slot_ptr<T>(c, 0), 0);
+  KB_CUDA(cudaGetLastError());
+  c.launches++;
+  KB_CUDA(cudaMemcpyAsync(c.hscal, c.dscal, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  c.sync();
+  *r1 = reinterpret_cast<T*>(c.hscal)[0];
+  *r2 = reinterpret_cast<T*>(c.hscal)[1];
+}
+
+#define INST(T)                                                                        \
+  template T k_dot<T>(Ctx&, int, const T*, const T*);                                  \
+  template T k_nrm2<T>(Ctx&, int, const T*);                                           \
+  template void k_dot2<T>(Ctx&, int, const T*, const T*, const T*, const T*, T*, T*);  \
+  template void k_dot_dev<T>(Ctx&, int, const T*, const T*, int);                      \
+  template void k_axpy<T>(Ctx&, int, T, const T*, T*);                                 \
+  template void k_axpby<T>(Ctx&, int, T, const T*, T, T*);                             \
+  template void k_scal<T>(Ctx&, int, T, T*);                                           \
+  template void k_copy<T>(Ctx&, int, T*, const T*);                                    \
+  template void k_scalcopy<T>(Ctx&, int, T*, T, const T*);                             \
+  template void k_divcopy<T>(Ctx&, int, T*, const T*, T);                              \
+  template void k_fill<T>(Ctx&, int, T*, T);                                           \
+  template void k_diagmul<T>(Ctx&, int, T*, const T*, const T*, bool);
+INST(double)
+INST(float)
+#undef INST
+
+}  // namespace kb

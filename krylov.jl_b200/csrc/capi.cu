@@ -1,0 +1,551 @@
+// capi.cu -- the C ABI declared in include/krylov_b200.h.
+//
+// Part 1 mirrors interfaces/src/LibKrylov.jl (entry points) and
+// interfaces/src/c_stores.jl (handle store, option mapping) of the reference:
+// never propagate exceptions, log to stderr, return -1; -2 for unknown
+// (solver, dtype); free returns 1 for an unknown handle.  Unlike the reference
+// (global typed Dicts, documented as not thread-safe) the handle table is a
+// single mutex-protected map.
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/krylov_b200.h"
+#include "kb_internal.h"
+
+using namespace kb;
+
+namespace {
+
+thread_local std::string g_last_error;
+int g_device = -1;
+
+struct CsrAny {
+  int dtype = 1;
+  Csr<double> d;
+  Csr<float> f;
+  Ctx* owner_ctx = nullptr;
+  ~CsrAny() { csr_free(d); csr_free(f); }
+};
+
+struct Handle {
+  int solver = 0, dtype = 1, device_kind = 0;
+  void* ws = nullptr;
+  std::shared_ptr<CsrAny> csr;
+  void* Mdiag = nullptr;
+  void* Ndiag = nullptr;
+  KrylovB200Options ext;
+  void *hx = nullptr, *hy = nullptr;   // pinned staging for host callbacks
+  void* xstage = nullptr;              // pinned staging for b / x transfers
+};
+
+std::mutex g_mu;
+std::unordered_map<void*, Handle*> g_handles;
+
+Handle* lookup(void* p) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_handles.find(p);
+  return it == g_handles.end() ? nullptr : it->second;
+}
+
+int fail(const char* where, const std::exception& e) {
+  g_last_error = std::string(where) + ": " + e.what();
+  fprintf(stderr, "[krylov_b200] %s\n", g_last_error.c_str());
+  return -1;
+}
+int fail(const char* where, const char* msg) {
+  g_last_error = std::string(where) + ": " + msg;
+  fprintf(stderr, "[krylov_b200] %s\n", g_last_error.c_str());
+  return -1;
+}
+
+bool supported_solver(int s) { return s == S_CG || s == S_MINRES || s == S_GMRES || s == S_BICGSTAB; }
+
+int pick_device() {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0) {
+    cudaGetLastError();
+    throw std::runtime_error("no usable CUDA device: libkrylov_b200 has no CPU compute path");
+  }
+  int dev = g_device;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+  if (dev >= cnt) throw std::runtime_error("device index out of range");
+  cudaDeviceProp prop;
+  KB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) throw std::runtime_error("libkrylov_b200 is built for sm_100a only");
+  return dev;
+}
+
+template <class T> Workspace<T>* W(Handle* h) { return reinterpret_cast<Workspace<T>*>(h->ws); }
+template <class T> Csr<T>& csr_of(CsrAny& a);
+template <> Csr<double>& csr_of<double>(CsrAny& a) { return a.d; }
+template <> Csr<float>& csr_of<float>(CsrAny& a) { return a.f; }
+
+template <class T> void destroy_handle(Handle* h) {
+  Workspace<T>* ws = W<T>(h);
+  if (ws) {
+    KB_CUDA(cudaSetDevice(ws->ctx.device));
+    if (ws->ctx.stream) cudaStreamSynchronize(ws->ctx.stream);
+  }
+  h->csr.reset();
+  dev_free(h->Mdiag); dev_free(h->Ndiag);
+  if (h->hx) cudaFreeHost(h->hx);
+  if (h->hy) cudaFreeHost(h->hy);
+  if (h->xstage) cudaFreeHost(h->xstage);
+  ws_destroy<T>(ws);
+  delete h;
+}
+
+// Bring a caller vector (host or device, per device_kind) into a device buffer.
+template <class T> const T* stage_in(Handle* h, Workspace<T>* ws, const void* src, T*& buf) {
+  if (!src) return nullptr;
+  if (h->device_kind == KRYLOV_CUDA) return (const T*)src;
+  if (!buf) buf = dev_alloc<T>((size_t)ws->n);
+  KB_CUDA(cudaMemcpyAsync(buf, src, sizeof(T) * (size_t)ws->n, cudaMemcpyHostToDevice, ws->ctx.stream));
+  return buf;
+}
+
+template <class T> LinOp<T> make_cb_op(Handle* h, Workspace<T>* ws, KrylovMatvec fn, void* ud) {
+  LinOp<T> op;
+  op.n = ws->n;
+  if (!fn) return op;
+  op.fn = fn; op.userdata = ud;
+  if (h->device_kind == KRYLOV_CUDA) { op.kind = LinOp<T>::DEV_CB; return op; }
+  op.kind = LinOp<T>::HOST_CB;
+  if (!h->hx) {
+    KB_CUDA(cudaHostAlloc(&h->hx, sizeof(T) * (size_t)ws->n, cudaHostAllocDefault));
+    KB_CUDA(cudaHostAlloc(&h->hy, sizeof(T) * (size_t)ws->n, cudaHostAllocDefault));
+  }
+  op.hx = (T*)h->hx; op.hy = (T*)h->hy;
+  return op;
+}
+
+// _opts_kw + per-family kwargs (interfaces/src/c_stores.jl:255-260, 288-300 CG,
+// 303-315 MINRES, 334-354 BiCGSTAB, 377-398 GMRES)
+SolveOpts map_opts(const Handle* h, const KrylovOptions* o) {
+  SolveOpts s;
+  KrylovOptions d = krylov_default_options();
+  if (!o) o = &d;
+  s.atol = std::isnan(o->atol) ? -1 : o->atol;
+  s.rtol = std::isnan(o->rtol) ? -1 : o->rtol;
+  s.itmax = o->itmax;
+  s.verbose = o->verbose;
+  s.timemax = std::isnan(o->timemax) ? INFINITY : o->timemax;
+  if (h->solver == S_CG) { s.radius = o->radius; s.linesearch = o->linesearch != 0; }
+  if (h->solver == S_MINRES) { s.lambda = o->lambda; s.linesearch = o->linesearch != 0; }
+  if (h->solver == S_GMRES) { s.restart = o->restart != 0; s.reorthogonalization = o->reorthogonalization != 0; }
+  s.history = h->ext.history != 0;
+  s.ldiv = h->ext.ldiv != 0;
+  s.etol = std::isnan(h->ext.etol) ? -1 : h->ext.etol;
+  s.conlim = std::isnan(h->ext.conlim) ? -1 : h->ext.conlim;
+  s.fused = h->ext.fused;
+  s.batch = h->ext.batch;
+  s.callback = h->ext.callback;
+  s.callback_user = h->ext.callback_user;
+  return s;
+}
+
+template <class T>
+int do_solve(Handle* h, KrylovMatvec fA, KrylovMatvec fM, KrylovMatvec fN, const void* b, const void* c, void* ud,
+             const KrylovOptions* opts) {
+  Workspace<T>* ws = W<T>(h);
+  KB_CUDA(cudaSetDevice(ws->ctx.device));
+  SolveOpts so = map_opts(h, opts);
+  LinOp<T> A;
+  if (fA) A = make_cb_op<T>(h, ws, fA, ud);
+  else if (h->csr) { A.kind = LinOp<T>::CSR; A.csr = &csr_of<T>(*h->csr); A.n = ws->n; }
+  else throw std::runtime_error("no operator: pass matvec_A or attach one with krylov_b200_set_operator_csr");
+  if (A.kind == LinOp<T>::CSR && A.csr->n != ws->n) throw std::runtime_error("(workspace.m, workspace.n) is inconsistent with size(A)");
+  LinOp<T> M = make_cb_op<T>(h, ws, fM, ud), N = make_cb_op<T>(h, ws, fN, ud);
+  if (!fM && h->Mdiag) { M.kind = LinOp<T>::DIAG; M.diag = (const T*)h->Mdiag; }
+  if (!fN && h->Ndiag) { N.kind = LinOp<T>::DIAG; N.diag = (const T*)h->Ndiag; }
+  if (!b) throw std::runtime_error("b is NULL");
+  const T* bd = stage_in<T>(h, ws, b, ws->bbuf);
+  switch (h->solver) {
+    case S_CG: cg_solve<T>(*ws, A, bd, M, so); break;
+    case S_MINRES: minres_solve<T>(*ws, A, bd, M, so); break;
+    case S_GMRES: gmres_solve<T>(*ws, A, bd, M, N, so); break;
+    case S_BICGSTAB: {
+      // the reference's C layer never forwards `c` for BiCGSTAB (c = b); we accept it when given
+      const T* cd = stage_in<T>(h, ws, c, ws->cbuf);
+      bicgstab_solve<T>(*ws, A, bd, cd, M, N, so);
+      break;
+    }
+  }
+  return 0;
+}
+
+template <class T> int do_get_x(Handle* h, void* x, int n) {
+  Workspace<T>* ws = W<T>(h);
+  if (n > ws->n) n = ws->n;
+  KB_CUDA(cudaSetDevice(ws->ctx.device));
+  KB_CUDA(cudaMemcpyAsync(x, ws->x, sizeof(T) * (size_t)n,
+                          h->device_kind == KRYLOV_CUDA ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ws->ctx.stream));
+  ws->ctx.sync();
+  return 0;
+}
+
+template <class T> int do_warm_start(Handle* h, const void* x0, int n) {
+  Workspace<T>* ws = W<T>(h);
+  if (n != ws->n) throw std::runtime_error("x0 should have size n");
+  KB_CUDA(cudaSetDevice(ws->ctx.device));
+  // c_stores.jl:218-229: allocate dx if empty, copy, set the flag
+  if (!ws->dx) ws->dx = dev_alloc<T>((size_t)ws->n);
+  KB_CUDA(cudaMemcpyAsync(ws->dx, x0, sizeof(T) * (size_t)n,
+                          h->device_kind == KRYLOV_CUDA ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ws->ctx.stream));
+  ws->ctx.sync();
+  ws->warm_start = true;
+  return 0;
+}
+
+template <class T> Stats& stats_of(Handle* h) { return W<T>(h)->stats; }
+Stats& stats_any(Handle* h) { return h->dtype == KRYLOV_FLOAT64 ? stats_of<double>(h) : stats_of<float>(h); }
+
+template <class T> void* vec_by_name(Workspace<T>* ws, const char* nm) {
+  struct { const char* n; T* p; } tab[] = {
+      {"x", ws->x}, {"dx", ws->dx}, {"r", ws->r}, {"p", ws->p}, {"Ap", ws->Ap}, {"z", ws->z}, {"npc_dir", ws->npc_dir},
+      {"v", ws->kind == S_MINRES ? (ws->vv ? ws->vv : ws->r2) : ws->v}, {"s", ws->s}, {"qd", ws->qd}, {"t", ws->t}, {"yz", ws->yz},
+      {"r1", ws->r1}, {"r2", ws->r2}, {"w1", ws->w1}, {"w2", ws->w2}, {"y", ws->y}, {"w", ws->w}, {"q", ws->q}};
+  for (auto& e : tab) if (!strcmp(e.n, nm)) return e.p;
+  if (nm[0] == 'V') { int i = atoi(nm + 1); if (i >= 1 && i <= (int)ws->V.size()) return ws->V[i - 1]; }
+  return nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------- part 1 -----------------------------------
+int krylov_workspace_create(KrylovSolverType solver, int m, int n, KrylovDataType dtype, KrylovDeviceType device,
+                            const KrylovWorkspaceOptions* wopts, void** ws_out) {
+  try {
+    if (!supported_solver((int)solver) || (dtype != KRYLOV_FLOAT32 && dtype != KRYLOV_FLOAT64)) return -2;
+    if (device != KRYLOV_CPU && device != KRYLOV_CUDA) return fail("krylov_workspace_create", "unknown device");
+    if (!ws_out) return fail("krylov_workspace_create", "ws_out is NULL");
+    if (m < 0 || n < 0) return fail("krylov_workspace_create", "negative dimension");
+    const int dev = pick_device();
+    const int memory = wopts ? wopts->memory : 0, window = wopts ? wopts->window : 0;   // 0 -> 20 / 5 (c_stores.jl:1799-1800)
+    Handle* h = new Handle();
+    h->solver = (int)solver; h->dtype = (int)dtype; h->device_kind = (int)device;
+    h->ext = krylov_b200_default_options();
+    try {
+      if (dtype == KRYLOV_FLOAT64) h->ws = ws_create<double>((SolverKind)solver, m, n, memory, window, dev);
+      else h->ws = ws_create<float>((SolverKind)solver, m, n, memory, window, dev);
+    } catch (...) { delete h; throw; }
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      g_handles[h] = h;
+    }
+    *ws_out = h;
+    return 0;
+  } catch (const std::exception& e) { return fail("krylov_workspace_create", e); }
+}
+
+KrylovWorkspaceOptions krylov_default_workspace_options(void) { KrylovWorkspaceOptions w = {0, 0}; return w; }
+
+KrylovOptions krylov_default_options(void) {
+  KrylovOptions o;
+  o.atol = NAN; o.rtol = NAN; o.itmax = 0; o.verbose = 0; o.lambda = 0.0; o.tau = NAN; o.nu = NAN;
+  o.timemax = NAN; o.radius = 0.0; o.restart = 0; o.reorthogonalization = 0; o.linesearch = 0;
+  return o;
+}
+
+void krylov_get_version(int* major, int* minor, int* patch) {
+  if (major) *major = KRYLOV_VERSION_MAJOR;
+  if (minor) *minor = KRYLOV_VERSION_MINOR;
+  if (patch) *patch = KRYLOV_VERSION_PATCH;
+}
+
+int krylov_solve(void* ws, KrylovMatvec matvec_A, KrylovMatvec matvec_At, KrylovMatvec matvec_M, KrylovMatvec matvec_N,
+                 const void* b, const void* c, void* userdata, const KrylovOptions* opts) {
+  (void)matvec_At;   // none of CG / MINRES / GMRES / BiCGSTAB uses the adjoint
+  try {
+    Handle* h = lookup(ws);
+    if (!h) return fail("krylov_solve", "unknown workspace handle");
+    return h->dtype == KRYLOV_FLOAT64 ? do_solve<double>(h, matvec_A, matvec_M, matvec_N, b, c, userdata, opts)
+                                      : do_solve<float>(h, matvec_A, matvec_M, matvec_N, b, c, userdata, opts);
+  } catch (const std::exception& e) { return fail("krylov_solve", e); }
+}
+
+int krylov_get_x(void* ws, void* x, int n) {
+  try {
+    Handle* h = lookup(ws);
+    if (!h) return fail("krylov_get_x", "unknown workspace handle");
+    return h->dtype == KRYLOV_FLOAT64 ? do_get_x<double>(h, x, n) : do_get_x<float>(h, x, n);
+  } catch (const std::exception& e) { return fail("krylov_get_x", e); }
+}
+
+int krylov_get_y(void* ws, void* y, int m) {
+  (void)y; (void)m;
+  Handle* h = lookup(ws);
+  if (!h) return fail("krylov_get_y", "unknown workspace handle");
+  return -2;   // solution_count == 1 for the four solvers (c_stores.jl:211-216)
+}
+
+int krylov_is_solved(void* ws) { Handle* h = lookup(ws); return h ? (stats_any(h).solved ? 1 : 0) : -1; }
+int krylov_niter(void* ws) { Handle* h = lookup(ws); return h ? stats_any(h).niter : -1; }
+double krylov_elapsed_time(void* ws) { Handle* h = lookup(ws); return h ? stats_any(h).timer : -1.0; }
+
+int krylov_warm_start(void* ws, const void* x0, int n) {
+  try {
+    Handle* h = lookup(ws);
+    if (!h) return fail("krylov_warm_start", "unknown workspace handle");
+    return h->dtype == KRYLOV_FLOAT64 ? do_warm_start<double>(h, x0, n) : do_warm_start<float>(h, x0, n);
+  } catch (const std::exception& e) { return fail("krylov_warm_start", e); }
+}
+
+int krylov_warm_start2(void* ws, const void* x0, const void* y0, int nx, int ny) {
+  (void)x0; (void)y0; (void)nx; (void)ny;
+  Handle* h = lookup(ws);
+  if (!h) return fail("krylov_warm_start2", "unknown workspace handle");
+  return -2;
+}
+
+int krylov_workspace_free(void* ws) {
+  Handle* h = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_handles.find(ws);
+    if (it == g_handles.end()) return 1;
+    h = it->second;
+    g_handles.erase(it);
+  }
+  try {
+    if (h->dtype == KRYLOV_FLOAT64) destroy_handle<double>(h); else destroy_handle<float>(h);
+  } catch (const std::exception& e) { fail("krylov_workspace_free", e); }
+  return 0;
+}
+
+// Block solvers: outside the path.
+int krylov_block_workspace_create(KrylovBlockSolverType, int, int, int, KrylovDataType, KrylovDeviceType,
+                                  const KrylovWorkspaceOptions*, void**) { return -2; }
+int krylov_block_solve(void*, KrylovBlockMatvec, KrylovBlockMatvec, KrylovBlockMatvec, const void*, void*, const KrylovOptions*) { return -1; }
+int krylov_block_get_X(void*, void*, int, int) { return -1; }
+int krylov_block_is_solved(void*) { return -1; }
+int krylov_block_niter(void*) { return -1; }
+double krylov_block_elapsed_time(void*) { return -1.0; }
+int krylov_block_warm_start(void*, const void*, int, int) { return -2; }
+int krylov_block_workspace_free(void*) { return 1; }
+
+// ------------------------------- part 2 -----------------------------------
+int krylov_b200_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return cnt;
+}
+int krylov_b200_set_device(int device) { g_device = device; return 0; }
+const char* krylov_b200_last_error(void) { return g_last_error.c_str(); }
+
+int krylov_b200_set_operator_csr(void* ws, int n, long long nnz, const void* rowptr, const void* colind, const void* values,
+                                 int index_base, int index_bytes, int location) {
+  try {
+    Handle* h = lookup(ws);
+    if (!h) return fail("krylov_b200_set_operator_csr", "unknown workspace handle");
+    auto a = std::make_shared<CsrAny>();
+    a->dtype = h->dtype;
+    if (h->dtype == KRYLOV_FLOAT64) {
+      Workspace<double>* w = W<double>(h);
+      KB_CUDA(cudaSetDevice(w->ctx.device));
+      if (n != w->n) throw std::runtime_error("(workspace.m, workspace.n) is inconsistent with size(A)");
+      csr_upload<double>(w->ctx, a->d, n, nnz, rowptr, colind, (const double*)values, index_base, index_bytes, location != 0);
+    } else {
+      Workspace<float>* w = W<float>(h);
+      KB_CUDA(cudaSetDevice(w->ctx.device));
+      if (n != w->n) throw std::runtime_error("(workspace.m, workspace.n) is inconsistent with size(A)");
+      csr_upload<float>(w->ctx, a->f, n, nnz, rowptr, colind, (const float*)values, index_base, index_bytes, location != 0);
+    }
+    h->csr = a;
+    return 0;
+  } catch (const std::exception& e) { return fail("krylov_b200_set_operator_csr", e); }
+}
+
+int krylov_b200_share_operator(void* ws, void* src) {
+  Handle* h = lookup(ws); Handle* s = lookup(src);
+  if (!h || !s) return fail("krylov_b200_share_operator", "unknown workspace handle");
+  if (!s->csr || s->dtype != h->dtype) return fail("krylov_b200_share_operator", "source has no CSR operator of this dtype");
+  h->csr = s->csr;
+  return 0;
+}
+
+int krylov_b200_set_preconditioner_diag(void* ws, int which, const void* d, int location) {
+  try {
+    Handle* h = lookup(ws);
+    if (!h) return fail("krylov_b200_set_preconditioner_diag", "unknown workspace handle");
+    void*& slot = which == 0 ? h->Mdiag : h->Ndiag;
+    if (!d) { dev_free(slot); slot = nullptr; return 0; }
+    const size_t esz = h->dtype == KRYLOV_FLOAT64 ? 8 : 4;
+    const int n = h->dtype == KRYLOV_FLOAT64 ? W<double>(h)->n : W<float>(h)->n;
+    const int dev = h->dtype == KRYLOV_FLOAT64 ? W<double>(h)->ctx.device : W<float>(h)->ctx.device;
+    KB_CUDA(cudaSetDevice(dev));
+    if (!slot) slot = dev_alloc<char>(esz * (size_t)n);
+    KB_CUDA(cudaMemcpy(slot, d, esz * (size_t)n, location ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    return 0;
+  } catch (const std::exception& e) { return fail("krylov_b200_set_preconditioner_diag", e); }
+}
+
+KrylovB200Options krylov_b200_default_options(void) {
+  KrylovB200Options o;
+  memset(&o, 0, sizeof(o));
+  o.etol = NAN; o.conlim = NAN; o.fused = 1;
+  return o;
+}
+
+int krylov_b200_set_options(void* ws, const KrylovB200Options* opts) {
+  Handle* h = lookup(ws);
+  if (!h) return fail("krylov_b200_set_options", "unknown workspace handle");
+  h->ext = opts ? *opts : krylov_b200_default_options();
+  return 0;
+}
+
+int krylov_b200_get_stats(void* ws, KrylovB200Stats* out) {
+  Handle* h = lookup(ws);
+  if (!h || !out) return fail("krylov_b200_get_stats", "unknown workspace handle");
+  const Stats& s = stats_any(h);
+  memset(out, 0, sizeof(*out));
+  out->niter = s.niter; out->solved = s.solved; out->inconsistent = s.inconsistent; out->indefinite = s.indefinite;
+  out->npcCount = s.npcCount; out->nresiduals = (int)s.residuals.size(); out->nAresiduals = (int)s.Aresiduals.size();
+  out->nAcond = (int)s.Acond.size(); out->allocation_timer = s.allocation_timer; out->timer = s.timer;
+  strncpy(out->status, s.status.c_str(), sizeof(out->status) - 1);
+  return 0;
+}
+
+int krylov_b200_get_history(void* ws, int which, double* out, int cap) {
+  Handle* h = lookup(ws);
+  if (!h) return fail("krylov_b200_get_history", "unknown workspace handle");
+  const Stats& s = stats_any(h);
+  const std::vector<double>& v = which == 0 ? s.residuals : which == 1 ? s.Aresiduals : s.Acond;
+  int k = (int)v.size() < cap ? (int)v.size() : cap;
+  for (int i = 0; i < k; i++) out[i] = v[i];
+  return k;
+}
+
+int krylov_b200_get_vector(void* ws, const char* name, void** dev_ptr) {
+  Handle* h = lookup(ws);
+  if (!h || !name || !dev_ptr) return fail("krylov_b200_get_vector", "bad arguments");
+  void* p = h->dtype == KRYLOV_FLOAT64 ? vec_by_name<double>(W<double>(h), name) : vec_by_name<float>(W<float>(h), name);
+  *dev_ptr = p;
+  return p ? 0 : -2;
+}
+
+long long krylov_b200_launch_count(void* ws) {
+  Handle* h = lookup(ws);
+  if (!h) return -1;
+  return h->dtype == KRYLOV_FLOAT64 ? W<double>(h)->ctx.launches : W<float>(h)->ctx.launches;
+}
+
+void* krylov_b200_stream(void* ws) {
+  Handle* h = lookup(ws);
+  if (!h) return nullptr;
+  return h->dtype == KRYLOV_FLOAT64 ? (void*)W<double>(h)->ctx.stream : (void*)W<float>(h)->ctx.stream;
+}
+
+// ------------------------------ flat primitives ---------------------------
+void* kb200_ctx_create(int device) {
+  try {
+    if (device < 0) device = pick_device();
+    Ctx* c = new Ctx();
+    c->init(device);
+    return c;
+  } catch (const std::exception& e) { fail("kb200_ctx_create", e); return nullptr; }
+}
+void kb200_ctx_destroy(void* ctx) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  c->destroy();
+  delete c;
+}
+int kb200_sync(void* ctx) {
+  try { ((Ctx*)ctx)->sync(); return 0; } catch (const std::exception& e) { return fail("kb200_sync", e); }
+}
+void* kb200_alloc(long long bytes) {
+  try { return dev_alloc<char>((size_t)bytes); } catch (const std::exception& e) { fail("kb200_alloc", e); return nullptr; }
+}
+int kb200_free(void* p) { dev_free(p); return 0; }
+int kb200_h2d(void* dst, const void* src, long long bytes) {
+  return cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : fail("kb200_h2d", "cudaMemcpy failed");
+}
+int kb200_d2h(void* dst, const void* src, long long bytes) {
+  return cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : fail("kb200_d2h", "cudaMemcpy failed");
+}
+
+#define FLAT(name, body_d, body_f)                                                        \
+  try {                                                                                   \
+    Ctx& c = *(Ctx*)ctx;                                                                  \
+    if (dtype == KRYLOV_FLOAT64) { typedef double T; (void)sizeof(T); body_d; }           \
+    else if (dtype == KRYLOV_FLOAT32) { typedef float T; (void)sizeof(T); body_f; }       \
+    else return -2;                                                                       \
+    return 0;                                                                             \
+  } catch (const std::exception& e) { return fail(name, e); }
+
+int kb200_dot(void* ctx, int dtype, int n, const void* x, const void* y, double* result) {
+  FLAT("kb200_dot", *result = k_dot<T>(c, n, (const T*)x, (const T*)y), *result = k_dot<T>(c, n, (const T*)x, (const T*)y))
+}
+int kb200_nrm2(void* ctx, int dtype, int n, const void* x, double* result) {
+  FLAT("kb200_nrm2", *result = k_nrm2<T>(c, n, (const T*)x), *result = k_nrm2<T>(c, n, (const T*)x))
+}
+int kb200_axpy(void* ctx, int dtype, int n, double s, const void* x, void* y) {
+  FLAT("kb200_axpy", k_axpy<T>(c, n, (T)s, (const T*)x, (T*)y), k_axpy<T>(c, n, (T)s, (const T*)x, (T*)y))
+}
+int kb200_axpby(void* ctx, int dtype, int n, double s, const void* x, double t, void* y) {
+  FLAT("kb200_axpby", k_axpby<T>(c, n, (T)s, (const T*)x, (T)t, (T*)y), k_axpby<T>(c, n, (T)s, (const T*)x, (T)t, (T*)y))
+}
+int kb200_scal(void* ctx, int dtype, int n, double s, void* x) {
+  FLAT("kb200_scal", k_scal<T>(c, n, (T)s, (T*)x), k_scal<T>(c, n, (T)s, (T*)x))
+}
+int kb200_copy(void* ctx, int dtype, int n, void* y, const void* x) {
+  FLAT("kb200_copy", k_copy<T>(c, n, (T*)y, (const T*)x), k_copy<T>(c, n, (T*)y, (const T*)x))
+}
+int kb200_scalcopy(void* ctx, int dtype, int n, void* y, double s, const void* x) {
+  FLAT("kb200_scalcopy", k_scalcopy<T>(c, n, (T*)y, (T)s, (const T*)x), k_scalcopy<T>(c, n, (T*)y, (T)s, (const T*)x))
+}
+int kb200_divcopy(void* ctx, int dtype, int n, void* y, const void* x, double s) {
+  FLAT("kb200_divcopy", k_divcopy<T>(c, n, (T*)y, (const T*)x, (T)s), k_divcopy<T>(c, n, (T*)y, (const T*)x, (T)s))
+}
+int kb200_fill(void* ctx, int dtype, int n, void* x, double v) {
+  FLAT("kb200_fill", k_fill<T>(c, n, (T*)x, (T)v), k_fill<T>(c, n, (T*)x, (T)v))
+}
+
+void* kb200_csr_create(void* ctx, int dtype, int n, long long nnz, const void* rowptr, const void* colind, const void* values,
+                       int index_base, int index_bytes, int location) {
+  try {
+    Ctx& c = *(Ctx*)ctx;
+    CsrAny* a = new CsrAny();
+    a->dtype = dtype; a->owner_ctx = &c;
+    try {
+      if (dtype == KRYLOV_FLOAT64) csr_upload<double>(c, a->d, n, nnz, rowptr, colind, (const double*)values, index_base, index_bytes, location != 0);
+      else if (dtype == KRYLOV_FLOAT32) csr_upload<float>(c, a->f, n, nnz, rowptr, colind, (const float*)values, index_base, index_bytes, location != 0);
+      else throw std::runtime_error("unsupported dtype");
+    } catch (...) { delete a; throw; }
+    return a;
+  } catch (const std::exception& e) { fail("kb200_csr_create", e); return nullptr; }
+}
+void kb200_csr_destroy(void* csr) { delete (CsrAny*)csr; }
+
+int kb200_spmv_csr(void* ctx, void* csr, const void* x, void* y, int variant) {
+  try {
+    Ctx& c = *(Ctx*)ctx;
+    CsrAny* a = (CsrAny*)csr;
+    if (a->dtype == KRYLOV_FLOAT64) k_spmv<double>(c, a->d, (const double*)x, (double*)y, variant);
+    else k_spmv<float>(c, a->f, (const float*)x, (float*)y, variant);
+    return 0;
+  } catch (const std::exception& e) { return fail("kb200_spmv_csr", e); }
+}
+
+int kb200_csr_plan(void* csr, long long* out) {
+  CsrAny* a = (CsrAny*)csr;
+  if (!a || !out) return -1;
+  if (a->dtype == KRYLOV_FLOAT64) {
+    const Csr<double>& A = a->d;
+    out[0] = A.ntiles; out[1] = A.tile_cap; out[2] = A.max_row; out[3] = A.tma_ok; out[4] = A.stages; out[5] = A.grid; out[6] = (long long)A.smem_bytes;
+  } else {
+    const Csr<float>& A = a->f;
+    out[0] = A.ntiles; out[1] = A.tile_cap; out[2] = A.max_row; out[3] = A.tma_ok; out[4] = A.stages; out[5] = A.grid; out[6] = (long long)A.smem_bytes;
+  }
+  return 0;
+}
+
+}  // extern "C"

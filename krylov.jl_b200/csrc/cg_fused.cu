@@ -1,0 +1,266 @@
+// cg_fused.cu -- the CG hot loop (src/cg.jl:195-268) as two launches per
+// iteration with every scalar recurrence on the device.
+//
+//   K1  p <- z + beta p   (cg.jl:259, applied on the fly while gathering)
+//       Ap <- A p         (cg.jl:196)
+//       pAp <- <p, Ap>    (cg.jl:197)   -> curvature test + alpha (cg.jl:198-213)
+//   K2  x += alpha p ; r -= alpha Ap    (cg.jl:239-240)
+//       gamma' <- <r, r>  (cg.jl:242)   -> rNorm, stop tests, beta, pNorm2 (cg.jl:244-258)
+//
+// The host only enqueues launches and polls a pinned copy of the scalar block
+// (one read-back per *batch* of iterations); kernels of iterations enqueued
+// past the stopping point see `done` and return immediately, so niter, x, r, p
+// at exit are those of the reference loop.  p is double-buffered because K1
+// reads the old direction of neighbouring rows while writing the new one.
+#include "kb_internal.h"
+#include "spmv_tiles.cuh"
+
+namespace kb {
+
+constexpr int kHist = 64;
+
+template <class T>
+struct CgState {
+  T gamma, pAp, alpha, beta, pNorm2, rNorm, eps_tol, pad0;
+  int iter, itmax, done, linesearch;
+  int solved, tired, zero_curvature, inconsistent;
+  int npc, not_spd, pad1, pad2;
+  T hist[kHist];
+};
+
+template <class T>
+__device__ __forceinline__ void cg_k1_finalize(CgState<T>* st, T pAp) {
+  st->pAp = pAp;
+  const T lim = mul_rn(Eps<T>::v, st->pNorm2);
+  if (pAp <= lim) {                       // radius == 0 on this path (cg.jl:198)
+    if (fabs(pAp) <= lim) { st->zero_curvature = 1; st->inconsistent = !st->linesearch; }
+    if (st->linesearch) { st->npc = 1; st->solved = 1; }
+    if (st->zero_curvature || st->solved) { st->done = 1; return; }
+  }
+  st->alpha = div_rn(st->gamma, pAp);      // cg.jl:213
+}
+
+template <class T>
+__device__ __forceinline__ void cg_k2_finalize(CgState<T>* st, T gamma_next) {
+  if (!(gamma_next >= T(0))) { st->not_spd = 1; st->done = 1; return; }   // cg.jl:243
+  const T rNorm = sqrt_rn(gamma_next);
+  st->rNorm = rNorm;
+  const int it1 = st->iter + 1;
+  st->hist[it1 % kHist] = rNorm;
+  const bool solved = (rNorm <= st->eps_tol) || (add_rn(rNorm, T(1)) <= T(1));   // cg.jl:249-253
+  if (!solved) {                                                                // cg.jl:255-258
+    const T beta = div_rn(gamma_next, st->gamma);
+    st->beta = beta;
+    st->pNorm2 = add_rn(gamma_next, mul_rn(mul_rn(beta, beta), st->pNorm2));
+    st->gamma = gamma_next;
+  }
+  st->iter = it1;
+  st->solved = solved;
+  st->tired = it1 >= st->itmax;
+  st->done = solved || st->tired;
+}
+
+// ---- K1, TMA-staged -------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(kTileThreads) cg_k1_tma(Csr<T> A, const T* __restrict__ r, const T* __restrict__ p_old,
+                                                          T* __restrict__ p_new, T* __restrict__ Ap, CgState<T>* st,
+                                                          T* part, unsigned* ticket) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ T sm[32];
+  if (*(volatile int*)&st->done) return;
+  const T beta = st->beta;
+  T dacc = T(0);
+  auto pval = [&](int j) { return add_rn(__ldg(&r[j]), mul_rn(beta, __ldg(&p_old[j]))); };
+  spmv_tiles_run<T>(A, smem, pval, [&](int row, T acc) {
+    const T pn = pval(row);
+    p_new[row] = pn;
+    Ap[row] = acc;
+    dacc += pn * acc;
+  });
+  T mine[1] = {block_sum(dacc, sm)}, tot[1];
+  if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) cg_k1_finalize(st, tot[0]);
+}
+
+// ---- K1, row-per-thread LDG (when the tile plan does not fit) --------------
+template <class T>
+__global__ void __launch_bounds__(kBlock) cg_k1_rows(Csr<T> A, const T* __restrict__ r, const T* __restrict__ p_old,
+                                                     T* __restrict__ p_new, T* __restrict__ Ap, CgState<T>* st, T* part,
+                                                     unsigned* ticket) {
+  __shared__ T sm[32];
+  if (*(volatile int*)&st->done) return;
+  const T beta = st->beta;
+  T dacc = T(0);
+  auto pval = [&](int j) { return add_rn(__ldg(&r[j]), mul_rn(beta, __ldg(&p_old[j]))); };
+  const int stride = gridDim.x * blockDim.x;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < A.n; row += stride) {
+    const int kb = A.rowptr[row], ke = A.rowptr[row + 1];
+    T acc = T(0);
+    for (int k = kb; k < ke; k++) acc = add_rn(acc, mul_rn(A.val[k], pval(A.colind[k])));
+    const T pn = pval(row);
+    p_new[row] = pn;
+    Ap[row] = acc;
+    dacc += pn * acc;
+  }
+  T mine[1] = {block_sum(dacc, sm)}, tot[1];
+  if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) cg_k1_finalize(st, tot[0]);
+}
+
+// ---- K2 -------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p,
+                                                const T* __restrict__ Ap, CgState<T>* st, T* part, unsigned* ticket) {
+  __shared__ T sm[32];
+  if (*(volatile int*)&st->done) return;
+  const T alpha = st->alpha, nalpha = -alpha;
+  T acc = T(0);
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    T xv[4], rv[4], pv[4], av[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int j = i + u * stride;
+      xv[u] = x[j]; rv[u] = r[j]; pv[u] = __ldg(&p[j]); av[u] = __ldg(&Ap[j]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int j = i + u * stride;
+      x[j] = add_rn(xv[u], mul_rn(alpha, pv[u]));
+      const T rn = add_rn(rv[u], mul_rn(nalpha, av[u]));
+      r[j] = rn;
+      acc += rn * rn;
+    }
+  }
+  for (; i < n; i += stride) {
+    x[i] = add_rn(x[i], mul_rn(alpha, p[i]));
+    const T rn = add_rn(r[i], mul_rn(nalpha, Ap[i]));
+    r[i] = rn;
+    acc += rn * rn;
+  }
+  T mine[1] = {block_sum(acc, sm)}, tot[1];
+  if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) cg_k2_finalize(st, tot[0]);
+}
+
+// ---------------------------------------------------------------------------
+template <class T> bool cg_fused_eligible(const LinOp<T>& A, const LinOp<T>& M, const SolveOpts& o) {
+  return o.fused && A.kind == LinOp<T>::CSR && M.is_identity() && o.radius == 0;
+}
+
+template <class T>
+void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamma0, T eps_tol, int itmax, double start_time,
+                   bool& solved, bool& tired, bool& zero_curvature, bool& inconsistent, bool& user_exit, bool& overtimed,
+                   int& iter) {
+  Ctx& c = ws.ctx;
+  const int n = ws.n;
+  typedef CgState<T> St;
+  if (!ws.fused_state) {
+    KB_CUDA(cudaMalloc(&ws.fused_state, sizeof(St)));
+    KB_CUDA(cudaHostAlloc(&ws.fused_host, 2 * sizeof(St), cudaHostAllocDefault));
+  }
+  if (!ws.p2) ws.p2 = dev_alloc<T>(n);
+  St* dst = (St*)ws.fused_state;
+  St* hst = (St*)ws.fused_host;
+
+  St init;
+  memset(&init, 0, sizeof(init));
+  init.gamma = gamma0; init.pNorm2 = gamma0; init.beta = T(0); init.eps_tol = eps_tol;
+  init.rNorm = sqrt(gamma0); init.itmax = itmax; init.linesearch = o.linesearch ? 1 : 0;
+  hst[0] = init;
+  KB_CUDA(cudaMemcpyAsync(dst, &hst[0], sizeof(St), cudaMemcpyHostToDevice, c.stream));
+  c.sync();   // hst[0] is reused below as a read-back slot
+
+  static bool attr_set = false;
+  if (A.tma_ok && !attr_set) {
+    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  const int g2 = stream_grid(n, 4, 8);
+  const int g1r = stream_grid(n, 1, 8);
+  T* P[2] = {ws.p, ws.p2};   // ws.p holds z (= r) from the prologue: with beta = 0, K1 forms p = r + 0*p
+  T* part = (T*)c.partials;
+
+  const bool single_step = (o.callback != nullptr) || (o.timemax < 1e300) || o.verbose > 0;
+  int batch = o.batch > 0 ? o.batch : 16;
+  if (batch > kHist / 2) batch = kHist / 2;
+  if (single_step) batch = 1;
+
+  cudaEvent_t ev[2];
+  KB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  KB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  int enq = 0;
+  auto enqueue = [&](int slot) {
+    for (int b = 0; b < batch; b++, enq++) {
+      T* p_old = P[enq & 1];
+      T* p_new = P[(enq + 1) & 1];
+      if (A.tma_ok)
+        cg_k1_tma<T><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2);
+      else
+        cg_k1_rows<T><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2);
+      cg_k2<T><<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3);
+      c.launches += 2;
+    }
+    KB_CUDA(cudaGetLastError());
+    KB_CUDA(cudaMemcpyAsync(&hst[slot], dst, sizeof(St), cudaMemcpyDeviceToHost, c.stream));
+    KB_CUDA(cudaEventRecord(ev[slot], c.stream));
+  };
+
+  int cur = 0, seen = 0;   // seen: iterations whose rNorm has been pushed to the history
+  St last;
+  enqueue(0);
+  for (;;) {
+    if (!single_step) enqueue(cur ^ 1);           // keep the GPU busy while the host inspects `cur`
+    KB_CUDA(cudaEventSynchronize(ev[cur]));
+    last = hst[cur];
+    for (int k = seen + 1; k <= last.iter; k++) {
+      if (o.history) ws.stats.residuals.push_back((double)last.hist[k % kHist]);
+    }
+    seen = last.iter;
+    if (last.done) break;
+    if (single_step) {
+      if (o.verbose > 0 && (last.iter % o.verbose == 0))
+        fprintf(stdout, "%5d  %7.1e  %8.1e  %8.1e\n", last.iter, (double)last.rNorm, (double)last.pAp, (double)last.alpha);
+      if (o.callback) {
+        // the callback may read ws.x / ws.r: the stream is idle here, data is current
+        ws.stats.niter = last.iter;
+        user_exit = o.callback(&ws, o.callback_user) != 0;
+      }
+      overtimed = (now_seconds() - start_time) > o.timemax;
+      if (user_exit || overtimed) break;
+      enqueue(cur);
+    } else {
+      cur ^= 1;
+    }
+  }
+  c.sync();   // drain speculative no-op launches
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  if (last.not_spd) throw std::runtime_error("The linear operator `A` or the preconditioner `M` is not symmetric positive definite.");
+
+  iter = last.iter;
+  solved = last.solved != 0;
+  tired = last.tired != 0;
+  zero_curvature = last.zero_curvature != 0;
+  inconsistent = last.inconsistent != 0;
+  // Which buffer holds the current direction?  K1 of iteration k writes P[(k+1)&1].
+  // Normal exit after K2 of iteration iter-1: p = P[iter & 1].  Exit from K1's
+  // curvature test at iteration `iter` (iter not incremented): p = P[(iter+1) & 1].
+  const bool k1_exit = zero_curvature || last.npc;
+  T* pcur = k1_exit ? P[(iter + 1) & 1] : P[iter & 1];
+  if (pcur != ws.p) { T* tmp = ws.p; ws.p = ws.p2; ws.p2 = tmp; }
+  if (last.npc) {                                   // linesearch branch, cg.jl:203-209
+    if (iter == 0) k_copy<T>(c, n, ws.x, ws.p);
+    k_copy<T>(c, n, ws.npc_dir, ws.p);
+    ws.stats.npcCount = 1;
+    ws.stats.indefinite = true;
+  }
+}
+
+#define INST(T)                                                                                              \
+  template bool cg_fused_eligible<T>(const LinOp<T>&, const LinOp<T>&, const SolveOpts&);                    \
+  template void cg_fused_loop<T>(Workspace<T>&, const Csr<T>&, const SolveOpts&, T, T, int, double, bool&, bool&, \
+                                 bool&, bool&, bool&, bool&, int&);
+INST(double)
+INST(float)
+#undef INST
+
+}  // namespace kb

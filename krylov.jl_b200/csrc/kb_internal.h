@@ -1,0 +1,192 @@
+// kb_internal.h -- internal C++ interfaces of libkrylov_b200.
+//
+// Layering (mirrors Krylov.jl's L1..L3):
+//   Ctx           one CUDA stream + reduction scratch + pinned scalar mailbox
+//   blas1.cu      k* primitives on device vectors   (src/krylov_utils.jl:309-349)
+//   spmv.cu       CSR operator: plain and TMA-staged SpMV (kmul!, krylov_utils.jl:305)
+//   cg_fused.cu   two-launch CG iteration               (src/cg.jl:195-268)
+//   solvers.cu    host control flow of cg!/gmres!/bicgstab!/minres! on the primitives
+//   capi.cu       the C ABI (include/krylov_b200.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace kb {
+
+// ---------------------------------------------------------------------------
+// Execution context: everything a solve needs besides its vectors.
+// ---------------------------------------------------------------------------
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  void* partials = nullptr;      // kMaxPartials * 4 doubles of reduction scratch
+  unsigned* tickets = nullptr;   // 8 tickets (zero-initialised, self re-arming)
+  void* dscal = nullptr;         // 16 device scalars (doubles) written by reductions
+  void* hscal = nullptr;         // pinned mirror of dscal
+  long long launches = 0;        // kernels launched through this context (bench: gpu_launches)
+
+  void init(int dev);
+  void destroy();
+  void sync() { KB_CUDA(cudaStreamSynchronize(stream)); }
+};
+
+template <class T> T* dev_alloc(size_t n);                // cudaMalloc, n elements (+ 64 B pad)
+void dev_free(void* p);
+
+// ---------------------------------------------------------------------------
+// BLAS-1 on device vectors.  Scalars that solvers consume on the host are
+// returned by value (one pinned read-back + stream sync), exactly like the
+// reference's kdot/knorm; the *_dev variants leave the result in ctx.dscal[slot].
+// ---------------------------------------------------------------------------
+template <class T> T    k_dot(Ctx& c, int n, const T* x, const T* y);
+template <class T> T    k_nrm2(Ctx& c, int n, const T* x);
+template <class T> void k_dot2(Ctx& c, int n, const T* a, const T* b, const T* u, const T* v, T* r1, T* r2);
+template <class T> void k_dot_dev(Ctx& c, int n, const T* x, const T* y, int slot);
+template <class T> void k_axpy(Ctx& c, int n, T s, const T* x, T* y);                 // y += s x
+template <class T> void k_axpby(Ctx& c, int n, T s, const T* x, T t, T* y);           // y = s x + t y
+template <class T> void k_scal(Ctx& c, int n, T s, T* x);                             // x *= s
+template <class T> void k_copy(Ctx& c, int n, T* y, const T* x);                      // y = x
+template <class T> void k_scalcopy(Ctx& c, int n, T* y, T s, const T* x);             // y = s x
+template <class T> void k_divcopy(Ctx& c, int n, T* y, const T* x, T s);              // y = x / s
+template <class T> void k_fill(Ctx& c, int n, T* x, T v);
+template <class T> void k_diagmul(Ctx& c, int n, T* y, const T* d, const T* x, bool ldiv);  // y = d.*x or x./d
+
+// ---------------------------------------------------------------------------
+// CSR operator resident in HBM (int32 indices, 0-based, columns ascending).
+// ---------------------------------------------------------------------------
+constexpr int kTileRows = 256;   // rows per TMA-staged tile (= consumer threads per CTA)
+
+template <class T>
+struct Csr {
+  int n = 0;
+  long long nnz = 0;
+  int* rowptr = nullptr;    // n+1 (+ pad)
+  int* colind = nullptr;    // nnz (+ pad)
+  T* val = nullptr;         // nnz (+ pad)
+  // TMA staging plan (filled by plan()):
+  int ntiles = 0;
+  int tile_cap = 0;         // max nnz of any kTileRows-row tile
+  int max_row = 0;          // longest row
+  bool tma_ok = false;      // tile fits the shared-memory stage budget
+  int stages = 0;           // pipeline depth chosen for tile_cap
+  size_t smem_bytes = 0;    // dynamic smem of the staged kernels
+  int grid = 0;             // persistent grid (multiple of the SM count)
+};
+
+template <class T> void csr_upload(Ctx& c, Csr<T>& A, int n, long long nnz, const void* rowptr, const void* colind,
+                                   const T* val, int index_base, int index_bytes, bool on_device);
+template <class T> void csr_free(Csr<T>& A);
+template <class T> void csr_plan(Ctx& c, Csr<T>& A);
+// y = A x.  variant: 0 auto (TMA-staged when the plan allows), 1 force row-per-thread LDG, 2 force TMA-staged
+template <class T> void k_spmv(Ctx& c, const Csr<T>& A, const T* x, T* y, int variant = 0);
+// y = A x and  <x, y>  in one launch (result in dscal[slot])
+template <class T> void k_spmv_dot_dev(Ctx& c, const Csr<T>& A, const T* x, T* y, int slot);
+
+// ---------------------------------------------------------------------------
+// Operators as the solvers see them (A, M, N of the reference's kwargs).
+// ---------------------------------------------------------------------------
+typedef void (*MatvecFn)(const void* x, void* y, void* userdata);
+
+template <class T>
+struct LinOp {
+  enum Kind { NONE, CSR, DIAG, HOST_CB, DEV_CB } kind = NONE;
+  const Csr<T>* csr = nullptr;
+  const T* diag = nullptr;       // DIAG: y = diag .* x (or x ./ diag with ldiv)
+  MatvecFn fn = nullptr;         // callbacks: host pointers (HOST_CB) or device pointers (DEV_CB)
+  void* userdata = nullptr;
+  T* hx = nullptr;               // pinned staging for HOST_CB
+  T* hy = nullptr;
+  int n = 0;
+  bool is_identity() const { return kind == NONE; }
+};
+template <class T> void op_apply(Ctx& c, const LinOp<T>& op, const T* x, T* y, bool ldiv = false);
+
+// ---------------------------------------------------------------------------
+// Solver options / statistics (kwargs of cg!/gmres!/bicgstab!/minres!;
+// SimpleStats, src/krylov_stats.jl:24-36).
+// ---------------------------------------------------------------------------
+struct SolveOpts {
+  double atol = -1, rtol = -1;      // <0 => sqrt(eps(T))
+  int itmax = 0;                    // 0 => 2n
+  double timemax = 1.0 / 0.0;
+  int verbose = 0;
+  bool history = false;
+  double radius = 0;                // CG
+  bool linesearch = false;          // CG, MINRES
+  double lambda = 0;                // MINRES
+  double etol = -1, conlim = -1;    // MINRES (<0 => defaults)
+  bool restart = false;             // GMRES
+  bool reorthogonalization = false; // GMRES
+  bool ldiv = false;
+  int (*callback)(void* ws, void* user) = nullptr;   // returns nonzero => user-requested exit
+  void* callback_user = nullptr;
+  int fused = 1;                    // 0 => force the generic primitive path
+  int batch = 0;                    // fused CG: iterations enqueued per host poll (0 => default)
+};
+
+struct Stats {
+  int niter = 0;
+  bool solved = false, inconsistent = false, indefinite = false;
+  int npcCount = 0;
+  std::vector<double> residuals, Aresiduals, Acond;
+  double allocation_timer = 0, timer = 0;
+  std::string status = "unknown";
+  void reset() { residuals.clear(); Aresiduals.clear(); Acond.clear(); indefinite = false; npcCount = 0; }
+};
+
+enum SolverKind { S_CG = 0, S_MINRES = 3, S_GMRES = 8, S_BICGSTAB = 10 };
+
+// One workspace per (solver, dtype): owns every device vector of the solver
+// (src/krylov_workspaces.jl; SURVEY.md appendix B for fields and aliasing).
+template <class T>
+struct Workspace {
+  SolverKind kind;
+  int m = 0, n = 0;
+  Ctx ctx;
+  Stats stats;
+  bool warm_start = false;
+  // device vectors (nullptr == Julia's length-0 vector)
+  T *x = nullptr, *dx = nullptr;
+  T *r = nullptr, *p = nullptr, *Ap = nullptr, *z = nullptr, *npc_dir = nullptr;      // CG
+  T *p2 = nullptr;                                                                   // CG fused: second p buffer
+  T *v = nullptr, *s = nullptr, *qd = nullptr, *t = nullptr, *yz = nullptr;           // BiCGSTAB (+ r, p)
+  T *r1 = nullptr, *r2 = nullptr, *w1 = nullptr, *w2 = nullptr, *y = nullptr, *vv = nullptr;  // MINRES
+  T *w = nullptr, *q = nullptr, *pp = nullptr;                                        // GMRES (+ V)
+  std::vector<T*> V;
+  std::vector<T> c, sgiv, zg, R;       // GMRES host-side Givens data
+  std::vector<T> err_vec;              // MINRES window
+  int memory = 20, window = 5;
+  int inner_iter = 0;
+  void* fused_state = nullptr;         // device scalar block of the fused paths
+  void* fused_host = nullptr;          // pinned mirror (2 slots)
+  T* bbuf = nullptr;                   // device copies of host b / c for the C ABI
+  T* cbuf = nullptr;
+};
+
+template <class T> Workspace<T>* ws_create(SolverKind kind, int m, int n, int memory, int window, int device);
+template <class T> void ws_destroy(Workspace<T>* ws);
+template <class T> void ws_warm_start(Workspace<T>* ws, const T* x0_dev);
+
+// Solver drivers (device pointers for b, c).  Throw std::runtime_error where
+// the reference calls error(...).
+template <class T> void cg_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const SolveOpts& o);
+template <class T> void gmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const LinOp<T>& N, const SolveOpts& o);
+template <class T> void bicgstab_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c, const LinOp<T>& M, const LinOp<T>& N, const SolveOpts& o);
+template <class T> void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const SolveOpts& o);
+
+// Fused CG (cg_fused.cu).  Returns false if the configuration is not eligible
+// (caller falls back to the generic primitive path, still on the GPU).
+template <class T> bool cg_fused_eligible(const LinOp<T>& A, const LinOp<T>& M, const SolveOpts& o);
+template <class T> void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamma0, T eps_tol, int itmax,
+                                      double start_time, bool& solved, bool& tired, bool& zero_curvature,
+                                      bool& inconsistent, bool& user_exit, bool& overtimed, int& iter);
+
+double now_seconds();
+
+}  // namespace kb

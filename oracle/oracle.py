@@ -171,6 +171,21 @@ def minres(A, b, x0=None, M=None, dtype=np.float64, **kw):
     return _result(st, x, res, dict(Aresiduals=ares[:k].copy(), Acond=acond[:k].copy(), npc_dir=npc))
 
 
+def cg_timed(rowptr, colind, val, b, iters, threads=1):
+    """Fixed-iteration CG loop on the host (bench.py CPU legs).  Returns (seconds, x, rNorm)."""
+    L = lib()
+    L.oracle_cg_timed_f64.restype = C.c_double
+    n = len(rowptr) - 1
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    colind = np.ascontiguousarray(colind, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros(n)
+    rn = C.c_double()
+    t = L.oracle_cg_timed_f64(n, _p(rowptr), _p(colind), _p(val), _p(b), int(iters), int(threads), _p(x), C.byref(rn))
+    return float(t), x, rn.value
+
+
 def spmv(A, x, dtype=np.float64):
     suf, _ = _suf(dtype)
     n, rp, ci, va = _csr(A, dtype)
@@ -235,9 +250,9 @@ def ddx(n):
 
 def get_div_grad(n1, n2, n3):
     """Div * Div'  (test/get_div_grad.jl:8-19) -- literal Kronecker construction."""
-    D1 = sp.kron(eye(n3), sp.kron(eye(n2), ddx(n1)))
-    D2 = sp.kron(eye(n3), sp.kron(ddx(n2), eye(n1)))
-    D3 = sp.kron(ddx(n3), sp.kron(eye(n2), eye(n1)))
+    D1 = sp.kron(eye(n3), sp.kron(eye(n2), ddx(n1), format="csc"), format="csc")
+    D2 = sp.kron(eye(n3), sp.kron(ddx(n2), eye(n1), format="csc"), format="csc")
+    D3 = sp.kron(ddx(n3), sp.kron(eye(n2), eye(n1), format="csc"), format="csc")
     Div = sp.hstack([D1, D2, D3], format="csc")
     A = sp.csr_matrix(Div @ Div.T)
     A.sort_indices()
@@ -266,9 +281,9 @@ def kron_unsymmetric(n=64):
     """test/test_utils.jl:160-169"""
     T = sp.diags([-np.ones(n - 1), 3.0 * np.ones(n), -2.0 * np.ones(n - 1)], [-1, 0, 1], format="csr")
     Id = sp.identity(n, format="csr")
-    A = sp.kron(T, Id) + sp.kron(Id, T)
+    A = sp.kron(T, Id, format="csr") + sp.kron(Id, T, format="csr")
     Id2 = Id  # the reference re-uses the same n x n identity in the second step
-    A = sp.kron(A, Id2) + sp.kron(Id2, A)
+    A = sp.kron(A, Id2, format="csr") + sp.kron(Id2, A, format="csr")
     A = sp.csr_matrix(A)
     A.sort_indices()
     return A, A @ np.ones(A.shape[0])

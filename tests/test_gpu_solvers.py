@@ -1,0 +1,206 @@
+"""GPU parity tests proper: cg!/gmres!/bicgstab!/minres! through the C ABI vs the CPU oracle.
+
+Bar (BASELINE.json north_star): identical iteration count and residual norms within 1e-6 relative
+for Float64.  Float32 histories are held to 5e-3 and the iteration count to +-1 (the oracle's
+sequential fp32 dots and the GPU's tree reductions differ by ~sqrt(n)*eps32)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import cases
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_histories.json")))
+F64_TOL = 1e-6
+
+
+def run_gpu(kb, name, **extra):
+    solver, A, b, kw, dt = cases.build(name)
+    kw = dict(kw)
+    mem = kw.pop("memory", 0)
+    ws = kb.krylov_workspace(solver, A.shape[0], A.shape[1], dt, memory=mem)
+    ws.solve(A, b.astype(dt), history=True, **kw, **extra)
+    x, st = ws.x, ws.stats
+    launches = ws.launches
+    ws.free()
+    return x, st, launches
+
+
+def check_against(st, x, g_res, g_niter, g_status, dt, xo=None):
+    res = np.asarray(st.residuals)
+    if dt == np.float64:
+        assert st.niter == g_niter, (st.niter, g_niter)
+        assert len(res) == len(g_res)
+        rel = np.abs(res - g_res) / np.maximum(np.abs(g_res), 1e-300)
+        assert rel.max() <= F64_TOL, f"max rel residual-history deviation {rel.max():.3e}"
+        assert st.status == g_status
+        if xo is not None:
+            assert np.linalg.norm(x - xo) <= 1e-6 * np.linalg.norm(xo)
+    else:
+        assert abs(st.niter - g_niter) <= 1
+        k = min(len(res), len(g_res)) - 2
+        assert np.allclose(res[:k], g_res[:k], rtol=5e-3)
+
+
+@pytest.mark.parametrize("name", cases.NAMES)
+def test_parity_with_golden_and_oracle(kb, O, name):
+    solver, A, b, kw, dt = cases.build(name)
+    x, st, launches = run_gpu(kb, name)
+    g = GOLD[name]
+    xo, so = cases.run_oracle(O, name)
+    check_against(st, x, np.asarray(g["residuals"]), g["niter"], g["status"], dt, xo if dt == np.float64 else None)
+    check_against(st, x, np.asarray(so["residuals"]), so["niter"], so["status"], dt)
+    assert st.solved == so["solved"] and st.inconsistent == so["inconsistent"]
+    assert launches > 0
+
+
+@pytest.mark.parametrize("name", ["cg_divgrad16_default", "cg_divgrad32_bench", "cg_ragged_7x5x3"])
+def test_fused_cg_equals_primitive_path(kb, name):
+    """The two-launch fused loop and the unfused primitive loop run the same arithmetic."""
+    x1, s1, l1 = run_gpu(kb, name, fused=True)
+    x0, s0, l0 = run_gpu(kb, name, fused=False)
+    assert s1.niter == s0.niter and s1.status == s0.status
+    assert np.allclose(s1.residuals, s0.residuals, rtol=1e-9)
+    assert np.linalg.norm(x1 - x0) <= 1e-9 * np.linalg.norm(x0)
+    # 2 launches per iteration (+ prologue) vs >= 6 for the primitive path
+    assert l1 < l0
+    for batch in (1, 3, 32):
+        xb, sb, _ = run_gpu(kb, name, fused=True, batch=batch)
+        assert sb.niter == s1.niter and np.array_equal(xb, x1) and sb.residuals == s1.residuals
+
+
+def test_cg_statuses_and_flags(kb, O):
+    """test/test_cg.jl:37-96,136-170 through the product path."""
+    A, b = O.zero_rhs()
+    x, st = kb.cg(A, b)
+    assert np.linalg.norm(x) == 0 and st.status == "x is a zero-residual solution" and st.niter == 0
+    A, b = O.symmetric_indefinite(shift=10)
+    for fused in (True, False):
+        ws = kb.CgWorkspace(A, b)
+        kb.cg_(ws, A, b, linesearch=True, fused=fused)
+        st = ws.stats
+        assert st.status == "nonpositive curvature" and not st.inconsistent and st.niter == 0
+        assert st.indefinite and st.npcCount == 1
+        npc = ws.npc_dir
+        assert npc @ (A @ npc) <= 0 and np.array_equal(npc, b)
+        # stats reset on reuse (test_cg.jl:136-170)
+        A2 = sp.csr_matrix(np.diag([10.0, 8.0, 5.0, 1.0, 2, 3, 4, 5, 6, 7]))
+        kb.cg_(ws, A2, np.ones(10), linesearch=True, fused=fused)
+        st = ws.stats
+        assert st.npcCount == 0 and not st.indefinite and st.solved
+        ws.free()
+    A4 = sp.csr_matrix(np.diag([10.0, 8.0, 5.0, -1.0]))
+    b4 = np.array([1.0, 1.0, 1.0, 0.1])
+    ws = kb.CgWorkspace(A4, b4)
+    kb.cg_(ws, A4, b4, radius=10.0)
+    st = ws.stats
+    assert st.npcCount == 1 and st.status == "nonpositive curvature" and st.indefinite
+    npc = ws.npc_dir
+    assert npc @ (A4 @ npc) <= 0.01
+    ws.free()
+    with pytest.raises(kb.B200Error):
+        kb.cg(A4, b4, radius=1.0, linesearch=True)
+    A, b = O.square_inconsistent()
+    x, st = kb.cg(A, b)
+    assert st.inconsistent and st.status == "zero curvature detected"
+    x, st = kb.cg(*O.sparse_laplacian(8), itmax=3)
+    assert st.status == "maximum number of iterations exceeded" and st.niter == 3 and not st.solved
+
+
+def test_cg_radius_preconditioner_warmstart(kb, O):
+    tol = 1e-6
+    A, b = O.symmetric_definite()
+    x, st = kb.cg(A, b, itmax=10)
+    radius = 0.75 * np.linalg.norm(x)
+    x, st = kb.cg(A, b, radius=radius, itmax=10)
+    xo, so = O.cg(A, b, radius=radius, itmax=10)
+    assert st.solved and abs(radius - np.linalg.norm(x)) <= tol * radius and st.status == "on trust-region boundary"
+    assert st.niter == so["niter"] and np.allclose(x, xo, rtol=1e-9)
+    A, b, M = O.square_preconditioned()
+    x, st = kb.cg(A, b, M=M, history=True)
+    xo, so = O.cg(A, b, M=M)
+    assert st.niter == so["niter"] and np.allclose(st.residuals, so["residuals"], rtol=1e-6, atol=1e-300)
+    A, b = O.sparse_laplacian(10)
+    x, st = kb.cg(A, b)
+    x0 = x + 1e-3 * np.sin(np.arange(len(x)))
+    xw, sw = kb.cg(A, b, x0, history=True)
+    xo, so = O.cg(A, b, x0=x0)
+    assert sw.niter == so["niter"] < st.niter and np.allclose(sw.residuals, so["residuals"], rtol=1e-6)
+    assert np.allclose(xw, xo, rtol=1e-9)
+
+
+def test_callback_and_timemax(kb, O):
+    A, b = O.sparse_laplacian(10)
+    seen = []
+    ws = kb.CgWorkspace(A, b)
+    kb.cg_(ws, A, b, callback=lambda w: (seen.append(1), len(seen) >= 5)[1])
+    assert ws.stats.status == "user-requested exit" and ws.stats.niter == 5
+    with pytest.raises(TypeError):                                # test_cg.jl:130
+        kb.cg_(ws, A, b, callback=lambda w: "string")
+    kb.cg_(ws, A, b, timemax=0.0)
+    assert ws.stats.status == "time limit exceeded"
+    ws.free()
+    for name, f in (("gmres", kb.gmres), ("bicgstab", kb.bicgstab), ("minres", kb.minres)):
+        cnt = []
+        x, st = f(A, b, callback=lambda w: (cnt.append(1), len(cnt) >= 3)[1])
+        assert st.status == "user-requested exit" and st.niter == 3, name
+
+
+def test_other_solver_options_match_oracle(kb, O):
+    A, b = O.sparse_laplacian(8)
+    d = 1.0 / A.diagonal()
+    for kw in (dict(M=d), dict(N=d), dict(M=d, N=1.0 / np.sqrt(A.diagonal()))):
+        for restart in (False, True):
+            x, st = kb.gmres(A, b, memory=10, restart=restart, history=True, **kw)
+            xo, so = O.gmres(A, b, memory=10, restart=restart, **kw)
+            assert st.niter == so["niter"] and np.allclose(st.residuals, so["residuals"], rtol=1e-6)
+            assert np.allclose(x, xo, rtol=1e-7, atol=1e-10)
+    for kw in (dict(M=d), dict(N=d)):
+        x, st = kb.bicgstab(A, b, history=True, **kw)
+        xo, so = O.bicgstab(A, b, **kw)
+        assert st.niter == so["niter"] and np.allclose(st.residuals, so["residuals"], rtol=1e-5)
+    x, st = kb.minres(A, b, M=d, history=True)
+    xo, so = O.minres(A, b, M=d)
+    assert st.niter == so["niter"] and np.allclose(st.residuals, so["residuals"], rtol=1e-6)
+    assert np.allclose(st.Aresiduals, so["Aresiduals"], rtol=1e-5, atol=1e-12) and np.allclose(st.Acond, so["Acond"], rtol=1e-6)
+    A2 = sp.csr_matrix(np.array([[1.0, 2.0], [3.0, 4.0]]))
+    x, st = kb.bicgstab(A2, np.array([0.0, 1.0]), c=np.array([1.0, 0.0]))
+    assert st.status == "Breakdown bᴴc = 0" and not st.solved
+    A, b = O.zero_rhs()
+    x, st = kb.minres(A, b)
+    assert st.niter == 1 and st.status == "x is a zero-residual solution"
+    A, b = O.symmetric_indefinite(shift=5)
+    x, st = kb.minres(A, b, linesearch=True)
+    xo, so = O.minres(A, b, linesearch=True)
+    assert st.status == so["status"] == "nonpositive curvature" and st.npcCount == so["npcCount"] and st.niter == so["niter"]
+
+
+def test_matrix_free_host_operator(kb, O):
+    """A Python callable stands in for the reference's C callback operator (c_operator.jl:35-42)."""
+    A, b = O.sparse_laplacian(8)
+    x, st = kb.cg(lambda v: A @ v, b, history=True)
+    xo, so = O.cg(A, b)
+    assert st.niter == so["niter"] and np.allclose(st.residuals, so["residuals"], rtol=1e-6)
+
+
+def test_property_at_scale_cg_poisson(kb):
+    """Benchmark-shaped size (N=128, n=2.1M): size-independent checks -- true residual matches the
+    recurrence residual, monotone A-norm error is implied by pAp>0, solution symmetric under axis swaps."""
+    from krylov_b200 import problems as P
+    N = 128
+    rp, ci, va = P.div_grad_csr(N)
+    n = N ** 3
+    b = np.ones(n)
+    ws = kb.CgWorkspace(n, n, np.float64)
+    ws.solve((rp, ci, va), b, atol=0.0, rtol=1e-8, history=True)
+    st, x = ws.stats, ws.x
+    A = sp.csr_matrix((va, ci, rp), shape=(n, n))
+    true_res = np.linalg.norm(b - A @ x)
+    assert st.solved and abs(true_res - st.residuals[-1]) <= 1e-6 * st.residuals[0]
+    X = x.reshape(N, N, N)
+    assert np.allclose(X, X.transpose(2, 1, 0), rtol=1e-9) and np.allclose(X, X[::-1, :, :], rtol=1e-9)
+    assert 300 <= st.niter <= 330       # ~2.45 N
+    ws.free()

@@ -1,0 +1,225 @@
+"""Pins the CPU oracle against the reference's own known-answer tests.
+
+Every case cites the reference test it restates (paths relative to Krylov.jl v0.10.8).
+"""
+import math
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+
+def resid(A, x, b):
+    return np.linalg.norm(b - A @ x) / np.linalg.norm(b)
+
+
+# ---- test/test_aux.jl:5-21 -------------------------------------------------
+def test_sym_givens_corner_cases(O):
+    assert O.sym_givens(0.0, 0.0) == (1.0, 0.0, 0.0)
+    a = 3.14
+    assert O.sym_givens(a, 0.0) == (1.0, 0.0, a)
+    assert O.sym_givens(-a, 0.0) == (-1.0, 0.0, a)
+    assert O.sym_givens(0.0, a) == (0.0, 1.0, a)
+    assert O.sym_givens(0.0, -a) == (0.0, -1.0, a)
+    c, s, r = O.sym_givens(3.0, 4.0)
+    assert abs(c * 3.0 + s * 4.0 - r) < 1e-15 and abs(s * 3.0 - c * 4.0) < 1e-15
+
+
+# ---- test/test_aux.jl:38-77 ------------------------------------------------
+def test_roots_quadratic(O):
+    assert O.roots_quadratic(0.0, 0.0, 0.0) == (0.0, 0.0)
+    with pytest.raises(ArithmeticError):
+        O.roots_quadratic(0.0, 0.0, 1.0)
+    assert O.roots_quadratic(0.0, 3.14, -1.0) == (1.0 / 3.14, 1.0 / 3.14)
+    with pytest.raises(ArithmeticError):
+        O.roots_quadratic(1.0, 0.0, 1.0)
+    assert O.roots_quadratic(1.0, 0.0, 0.0) == (0.0, 0.0)
+    r = O.roots_quadratic(1.0, 3.0, 2.0)
+    assert r[0] == pytest.approx(-2.0) and r[1] == pytest.approx(-1.0)
+    with pytest.raises(ArithmeticError):
+        O.roots_quadratic(1.0e8, 1.0, 1.0)
+    assert O.roots_quadratic(-1.0e-8, 1.0e5, 1.0, nitref=0) == (1.0e13, 0.0)
+    assert O.roots_quadratic(-1.0e-8, 1.0e5, 1.0, nitref=1) == (1.0e13, -1.0e-05)
+    for nitref in (0, 1):
+        r = O.roots_quadratic(-1.0e-7, 1.0, 1.0, nitref=nitref)
+        assert r[0] == pytest.approx(1.0e7, rel=1e-6) and r[1] == pytest.approx(-1.0, rel=1e-6)
+
+
+# ---- test/test_aux.jl:103-117 ----------------------------------------------
+def test_to_boundary(O):
+    n = 5
+    x = np.ones(n)
+    d = np.ones(n)
+    d[0::2] = -1
+    for bad in (-1.0, 0.5):
+        with pytest.raises(ArithmeticError):
+            O.to_boundary(x, d, bad)
+    with pytest.raises(ArithmeticError):
+        O.to_boundary(x, np.zeros(n), 1.0)
+    assert max(O.to_boundary(x, d, 5.0)) == pytest.approx(2.209975124224178)
+    assert min(O.to_boundary(x, d, 5.0)) == pytest.approx(-1.8099751242241782)
+    assert max(O.to_boundary(x, d, 5.0, flip=True)) == pytest.approx(1.8099751242241782)
+    assert min(O.to_boundary(x, d, 5.0, flip=True)) == pytest.approx(-2.209975124224178)
+
+
+# ---- interfaces/examples/C/basic_cg.c:13-15 ---------------------------------
+def test_basic_cg_example(O):
+    A = sp.diags([-np.ones(4), 2 * np.ones(5), -np.ones(4)], [-1, 0, 1], format="csr")
+    x, st = O.cg(A, np.array([1.0, 0, 0, 0, 1.0]))
+    assert st["solved"] and st["niter"] == 3
+    assert np.allclose(x, 1.0, atol=1e-12)
+
+
+# ---- test/test_cg.jl ---------------------------------------------------------
+def test_cg_reference_cases(O):
+    tol = 1e-6
+    A, b = O.symmetric_definite()                                    # :8-13
+    x, st = O.cg(A, b, itmax=10)
+    assert resid(A, x, b) <= tol and st["solved"]
+    radius = 0.75 * np.linalg.norm(x)                                 # :15-20
+    x, st = O.cg(A, b, radius=radius, itmax=10)
+    assert st["solved"] and abs(radius - np.linalg.norm(x)) <= tol * radius
+    assert st["status"] == "on trust-region boundary"
+    A, b = O.sparse_laplacian()                                       # :22-28
+    x, st = O.cg(A, b)
+    assert resid(A, x, b) <= tol and st["solved"]
+    radius = 0.75 * np.linalg.norm(x)                                 # :30-35
+    x, st = O.cg(A, b, radius=radius, itmax=10)
+    assert st["solved"] and abs(radius - np.linalg.norm(x)) <= tol * radius
+    A, b = O.zero_rhs()                                               # :37-41
+    x, st = O.cg(A, b)
+    assert np.linalg.norm(x) == 0 and st["status"] == "x is a zero-residual solution"
+    A, b, M = O.square_preconditioned()                               # :43-49
+    x, st = O.cg(A, b, M=M)
+    r = b - A @ x
+    assert math.sqrt(r @ (M * r)) / math.sqrt(b @ (M * b)) <= tol and st["solved"]
+    A, b = O.symmetric_indefinite(shift=10)                           # :51-62
+    x, st = O.cg(A, b, linesearch=True)
+    assert st["status"] == "nonpositive curvature" and not st["inconsistent"] and st["niter"] == 0
+    assert st["indefinite"] and st["npcCount"] == 1
+    assert st["npc_dir"] @ (A @ st["npc_dir"]) <= 0 and np.all(st["npc_dir"] == b)
+    A, b = O.zero_rhs()                                               # :64-71, :73-80
+    for kw in (dict(linesearch=True), dict(radius=10.0)):
+        x, st = O.cg(A, b, **kw)
+        assert st["status"] == "x is a zero-residual solution" and np.linalg.norm(x) == 0 and st["niter"] == 0
+    A4 = sp.csr_matrix(np.diag([10.0, 8.0, 5.0, -1.0]))               # :82-96
+    b4 = np.array([1.0, 1.0, 1.0, 0.1])
+    x, st = O.cg(A4, b4, radius=10.0)
+    assert st["npcCount"] == 1 and st["status"] == "nonpositive curvature" and st["indefinite"]
+    assert st["npc_dir"] @ (A4 @ st["npc_dir"]) <= 0.01
+    A, b = O.singular_consistent()                                    # :98-103
+    x, st = O.cg(A, b)
+    assert resid(A, x, b) <= tol and not st["inconsistent"]
+    A, b = O.square_inconsistent()                                    # :105-109
+    x, st = O.cg(A, b)
+    assert st["inconsistent"]
+    A, b = O.cartesian_poisson()                                      # :111-117 (negative definite: alpha < 0 throughout, same iterates)
+    x, st = O.cg(A, b)
+    assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.symmetric_indefinite(shift=5)                            # :132-134
+    x, st = O.cg(A, b, radius=1.0, linesearch=True)
+    assert st["error"] == 1
+    x, st = O.cg(A4, b4, linesearch=True)                             # :136-170
+    assert st["npcCount"] == 1 and st["indefinite"] and st["status"] == "nonpositive curvature"
+    x, st = O.cg(sp.csr_matrix(np.diag([10.0, 8.0, 5.0, 1.0])), np.ones(4), linesearch=True)
+    assert st["npcCount"] == 0 and not st["indefinite"] and st["solved"]
+
+
+# ---- test/test_gmres.jl (thresholds 1e-6; restart :93-129) -------------------
+def test_gmres_reference_cases(O):
+    tol = 1e-6
+    A, b = O.symmetric_definite()
+    x, st = O.gmres(A, b)
+    assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.symmetric_indefinite()
+    x, st = O.gmres(A, b)
+    assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.sparse_laplacian()
+    d = A.diagonal()
+    for restart in (False, True):
+        x, st = O.gmres(A, b, restart=restart, memory=10)
+        assert resid(A, x, b) <= tol and st["niter"] > 10 and st["solved"]
+        M = 1.0 / d
+        x, st = O.gmres(A, b, M=M, restart=restart, memory=10)
+        r = b - A @ x
+        assert np.linalg.norm(M * r) / np.linalg.norm(M * b) <= tol and st["niter"] > 10 and st["solved"]
+        x, st = O.gmres(A, b, N=M, restart=restart, memory=10)
+        assert resid(A, x, b) <= tol and st["niter"] > 10 and st["solved"]
+        Ns = 1.0 / np.sqrt(d)
+        x, st = O.gmres(A, b, M=M, N=Ns, restart=restart, memory=10)
+        r = b - A @ x
+        assert np.linalg.norm(M * r) / np.linalg.norm(M * b) <= tol and st["niter"] > 10 and st["solved"]
+    A, b = O.zero_rhs()
+    x, st = O.gmres(A, b)
+    assert np.linalg.norm(x) == 0 and st["status"] == "x is a zero-residual solution"
+    A, b = O.kron_unsymmetric(8)
+    x, st = O.gmres(A, b)
+    assert resid(A, x, b) <= tol and st["solved"]
+
+
+# ---- test/test_bicgstab.jl ----------------------------------------------------
+def test_bicgstab_reference_cases(O):
+    tol = 1e-6
+    for gen in (O.symmetric_definite, O.sparse_laplacian):
+        A, b = gen()
+        x, st = O.bicgstab(A, b)
+        assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.kron_unsymmetric(8)
+    x, st = O.bicgstab(A, b)
+    assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.zero_rhs()
+    x, st = O.bicgstab(A, b)
+    assert np.linalg.norm(x) == 0 and st["status"] == "x is a zero-residual solution"
+    A = sp.csr_matrix(np.array([[1.0, 2.0], [3.0, 4.0]]))             # bc_breakdown, test_bicgstab.jl:85-88
+    x, st = O.bicgstab(A, np.array([0.0, 1.0]), c=np.array([1.0, 0.0]))
+    assert st["status"] == "Breakdown bᴴc = 0" and not st["solved"] and st["niter"] == 0
+    A, b = O.sparse_laplacian()
+    M = 1.0 / A.diagonal()
+    x, st = O.bicgstab(A, b, M=M)
+    assert resid(A, x, b) <= tol and st["solved"]
+    x, st = O.bicgstab(A, b, N=M)
+    assert resid(A, x, b) <= tol and st["solved"]
+
+
+# ---- test/test_minres.jl -------------------------------------------------------
+def test_minres_reference_cases(O):
+    tol = 1e-5
+    A, b = O.symmetric_definite()
+    x, st = O.minres(A, b)
+    assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.symmetric_indefinite()
+    x, st = O.minres(A, b)
+    assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.sparse_laplacian()
+    x, st = O.minres(A, b)
+    assert resid(A, x, b) <= tol and st["solved"]
+    lam = 0.5                                                          # shifted system
+    x, st = O.minres(A, b, lambda_=lam, atol=1e-10, rtol=1e-10)
+    assert np.linalg.norm(b - (A @ x + lam * x)) / np.linalg.norm(b) <= tol
+    A, b = O.zero_rhs()                                                # test_minres.jl:45-52: niter == 1 quirk
+    x, st = O.minres(A, b)
+    assert np.linalg.norm(x) == 0 and st["status"] == "x is a zero-residual solution" and st["niter"] == 1
+    A, b = O.symmetric_indefinite(shift=5)                             # linesearch: npc at first iteration
+    x, st = O.minres(A, b, linesearch=True)
+    assert st["status"] == "nonpositive curvature" and st["indefinite"] and st["npcCount"] >= 1
+    A, b = O.sparse_laplacian()
+    x, st = O.minres(A, b, M=1.0 / A.diagonal())
+    assert resid(A, x, b) <= tol and st["solved"]
+
+
+# ---- expected magnitudes of the benchmark family --------
+def test_cg_iteration_counts_div_grad(O):
+    for N, default, tight in ((16, 38, 39), (32, 78, 79)):
+        A, b = O.sparse_laplacian(N)
+        assert A.nnz == 7 * N ** 3 - 6 * N ** 2
+        assert O.cg(A, b)[1]["niter"] == default
+        assert O.cg(A, b, atol=0.0, rtol=1e-8)[1]["niter"] == tight
+
+
+def test_float32_instantiation(O):
+    A, b = O.sparse_laplacian(8)
+    x, st = O.cg(A, b, dtype=np.float32)
+    assert st["solved"] and x.dtype == np.float32
+    assert resid(A, x.astype(np.float64), b) <= 1e-3
+    x, st = O.bicgstab(A, b, dtype=np.float32)
+    assert st["solved"]
