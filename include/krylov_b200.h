@@ -133,6 +133,8 @@ int krylov_b200_set_operator_csr(void *ws, int n, long long nnz, const void *row
                                  const void *values, int index_base, int index_bytes, int location);
 /* Share the CSR operator already attached to `src` (no copy). */
 int krylov_b200_share_operator(void *ws, void *src);
+/* Attach a CSR object made by kb200_csr_create (not owned: keep it alive while `ws` uses it). */
+int krylov_b200_attach_csr(void *ws, void *csr);
 /* Diagonal preconditioner: which = 0 -> M, 1 -> N; d[n] holds the diagonal of
  * the operator the solver applies (P^-1 with the default ldiv=false). NULL detaches. */
 int krylov_b200_set_preconditioner_diag(void *ws, int which, const void *d, int location);

@@ -369,6 +369,15 @@ int krylov_b200_share_operator(void* ws, void* src) {
   return 0;
 }
 
+int krylov_b200_attach_csr(void* ws, void* csr) {
+  Handle* h = lookup(ws);
+  if (!h || !csr) return fail("krylov_b200_attach_csr", "bad arguments");
+  CsrAny* a = (CsrAny*)csr;
+  if (a->dtype != h->dtype) return fail("krylov_b200_attach_csr", "dtype mismatch");
+  h->csr = std::shared_ptr<CsrAny>(std::shared_ptr<CsrAny>(), a);   // non-owning alias
+  return 0;
+}
+
 int krylov_b200_set_preconditioner_diag(void* ws, int which, const void* d, int location) {
   try {
     Handle* h = lookup(ws);

@@ -74,6 +74,7 @@ SIGNATURES = {
     "krylov_b200_last_error": (C.c_char_p, []),
     "krylov_b200_set_operator_csr": (_I, [_P, _I, _LL, _P, _P, _P, _I, _I, _I]),
     "krylov_b200_share_operator": (_I, [_P, _P]),
+    "krylov_b200_attach_csr": (_I, [_P, _P]),
     "krylov_b200_set_preconditioner_diag": (_I, [_P, _I, _P, _I]),
     "krylov_b200_default_options": (KrylovB200Options, []),
     "krylov_b200_set_options": (_I, [_P, C.POINTER(KrylovB200Options)]),
