@@ -149,6 +149,7 @@ typedef struct {
   int batch;          /* fused CG: iterations enqueued per host poll; 0 -> default  */
   int (*callback)(void *ws, void *user); /* kwarg `callback`; nonzero return = stop */
   void *callback_user;
+  int time_kernels;   /* fused CG: event-time launches 8..39 of each kernel (see krylov_b200_get_kernel_times) */
 } KrylovB200Options;
 KrylovB200Options krylov_b200_default_options(void);
 int krylov_b200_set_options(void *ws, const KrylovB200Options *opts);
@@ -173,10 +174,30 @@ int krylov_b200_get_history(void *ws, int which, double *out, int cap);
 /* Device pointer of a workspace vector by its reference field name
  * ("x","r","p","Ap","z","npc_dir","v","s","qd","r1","r2","w1","w2","y","w","dx","V1".."Vk"). */
 int krylov_b200_get_vector(void *ws, const char *name, void **dev_ptr);
+/* Average durations (ms) of the fused kernels measured with CUDA events on the workspace stream during the
+ * last solve run with time_kernels = 1: out[0] = K1 (SpMV + p update + <p,Ap>), out[1] = K2 (x, r update + <r,r>),
+ * out[2] = number of timed iterations. */
+int krylov_b200_get_kernel_times(void *ws, double *out3);
 /* Kernels launched so far through this workspace's stream. */
 long long krylov_b200_launch_count(void *ws);
 /* The CUDA stream (cudaStream_t) all of this workspace's work is ordered on. */
 void *krylov_b200_stream(void *ws);
+
+/* ---- row-partitioned solves: one process per GPU, one workspace per process ----
+ * The workspace is created with n = number of LOCAL rows; its CSR operator has
+ * n rows and n + nhalo columns: column j < n is local, column n + h is the halo
+ * entry h, owned by rank halo_rank[h] at offset halo_off[h] of that rank's local
+ * vectors.  Peers' vectors are mapped with CUDA IPC: every rank calls dist_init,
+ * dist_export (fills krylov_b200_dist_handle_bytes() bytes), the caller gathers
+ * the blobs of all ranks in rank order (e.g. torch.distributed.all_gather) and
+ * passes the concatenation to dist_import.  Afterwards krylov_solve on a CG
+ * workspace runs the fused path with in-kernel NVLink halo loads and in-kernel
+ * all-reduces of the dot products (csrc/dist.cuh).  All ranks must call
+ * krylov_solve with the same options. */
+int krylov_b200_dist_handle_bytes(void);
+int krylov_b200_dist_init(void *ws, int rank, int world, int nhalo, const int *halo_rank, const int *halo_off);
+int krylov_b200_dist_export(void *ws, void *handles_out);
+int krylov_b200_dist_import(void *ws, const void *all_handles);
 
 /* ---- flat primitives: the k* wrappers of src/krylov_utils.jl:305-349 ----
  * dtype selects float/double; all pointers are device pointers; scalars by

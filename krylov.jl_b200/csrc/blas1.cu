@@ -135,7 +135,7 @@ template <class T> void k_diagmul(Ctx& c, int n, T* y, const T* d, const T* x, b
 template <class T, int K>
 __global__ void __launch_bounds__(kBlock) dot_kernel(int n, const T* __restrict__ a, const T* __restrict__ b,
                                                      const T* __restrict__ u, const T* __restrict__ v, T* part,
-                                                     unsigned* ticket, T* out, int do_sqrt) {
+                                                     unsigned* ticket, T* out, int do_sqrt, DistComm* dc) {
   __shared__ T sm[32];
   const int stride = gridDim.x * blockDim.x;
   T acc[K];
@@ -167,7 +167,10 @@ __global__ void __launch_bounds__(kBlock) dot_kernel(int n, const T* __restrict_
   if (grid_sum_last<T, K>(mine, part, ticket, sm, tot)) {
     if (threadIdx.x == 0) {
 #pragma unroll
-      for (int k = 0; k < K; k++) out[k] = do_sqrt ? sqrt_rn(tot[k]) : tot[k];
+      for (int k = 0; k < K; k++) {
+        const T g = dist_reduce(dc, tot[k]);       // row-partitioned solve: sum over ranks
+        out[k] = do_sqrt ? sqrt_rn(g) : g;
+      }
     }
   }
 }
@@ -178,7 +181,7 @@ static T* slot_ptr(Ctx& c, int slot) { return reinterpret_cast<T*>(reinterpret_c
 template <class T>
 static void dot_launch(Ctx& c, int n, const T* a, const T* b, int slot, int do_sqrt) {
   const int grid = n > 0 ? stream_grid(n, 4, 4) : 1;
-  dot_kernel<T, 1><<<grid, kBlock, 0, c.stream>>>(n, a, b, nullptr, nullptr, (T*)c.partials, c.tickets, slot_ptr<T>(c, slot), do_sqrt);
+  dot_kernel<T, 1><<<grid, kBlock, 0, c.stream>>>(n, a, b, nullptr, nullptr, (T*)c.partials, c.tickets, slot_ptr<T>(c, slot), do_sqrt, c.dcomm);
   KB_CUDA(cudaGetLastError());
   c.launches++;
 }
@@ -203,7 +206,7 @@ template <class T> T k_nrm2(Ctx& c, int n, const T* x) {
 template <class T> void k_dot2(Ctx& c, int n, const T* a, const T* b, const T* u, const T* v, T* r1, T* r2) {
   const int grid = n > 0 ? stream_grid(n, 4, 4) : 1;
   // two adjacent T outputs live in slot 0 (out[0], out[1])
-  dot_kernel<T, 2><<<grid, kBlock, 0, c.stream>>>(n, a, b, u, v, (T*)c.partials, c.tickets, slot_ptr<T>(c, 0), 0);
+  dot_kernel<T, 2><<<grid, kBlock, 0, c.stream>>>(n, a, b, u, v, (T*)c.partials, c.tickets, slot_ptr<T>(c, 0), 0, c.dcomm);
   KB_CUDA(cudaGetLastError());
   c.launches++;
   KB_CUDA(cudaMemcpyAsync(c.hscal, c.dscal, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));

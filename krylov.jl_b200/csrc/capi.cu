@@ -144,6 +144,7 @@ SolveOpts map_opts(const Handle* h, const KrylovOptions* o) {
   s.batch = h->ext.batch;
   s.callback = h->ext.callback;
   s.callback_user = h->ext.callback_user;
+  s.time_kernels = h->ext.time_kernels;
   return s;
 }
 
@@ -438,6 +439,14 @@ int krylov_b200_get_vector(void* ws, const char* name, void** dev_ptr) {
   return p ? 0 : -2;
 }
 
+int krylov_b200_get_kernel_times(void* ws, double* out) {
+  Handle* h = lookup(ws);
+  if (!h || !out) return fail("krylov_b200_get_kernel_times", "bad arguments");
+  if (h->dtype == KRYLOV_FLOAT64) { auto* w = W<double>(h); out[0] = w->k1_ms; out[1] = w->k2_ms; out[2] = w->timed_pairs; }
+  else { auto* w = W<float>(h); out[0] = w->k1_ms; out[1] = w->k2_ms; out[2] = w->timed_pairs; }
+  return 0;
+}
+
 long long krylov_b200_launch_count(void* ws) {
   Handle* h = lookup(ws);
   if (!h) return -1;
@@ -448,6 +457,99 @@ void* krylov_b200_stream(void* ws) {
   Handle* h = lookup(ws);
   if (!h) return nullptr;
   return h->dtype == KRYLOV_FLOAT64 ? (void*)W<double>(h)->ctx.stream : (void*)W<float>(h)->ctx.stream;
+}
+
+// ------------------------------ row-partitioned solves --------------------
+}  // extern "C" (templates below need C++ linkage)
+namespace {
+constexpr int kIpcHandles = 4;   // r, p, p2, mailbox
+constexpr size_t kMailDoubles = 2 * kMaxRanks;
+constexpr size_t kMailBytes = kMailDoubles * sizeof(double) + kMailDoubles * sizeof(unsigned long long);
+
+template <class T> int dist_init_t(Handle* h, int rank, int world, int nhalo, const int* halo_rank, const int* halo_off) {
+  Workspace<T>* ws = W<T>(h);
+  if (h->solver != S_CG) throw std::runtime_error("row-partitioned solves are implemented for cg! only");
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) throw std::runtime_error("bad rank/world");
+  KB_CUDA(cudaSetDevice(ws->ctx.device));
+  if (!ws->p2) ws->p2 = dev_alloc<T>((size_t)ws->n);
+  KB_CUDA(cudaMemset(ws->p2, 0, sizeof(T) * (size_t)ws->n));
+  ws->dist.rank = rank; ws->dist.world = world;
+  int *dr = nullptr, *dof = nullptr;
+  KB_CUDA(cudaMalloc((void**)&dr, sizeof(int) * (size_t)(nhalo > 0 ? nhalo : 1)));
+  KB_CUDA(cudaMalloc((void**)&dof, sizeof(int) * (size_t)(nhalo > 0 ? nhalo : 1)));
+  if (nhalo > 0) {
+    KB_CUDA(cudaMemcpy(dr, halo_rank, sizeof(int) * (size_t)nhalo, cudaMemcpyHostToDevice));
+    KB_CUDA(cudaMemcpy(dof, halo_off, sizeof(int) * (size_t)nhalo, cudaMemcpyHostToDevice));
+  }
+  ws->dist.halo = HaloMap{ws->n, nhalo, dr, dof};
+  KB_CUDA(cudaMalloc(&ws->dist.mailbox, kMailBytes));
+  KB_CUDA(cudaMemset(ws->dist.mailbox, 0, kMailBytes));
+  return 0;
+}
+
+template <class T> int dist_export_t(Handle* h, void* out) {
+  Workspace<T>* ws = W<T>(h);
+  if (!ws->dist.mailbox) throw std::runtime_error("call krylov_b200_dist_init first");
+  KB_CUDA(cudaSetDevice(ws->ctx.device));
+  cudaIpcMemHandle_t* hs = (cudaIpcMemHandle_t*)out;
+  void* ptrs[kIpcHandles] = {ws->r, ws->p, ws->p2, ws->dist.mailbox};
+  for (int i = 0; i < kIpcHandles; i++) KB_CUDA(cudaIpcGetMemHandle(&hs[i], ptrs[i]));
+  return 0;
+}
+
+template <class T> int dist_import_t(Handle* h, const void* all) {
+  Workspace<T>* ws = W<T>(h);
+  auto& D = ws->dist;
+  KB_CUDA(cudaSetDevice(ws->ctx.device));
+  const cudaIpcMemHandle_t* hs = (const cudaIpcMemHandle_t*)all;
+  DistComm hc;
+  memset(&hc, 0, sizeof(hc));
+  hc.rank = D.rank; hc.world = D.world;
+  for (int k = 0; k < D.world; k++) {
+    void* ptr[kIpcHandles];
+    if (k == D.rank) {
+      ptr[0] = ws->r; ptr[1] = ws->p; ptr[2] = ws->p2; ptr[3] = D.mailbox;
+    } else {
+      for (int i = 0; i < kIpcHandles; i++) {
+        KB_CUDA(cudaIpcOpenMemHandle(&ptr[i], hs[k * kIpcHandles + i], cudaIpcMemLazyEnablePeerAccess));
+        D.opened.push_back(ptr[i]);
+      }
+    }
+    D.r_peer[k] = (T*)ptr[0]; D.bufA_peer[k] = (T*)ptr[1]; D.bufB_peer[k] = (T*)ptr[2];
+    hc.mail_val[k] = (double*)ptr[3];
+    hc.mail_seq[k] = (unsigned long long*)((double*)ptr[3] + kMailDoubles);
+  }
+  D.swapped = false;
+  if (!ws->ctx.dcomm) KB_CUDA(cudaMalloc((void**)&ws->ctx.dcomm, sizeof(DistComm)));
+  KB_CUDA(cudaMemcpy(ws->ctx.dcomm, &hc, sizeof(DistComm), cudaMemcpyHostToDevice));
+  return 0;
+}
+}  // namespace
+extern "C" {
+
+int krylov_b200_dist_handle_bytes(void) { return (int)(kIpcHandles * sizeof(cudaIpcMemHandle_t)); }
+
+int krylov_b200_dist_init(void* ws, int rank, int world, int nhalo, const int* halo_rank, const int* halo_off) {
+  try {
+    Handle* h = lookup(ws);
+    if (!h) return fail("krylov_b200_dist_init", "unknown workspace handle");
+    return h->dtype == KRYLOV_FLOAT64 ? dist_init_t<double>(h, rank, world, nhalo, halo_rank, halo_off)
+                                      : dist_init_t<float>(h, rank, world, nhalo, halo_rank, halo_off);
+  } catch (const std::exception& e) { return fail("krylov_b200_dist_init", e); }
+}
+int krylov_b200_dist_export(void* ws, void* handles_out) {
+  try {
+    Handle* h = lookup(ws);
+    if (!h) return fail("krylov_b200_dist_export", "unknown workspace handle");
+    return h->dtype == KRYLOV_FLOAT64 ? dist_export_t<double>(h, handles_out) : dist_export_t<float>(h, handles_out);
+  } catch (const std::exception& e) { return fail("krylov_b200_dist_export", e); }
+}
+int krylov_b200_dist_import(void* ws, const void* all_handles) {
+  try {
+    Handle* h = lookup(ws);
+    if (!h) return fail("krylov_b200_dist_import", "unknown workspace handle");
+    return h->dtype == KRYLOV_FLOAT64 ? dist_import_t<double>(h, all_handles) : dist_import_t<float>(h, all_handles);
+  } catch (const std::exception& e) { return fail("krylov_b200_dist_import", e); }
 }
 
 // ------------------------------ flat primitives ---------------------------

@@ -12,6 +12,14 @@
 // past the stopping point see `done` and return immediately, so niter, x, r, p
 // at exit are those of the reference loop.  p is double-buffered because K1
 // reads the old direction of neighbouring rows while writing the new one.
+//
+// Row-partitioned (multi-GPU) variant, template DIST: same two kernels; K1
+// additionally gathers the halo entries of r and p straight from the peers'
+// HBM over NVLink and both kernels finish their dot product with the in-kernel
+// cross-GPU all-reduce of dist.cuh.  Hazards: a peer's r is rewritten only in
+// its K2, which starts after the pAp all-reduce that needs MY K1's partial
+// (published after all my halo reads); a peer's p buffer read here (p_k) is
+// rewritten only in its K1 two iterations later.
 #include "kb_internal.h"
 #include "spmv_tiles.cuh"
 
@@ -24,8 +32,15 @@ struct CgState {
   T gamma, pAp, alpha, beta, pNorm2, rNorm, eps_tol, pad0;
   int iter, itmax, done, linesearch;
   int solved, tired, zero_curvature, inconsistent;
-  int npc, not_spd, pad1, pad2;
+  int npc, not_spd, comm_error, pad2;
   T hist[kHist];
+};
+
+template <class T>
+struct CgPeers {           // peers' vectors for the halo gather (DIST only)
+  HaloMap halo;
+  const T* r[kMaxRanks];
+  const T* p_old[kMaxRanks];
 };
 
 template <class T>
@@ -60,37 +75,59 @@ __device__ __forceinline__ void cg_k2_finalize(CgState<T>* st, T gamma_next) {
   st->done = solved || st->tired;
 }
 
-// ---- K1, TMA-staged -------------------------------------------------------
+// Global (all ranks) value of a finished local reduction; flags a dead peer.
 template <class T>
+__device__ __forceinline__ bool cg_global_sum(CgState<T>* st, DistComm* dc, T& v) {
+  if (dc) {
+    v = dist_reduce(dc, v);
+    if (dc->error) { st->comm_error = 1; st->done = 1; return false; }
+  }
+  return true;
+}
+
+template <class T, bool DIST>
+struct PVal {               // p_j = z_j + beta p_j, for local and (DIST) halo columns
+  const T* r; const T* p_old; T beta; const CgPeers<T>* peers;
+  __device__ __forceinline__ T operator()(int j) const {
+    if (DIST && j >= peers->halo.nloc) {
+      const int h = j - peers->halo.nloc;
+      const int rk = __ldg(&peers->halo.src_rank[h]), off = __ldg(&peers->halo.src_off[h]);
+      return add_rn(__ldg(&peers->r[rk][off]), mul_rn(beta, __ldg(&peers->p_old[rk][off])));
+    }
+    return add_rn(__ldg(&r[j]), mul_rn(beta, __ldg(&p_old[j])));
+  }
+};
+
+// ---- K1, TMA-staged -------------------------------------------------------
+template <class T, bool DIST>
 __global__ void __launch_bounds__(kTileThreads) cg_k1_tma(Csr<T> A, const T* __restrict__ r, const T* __restrict__ p_old,
                                                           T* __restrict__ p_new, T* __restrict__ Ap, CgState<T>* st,
-                                                          T* part, unsigned* ticket) {
+                                                          T* part, unsigned* ticket, DistComm* dc, CgPeers<T> peers) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ T sm[32];
   if (*(volatile int*)&st->done) return;
-  const T beta = st->beta;
   T dacc = T(0);
-  auto pval = [&](int j) { return add_rn(__ldg(&r[j]), mul_rn(beta, __ldg(&p_old[j]))); };
-  spmv_tiles_run<T>(A, smem, pval, [&](int row, T acc) {
-    const T pn = pval(row);
+  const PVal<T, DIST> pval{r, p_old, st->beta, &peers};
+  spmv_tiles_run<T>(A, smem, pval, pval, [&](int row, T acc, T pn) {
     p_new[row] = pn;
     Ap[row] = acc;
     dacc += pn * acc;
   });
   T mine[1] = {block_sum(dacc, sm)}, tot[1];
-  if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) cg_k1_finalize(st, tot[0]);
+  if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) {
+    if (cg_global_sum(st, DIST ? dc : nullptr, tot[0])) cg_k1_finalize(st, tot[0]);
+  }
 }
 
 // ---- K1, row-per-thread LDG (when the tile plan does not fit) --------------
-template <class T>
+template <class T, bool DIST>
 __global__ void __launch_bounds__(kBlock) cg_k1_rows(Csr<T> A, const T* __restrict__ r, const T* __restrict__ p_old,
                                                      T* __restrict__ p_new, T* __restrict__ Ap, CgState<T>* st, T* part,
-                                                     unsigned* ticket) {
+                                                     unsigned* ticket, DistComm* dc, CgPeers<T> peers) {
   __shared__ T sm[32];
   if (*(volatile int*)&st->done) return;
-  const T beta = st->beta;
   T dacc = T(0);
-  auto pval = [&](int j) { return add_rn(__ldg(&r[j]), mul_rn(beta, __ldg(&p_old[j]))); };
+  const PVal<T, DIST> pval{r, p_old, st->beta, &peers};
   const int stride = gridDim.x * blockDim.x;
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < A.n; row += stride) {
     const int kb = A.rowptr[row], ke = A.rowptr[row + 1];
@@ -102,13 +139,16 @@ __global__ void __launch_bounds__(kBlock) cg_k1_rows(Csr<T> A, const T* __restri
     dacc += pn * acc;
   }
   T mine[1] = {block_sum(dacc, sm)}, tot[1];
-  if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) cg_k1_finalize(st, tot[0]);
+  if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) {
+    if (cg_global_sum(st, DIST ? dc : nullptr, tot[0])) cg_k1_finalize(st, tot[0]);
+  }
 }
 
 // ---- K2 -------------------------------------------------------------------
 template <class T>
 __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p,
-                                                const T* __restrict__ Ap, CgState<T>* st, T* part, unsigned* ticket) {
+                                                const T* __restrict__ Ap, CgState<T>* st, T* part, unsigned* ticket,
+                                                DistComm* dc) {
   __shared__ T sm[32];
   if (*(volatile int*)&st->done) return;
   const T alpha = st->alpha, nalpha = -alpha;
@@ -138,7 +178,9 @@ __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __r
     acc += rn * rn;
   }
   T mine[1] = {block_sum(acc, sm)}, tot[1];
-  if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) cg_k2_finalize(st, tot[0]);
+  if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) {
+    if (cg_global_sum(st, dc, tot[0])) cg_k2_finalize(st, tot[0]);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -153,6 +195,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   Ctx& c = ws.ctx;
   const int n = ws.n;
   typedef CgState<T> St;
+  const bool dist = ws.dist.world > 1;
   if (!ws.fused_state) {
     KB_CUDA(cudaMalloc(&ws.fused_state, sizeof(St)));
     KB_CUDA(cudaHostAlloc(&ws.fused_host, 2 * sizeof(St), cudaHostAllocDefault));
@@ -171,13 +214,27 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
 
   static bool attr_set = false;
   if (A.tma_ok && !attr_set) {
-    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
   const int g2 = stream_grid(n, 4, 8);
   const int g1r = stream_grid(n, 1, 8);
   T* P[2] = {ws.p, ws.p2};   // ws.p holds z (= r) from the prologue: with beta = 0, K1 forms p = r + 0*p
   T* part = (T*)c.partials;
+  // peers' direction buffers in the same order as P[]
+  CgPeers<T> peersP[2];
+  memset(peersP, 0, sizeof(peersP));
+  if (dist) {
+    for (int b = 0; b < 2; b++) {
+      peersP[b].halo = ws.dist.halo;
+      const bool wantB = (b == 1) != ws.dist.swapped;     // P[b] is the bufB allocation?
+      for (int k = 0; k < ws.dist.world; k++) {
+        peersP[b].r[k] = ws.dist.r_peer[k];
+        peersP[b].p_old[k] = wantB ? ws.dist.bufB_peer[k] : ws.dist.bufA_peer[k];
+      }
+    }
+  }
 
   const bool single_step = (o.callback != nullptr) || (o.timemax < 1e300) || o.verbose > 0;
   int batch = o.batch > 0 ? o.batch : 16;
@@ -188,15 +245,31 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   KB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
   KB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
   int enq = 0;
+  // optional per-kernel timing (bench.py roofline breakdown): events around launches 8..39
+  constexpr int kTimedFirst = 8, kTimedCount = 32;
+  std::vector<cudaEvent_t> tev;
+  if (o.time_kernels) {
+    tev.resize(3 * kTimedCount);
+    for (auto& e : tev) KB_CUDA(cudaEventCreate(&e));
+  }
   auto enqueue = [&](int slot) {
     for (int b = 0; b < batch; b++, enq++) {
       T* p_old = P[enq & 1];
       T* p_new = P[(enq + 1) & 1];
-      if (A.tma_ok)
-        cg_k1_tma<T><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2);
-      else
-        cg_k1_rows<T><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2);
-      cg_k2<T><<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3);
+      const CgPeers<T>& pe = peersP[enq & 1];
+      const int ti = enq - kTimedFirst;
+      const bool timed = o.time_kernels && ti >= 0 && ti < kTimedCount;
+      if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti], c.stream));
+      if (A.tma_ok) {
+        if (dist) cg_k1_tma<T, true><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
+        else cg_k1_tma<T, false><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
+      } else {
+        if (dist) cg_k1_rows<T, true><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
+        else cg_k1_rows<T, false><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
+      }
+      if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti + 1], c.stream));
+      cg_k2<T><<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3, dist ? c.dcomm : nullptr);
+      if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti + 2], c.stream));
       c.launches += 2;
     }
     KB_CUDA(cudaGetLastError());
@@ -234,6 +307,21 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   c.sync();   // drain speculative no-op launches
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);
+  if (o.time_kernels) {
+    const int pairs = std::min(kTimedCount, std::max(0, std::min(enq, last.iter) - kTimedFirst));
+    double s1 = 0, s2 = 0;
+    for (int i = 0; i < pairs; i++) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, tev[3 * i], tev[3 * i + 1]);
+      cudaEventElapsedTime(&b, tev[3 * i + 1], tev[3 * i + 2]);
+      s1 += a; s2 += b;
+    }
+    ws.timed_pairs = pairs;
+    ws.k1_ms = pairs ? s1 / pairs : 0;
+    ws.k2_ms = pairs ? s2 / pairs : 0;
+    for (auto& e : tev) cudaEventDestroy(e);
+  }
+  if (last.comm_error) throw std::runtime_error("cross-GPU all-reduce timed out: a peer rank is not participating");
   if (last.not_spd) throw std::runtime_error("The linear operator `A` or the preconditioner `M` is not symmetric positive definite.");
 
   iter = last.iter;
@@ -246,7 +334,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   // curvature test at iteration `iter` (iter not incremented): p = P[(iter+1) & 1].
   const bool k1_exit = zero_curvature || last.npc;
   T* pcur = k1_exit ? P[(iter + 1) & 1] : P[iter & 1];
-  if (pcur != ws.p) { T* tmp = ws.p; ws.p = ws.p2; ws.p2 = tmp; }
+  if (pcur != ws.p) { T* tmp = ws.p; ws.p = ws.p2; ws.p2 = tmp; ws.dist.swapped = !ws.dist.swapped; }
   if (last.npc) {                                   // linesearch branch, cg.jl:203-209
     if (iter == 0) k_copy<T>(c, n, ws.x, ws.p);
     k_copy<T>(c, n, ws.npc_dir, ws.p);

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "dist.cuh"
 
 namespace kb {
 
@@ -30,6 +31,7 @@ struct Ctx {
   void* dscal = nullptr;         // 16 device scalars (doubles) written by reductions
   void* hscal = nullptr;         // pinned mirror of dscal
   long long launches = 0;        // kernels launched through this context (bench: gpu_launches)
+  DistComm* dcomm = nullptr;     // device-resident communicator of a row-partitioned solve (nullptr: single GPU)
 
   void init(int dev);
   void destroy();
@@ -128,6 +130,7 @@ struct SolveOpts {
   void* callback_user = nullptr;
   int fused = 1;                    // 0 => force the generic primitive path
   int batch = 0;                    // fused CG: iterations enqueued per host poll (0 => default)
+  int time_kernels = 0;             // fused CG: bracket the first launches of K1/K2 with CUDA events
 };
 
 struct Stats {
@@ -163,10 +166,23 @@ struct Workspace {
   std::vector<T> err_vec;              // MINRES window
   int memory = 20, window = 5;
   int inner_iter = 0;
+  double k1_ms = 0, k2_ms = 0;         // average event-timed duration of the fused kernels (time_kernels)
+  int timed_pairs = 0;
   void* fused_state = nullptr;         // device scalar block of the fused paths
   void* fused_host = nullptr;          // pinned mirror (2 slots)
   T* bbuf = nullptr;                   // device copies of host b / c for the C ABI
   T* cbuf = nullptr;
+  // row-partitioned (multi-GPU) state; world == 1 means single GPU
+  struct Dist {
+    int rank = 0, world = 1;
+    HaloMap halo{0, 0, nullptr, nullptr};      // device arrays
+    void* mailbox = nullptr;                    // local mailbox allocation (values + flags)
+    T* bufA_peer[kMaxRanks] = {};               // every rank's `p` allocation (as created)
+    T* bufB_peer[kMaxRanks] = {};               // every rank's `p2` allocation
+    T* r_peer[kMaxRanks] = {};
+    std::vector<void*> opened;                  // cudaIpcOpenMemHandle results to close
+    bool swapped = false;                       // ws.p currently points at the bufB allocation
+  } dist;
 };
 
 template <class T> Workspace<T>* ws_create(SolverKind kind, int m, int n, int memory, int window, int device);

@@ -63,6 +63,11 @@ template <class T> void ws_destroy(Workspace<T>* ws) {
   for (T* p : ws->V) dev_free(p);
   if (ws->fused_state) cudaFree(ws->fused_state);
   if (ws->fused_host) cudaFreeHost(ws->fused_host);
+  for (void* p : ws->dist.opened) cudaIpcCloseMemHandle(p);
+  if (ws->dist.mailbox) cudaFree(ws->dist.mailbox);
+  if (ws->dist.halo.src_rank) cudaFree((void*)ws->dist.halo.src_rank);
+  if (ws->dist.halo.src_off) cudaFree((void*)ws->dist.halo.src_off);
+  if (ws->ctx.dcomm) cudaFree(ws->ctx.dcomm);
   ws->ctx.destroy();
   delete ws;
 }
@@ -100,6 +105,8 @@ void cg_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
   if (ws.warm_start && linesearch) throw std::runtime_error("warm_start and linesearch cannot be used together");
   if (o.verbose > 0) printf("CG: system of %d equations in %d variables\n", n, n);
   const bool MisI = M.is_identity();
+  if (ws.dist.world > 1 && (ws.warm_start || !cg_fused_eligible(A, M, o) || o.callback))
+    throw std::runtime_error("row-partitioned cg!: only the fused path (CSR operator, M = I, radius = 0, no warm start, no callback) is distributed");
   allocate_if(!MisI, ws, ws.z);
   allocate_if(linesearch || radius > 0, ws, ws.npc_dir);
   T *dx = ws.dx, *x = ws.x, *r = ws.r, *Ap = ws.Ap;
@@ -282,6 +289,7 @@ void bicgstab_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c_
   const int n = ws.n;
   const bool history = o.history, ldiv = o.ldiv;
   if (o.verbose > 0) printf("BICGSTAB: system of size %d\n", n);
+  if (ws.dist.world > 1) throw std::runtime_error("row-partitioned solves are implemented for cg! only");
   const bool MisI = M.is_identity(), NisI = N.is_identity();
   allocate_if(!MisI, ws, ws.t);
   allocate_if(!NisI, ws, ws.yz);
@@ -392,6 +400,7 @@ void gmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>
   const int n = ws.n;
   const bool history = o.history, ldiv = o.ldiv, restart = o.restart, reorth = o.reorthogonalization;
   if (o.verbose > 0) printf("GMRES: system of size %d\n", n);
+  if (ws.dist.world > 1) throw std::runtime_error("row-partitioned solves are implemented for cg! only");
   const bool MisI = M.is_identity(), NisI = N.is_identity();
   allocate_if(!MisI, ws, ws.q);
   allocate_if(!NisI, ws, ws.pp);
@@ -564,6 +573,7 @@ void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T
   const int n = ws.n;
   const bool history = o.history, ldiv = o.ldiv, linesearch = o.linesearch;
   if (o.verbose > 0) printf("MINRES: system of size %d\n", n);
+  if (ws.dist.world > 1) throw std::runtime_error("row-partitioned solves are implemented for cg! only");
   if (ws.warm_start && linesearch) throw std::runtime_error("warm_start and linesearch cannot be used together");
   const bool MisI = M.is_identity();
   allocate_if(!MisI, ws, ws.vv);

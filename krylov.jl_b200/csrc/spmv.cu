@@ -137,6 +137,15 @@ template <class T> void csr_plan(Ctx& c, Csr<T>& A) {
   const size_t two_cta = 110 * 1024, one_cta = 220 * 1024;
   A.tma_ok = false;
   int per_sm = 2;
+  // tuning overrides (profiles/sweep_k1.py): KB200_STAGES, KB200_CTAS_PER_SM
+  const char* es = getenv("KB200_STAGES");
+  const char* ec = getenv("KB200_CTAS_PER_SM");
+  if (es && ec) {
+    const int s = atoi(es), cps = atoi(ec);
+    if (s >= 1 && s <= 8 && cps >= 1 && cps <= 8 && L.total_bytes(s) * cps <= 226 * 1024) { A.tma_ok = true; A.stages = s; per_sm = cps; }
+  }
+  // default: 3 CTAs/SM x 3 stages when it fits (27 warps/SM hide the gather latency better than 2 x 4)
+  if (!A.tma_ok && L.total_bytes(3) * 3 <= 226 * 1024) { A.tma_ok = true; A.stages = 3; per_sm = 3; }
   for (int s = 4; s >= 2 && !A.tma_ok; s--)
     if (L.total_bytes(s) <= two_cta) { A.tma_ok = true; A.stages = s; per_sm = 2; }
   for (int s = 4; s >= 2 && !A.tma_ok; s--)
@@ -181,10 +190,10 @@ __global__ void __launch_bounds__(kTileThreads) spmv_tma_kernel(Csr<T> A, const 
   __shared__ T sm[32];
   T dacc = T(0);
   spmv_tiles_run<T>(
-      A, smem, [&](int j) { return __ldg(&x[j]); },
-      [&](int row, T acc) {
+      A, smem, [&](int j) { return __ldg(&x[j]); }, [&](int row) { return DOT ? __ldg(&x[row]) : T(0); },
+      [&](int row, T acc, T xr) {
         y[row] = acc;
-        if (DOT) dacc += __ldg(&x[row]) * acc;
+        if (DOT) dacc += xr * acc;
       });
   if (DOT) {
     T mine[1] = {block_sum(dacc, sm)}, tot[1];

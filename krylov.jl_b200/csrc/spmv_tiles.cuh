@@ -12,7 +12,9 @@
 //
 // Row sums accumulate left to right in ascending column order with the product
 // rounded before the add -- the order SparseArrays' CSC mul! produces for every
-// y[i] -- so y is bit-identical to the sequential CPU oracle.
+// y[i] -- so y is bit-identical to the sequential CPU oracle.  (The gathers of
+// up to kGatherDepth nonzeros are ISSUED together to overlap their latencies;
+// the additions are still performed in column order.)
 #pragma once
 #include "common.cuh"
 #include "kb_internal.h"
@@ -21,6 +23,7 @@ namespace kb {
 
 constexpr int kConsumerWarps = kTileRows / 32;            // 8
 constexpr int kTileThreads = kTileRows + 32;              // + 1 producer warp
+constexpr int kGatherDepth = 8;                           // gathers in flight per thread
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -72,11 +75,18 @@ struct TileLayout {
   __host__ __device__ size_t total_bytes(int stages) const { return 128 + (size_t)stages * stage_bytes(); }
 };
 
+struct NoRowBegin {
+  __device__ __forceinline__ int operator()(int) const { return 0; }
+};
+
 // Runs the tile pipeline.  Every thread of the CTA must call it (blockDim.x ==
-// kTileThreads).  `gather(j)` returns the x value for column j; `row_done(row,
-// acc)` receives each finished row sum (consumer threads only, row < n).
-template <class T, class Gather, class RowDone>
-__device__ __forceinline__ void spmv_tiles_run(const Csr<T>& A, unsigned char* smem, Gather gather, RowDone row_done) {
+// kTileThreads).  `gather(j)` returns the x value for column j; `row_begin(row)`
+// is evaluated before the row's gathers (use it to start loads the epilogue
+// needs) and its result is handed to `row_done(row, acc, pre)` with the
+// finished row sum (consumer threads only, row < n).
+template <class T, class Gather, class RowBegin, class RowDone>
+__device__ __forceinline__ void spmv_tiles_run(const Csr<T>& A, unsigned char* smem, Gather gather, RowBegin row_begin,
+                                               RowDone row_done) {
   const TileLayout<T> L{A.tile_cap};
   const int S = A.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);        // [S]
@@ -96,13 +106,18 @@ __device__ __forceinline__ void spmv_tiles_run(const Csr<T>& A, unsigned char* s
     if (lane == 0) {
       const uint64_t pol = l2_evict_first_policy();
       int it = 0;
-      for (int t = blockIdx.x; t < A.ntiles; t += gridDim.x, it++) {
+      int t = blockIdx.x;
+      int k0 = 0, k1 = 0;
+      if (t < A.ntiles) { k0 = __ldg(&A.rowptr[t * kTileRows]); k1 = __ldg(&A.rowptr[min(t * kTileRows + kTileRows, A.n)]); }
+      for (; t < A.ntiles; t += gridDim.x, it++) {
+        // start fetching the NEXT tile's nnz range before blocking on the ring slot
+        const int tn = t + gridDim.x;
+        int nk0 = 0, nk1 = 0;
+        if (tn < A.ntiles) { nk0 = __ldg(&A.rowptr[tn * kTileRows]); nk1 = __ldg(&A.rowptr[min(tn * kTileRows + kTileRows, A.n)]); }
         const int s = it % S;
         mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
         unsigned char* st = ring + (size_t)s * L.stage_bytes();
         const int r0 = t * kTileRows;
-        const int r1 = min(r0 + kTileRows, A.n);
-        const int k0 = __ldg(&A.rowptr[r0]), k1 = __ldg(&A.rowptr[r1]);
         const int k0v = k0 & ~(VA - 1), k1v = (k1 + VA - 1) & ~(VA - 1);
         const int k0c = k0 & ~3, k1c = (k1 + 3) & ~3;
         const unsigned rp_b = (kTileRows + 4) * sizeof(int);
@@ -112,35 +127,39 @@ __device__ __forceinline__ void spmv_tiles_run(const Csr<T>& A, unsigned char* s
         tma_load_1d(st, A.rowptr + r0, rp_b, &full[s], pol);
         if (v_b) tma_load_1d(st + L.rp_bytes(), A.val + k0v, v_b, &full[s], pol);
         if (c_b) tma_load_1d(st + L.rp_bytes() + L.val_bytes(), A.colind + k0c, c_b, &full[s], pol);
+        k0 = nk0; k1 = nk1;
       }
     }
   } else {
     // ------------------------------ consumers -----------------------------
     int it = 0;
     for (int t = blockIdx.x; t < A.ntiles; t += gridDim.x, it++) {
+      const int row = t * kTileRows + tid;
+      auto pre = row_begin(row < A.n ? row : 0);               // independent of the tile: issue before waiting
       const int s = it % S;
       mbar_wait(&full[s], (it / S) & 1);
       const unsigned char* st = ring + (size_t)s * L.stage_bytes();
       const int* rp = reinterpret_cast<const int*>(st);
       const T* vs = reinterpret_cast<const T*>(st + L.rp_bytes());
       const int* cs = reinterpret_cast<const int*>(st + L.rp_bytes() + L.val_bytes());
-      const int row = t * kTileRows + tid;
       if (row < A.n) {
         const int k0 = rp[0];
-        const int voff = k0 & ~(VA - 1), coff = k0 & ~3;
+        const T* vrow = vs - (k0 & ~(VA - 1));
+        const int* crow = cs - (k0 & ~3);
         const int kb = rp[tid], ke = rp[tid + 1];
         T acc = T(0);
-        int k = kb;
-        // two nonzeros per trip: both gathers are issued before either is consumed
-        for (; k + 1 < ke; k += 2) {
-          const int c0 = cs[k - coff], c1 = cs[k + 1 - coff];
-          const T a0 = vs[k - voff], a1 = vs[k + 1 - voff];
-          const T x0 = gather(c0), x1 = gather(c1);
-          acc = add_rn(acc, mul_rn(a0, x0));
-          acc = add_rn(acc, mul_rn(a1, x1));
+        for (int k = kb; k < ke; k += kGatherDepth) {
+          T xv[kGatherDepth], av[kGatherDepth];
+#pragma unroll
+          for (int u = 0; u < kGatherDepth; u++) {
+            if (k + u < ke) { av[u] = vrow[k + u]; xv[u] = gather(crow[k + u]); }
+          }
+#pragma unroll
+          for (int u = 0; u < kGatherDepth; u++) {
+            if (k + u < ke) acc = add_rn(acc, mul_rn(av[u], xv[u]));
+          }
         }
-        if (k < ke) acc = add_rn(acc, mul_rn(vs[k - voff], gather(cs[k - coff])));
-        row_done(row, acc);
+        row_done(row, acc, pre);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);

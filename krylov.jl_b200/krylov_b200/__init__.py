@@ -200,7 +200,7 @@ class KrylovWorkspace:
 
     def solve(self, A, b, *, c=None, M=None, N=None, atol=None, rtol=None, itmax=0, timemax=math.inf, verbose=0,
               history=False, callback=None, radius=0.0, linesearch=False, lambda_=0.0, etol=None, conlim=None,
-              restart=False, reorthogonalization=False, ldiv=False, fused=True, batch=0):
+              restart=False, reorthogonalization=False, ldiv=False, fused=True, batch=0, time_kernels=False):
         """solver!(ws, A, b; kwargs...)  -- kwargs as in cg.jl:100-111, gmres.jl:96-108,
         bicgstab.jl:105-116, minres.jl:138-151.  M / N: None (identity), a 1-D array
         (Diagonal preconditioner) or a host callable."""
@@ -215,6 +215,7 @@ class KrylovWorkspace:
         o.restart, o.reorthogonalization = int(restart), int(reorthogonalization)
         e = lib().krylov_b200_default_options()
         e.history, e.ldiv, e.fused, e.batch = int(history), int(ldiv), int(fused), int(batch)
+        e.time_kernels = int(time_kernels)
         if etol is not None:
             e.etol = float(etol)
         if conlim is not None:
@@ -326,6 +327,13 @@ class KrylovWorkspace:
     @property
     def launches(self) -> int:
         return int(lib().krylov_b200_launch_count(self._h))
+
+    @property
+    def kernel_times(self):
+        """(K1 ms, K2 ms, timed iterations) of the last solve run with time_kernels=True."""
+        out = (C.c_double * 3)()
+        lib().krylov_b200_get_kernel_times(self._h, out)
+        return float(out[0]), float(out[1]), int(out[2])
 
     @property
     def npc_dir(self):

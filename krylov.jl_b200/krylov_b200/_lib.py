@@ -36,7 +36,8 @@ class KrylovOptions(C.Structure):
 
 class KrylovB200Options(C.Structure):
     _fields_ = [("history", C.c_int), ("ldiv", C.c_int), ("etol", C.c_double), ("conlim", C.c_double),
-                ("fused", C.c_int), ("batch", C.c_int), ("callback", CALLBACK), ("callback_user", C.c_void_p)]
+                ("fused", C.c_int), ("batch", C.c_int), ("callback", CALLBACK), ("callback_user", C.c_void_p),
+                ("time_kernels", C.c_int)]
 
 
 class KrylovB200Stats(C.Structure):
@@ -81,8 +82,13 @@ SIGNATURES = {
     "krylov_b200_get_stats": (_I, [_P, C.POINTER(KrylovB200Stats)]),
     "krylov_b200_get_history": (_I, [_P, _I, C.POINTER(_D), _I]),
     "krylov_b200_get_vector": (_I, [_P, C.c_char_p, C.POINTER(_P)]),
+    "krylov_b200_get_kernel_times": (_I, [_P, C.POINTER(_D)]),
     "krylov_b200_launch_count": (_LL, [_P]),
     "krylov_b200_stream": (_P, [_P]),
+    "krylov_b200_dist_handle_bytes": (_I, []),
+    "krylov_b200_dist_init": (_I, [_P, _I, _I, _I, _P, _P]),
+    "krylov_b200_dist_export": (_I, [_P, _P]),
+    "krylov_b200_dist_import": (_I, [_P, _P]),
     "kb200_ctx_create": (_P, [_I]),
     "kb200_ctx_destroy": (None, [_P]),
     "kb200_sync": (_I, [_P]),

@@ -1,0 +1,211 @@
+"""Row-partitioned (multi-GPU) CG: one process per GPU under torchrun.
+
+torch.distributed is plumbing only (rendezvous, exchanging 256-byte CUDA-IPC
+handle blobs, the max-over-ranks of the timing); the data path is inside the
+CUDA kernels: halo entries of r and p are loaded from the peers' HBM over
+NVLink while K1 runs, and the two dot products per iteration finish with an
+in-kernel all-reduce through peer mailboxes (csrc/dist.cuh).
+
+The reference has no distributed code; docs/src/custom_workspaces.md:464-637
+sketches the same decomposition with MPI (local dot + Allreduce, user-written
+distributed mul!).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+from . import _lib
+
+
+# --------------------------------------------------------------------------
+# partitioning (pure NumPy: testable on CPU with gloo)
+# --------------------------------------------------------------------------
+def slab_bounds(n3: int, world: int):
+    """Balanced split of n3 z-planes over `world` ranks -> list of (k_lo, k_hi)."""
+    base, rem = divmod(n3, world)
+    out, k = [], 0
+    for r in range(world):
+        h = base + (1 if r < rem else 0)
+        out.append((k, k + h))
+        k += h
+    return out
+
+
+def localize_columns(colind_global, row_starts, rank):
+    """Map GLOBAL column indices of a row block to [local | halo] numbering.
+
+    row_starts: array of length world+1 with the first global row of every rank.
+    Returns (colind_local int32, halo_rank int32[nhalo], halo_off int32[nhalo]).
+    Column j owned by this rank -> j - lo; any other column -> nloc + h where h indexes the sorted
+    unique list of off-rank columns this block touches ("bit-exact integer indexing": the map is a
+    bijection on the touched columns and preserves the ascending order inside every row)."""
+    xp_is_torch = type(colind_global).__module__.startswith("torch")
+    if xp_is_torch:
+        import torch
+        rs = torch.as_tensor(np.asarray(row_starts), device=colind_global.device, dtype=torch.int64)
+        lo, hi = int(row_starts[rank]), int(row_starts[rank + 1])
+        cg = colind_global.to(torch.int64)
+        off = (cg < lo) | (cg >= hi)
+        halo_cols = torch.unique(cg[off])                      # sorted
+        owner = torch.searchsorted(rs, halo_cols, right=True) - 1
+        halo_off = halo_cols - rs[owner]
+        local = cg - lo
+        if halo_cols.numel():
+            local[off] = (hi - lo) + torch.searchsorted(halo_cols, cg[off])
+        return (local.to(torch.int32), owner.to(torch.int32).cpu().numpy(), halo_off.to(torch.int32).cpu().numpy())
+    rs = np.asarray(row_starts, dtype=np.int64)
+    lo, hi = int(rs[rank]), int(rs[rank + 1])
+    cg = np.asarray(colind_global, dtype=np.int64)
+    off = (cg < lo) | (cg >= hi)
+    halo_cols = np.unique(cg[off])
+    owner = np.searchsorted(rs, halo_cols, side="right") - 1
+    halo_off = halo_cols - rs[owner]
+    local = cg - lo
+    if len(halo_cols):
+        local[off] = (hi - lo) + np.searchsorted(halo_cols, cg[off])
+    return local.astype(np.int32), owner.astype(np.int32), halo_off.astype(np.int32)
+
+
+# --------------------------------------------------------------------------
+# distributed workspace
+# --------------------------------------------------------------------------
+class DistCgWorkspace:
+    """CgWorkspace for one row block.  `csr_local` = (rowptr, colind_local, values) with the
+    [local | halo] column numbering of localize_columns()."""
+
+    def __init__(self, csr_local, halo_rank, halo_off, rank, world, dtype=np.float64, device="cuda"):
+        import torch.distributed as dist
+        from . import CgWorkspace
+        self.rank, self.world = rank, world
+        nloc = int(csr_local[0].shape[0]) - 1
+        self.ws = CgWorkspace(nloc, nloc, dtype, device=device)
+        self.ws.set_operator(csr_local)
+        L = _lib.lib()
+        hr = np.ascontiguousarray(halo_rank, dtype=np.int32)
+        ho = np.ascontiguousarray(halo_off, dtype=np.int32)
+        if L.krylov_b200_dist_init(self.ws._h, rank, world, len(hr), hr.ctypes.data_as(C.c_void_p),
+                                   ho.ctypes.data_as(C.c_void_p)) != 0:
+            raise RuntimeError(_lib.last_error())
+        nb = L.krylov_b200_dist_handle_bytes()
+        mine = (C.c_ubyte * nb)()
+        if L.krylov_b200_dist_export(self.ws._h, mine) != 0:
+            raise RuntimeError(_lib.last_error())
+        blobs = [None] * world
+        dist.all_gather_object(blobs, bytes(mine))
+        allb = b"".join(blobs)
+        buf = (C.c_ubyte * len(allb)).from_buffer_copy(allb)
+        if L.krylov_b200_dist_import(self.ws._h, buf) != 0:
+            raise RuntimeError(_lib.last_error())
+        dist.barrier()
+
+    def solve(self, b_local, **kw):
+        return self.ws.solve(None, b_local, **kw)
+
+    @property
+    def x(self):
+        return self.ws.x
+
+    @property
+    def stats(self):
+        return self.ws.stats
+
+    def free(self):
+        self.ws.free()
+
+
+def make_poisson_rank(N, rank, world, torch, device, dtype=np.float64):
+    """This rank's z-slab of get_div_grad(N,N,N) with localized columns."""
+    from .problems import div_grad_csr
+    bounds = slab_bounds(N, world)
+    k_lo, k_hi = bounds[rank]
+    rp, ci, va = div_grad_csr(N, dtype=dtype, k_lo=k_lo, k_hi=k_hi, xp=torch, device=device)
+    row_starts = np.array([b[0] * N * N for b in bounds] + [N ** 3], dtype=np.int64)
+    ci_loc, hr, ho = localize_columns(ci, row_starts, rank)
+    return (rp, ci_loc, va), hr, ho, (k_hi - k_lo) * N * N
+
+
+# --------------------------------------------------------------------------
+# bench entry (called by bench.py when WORLD_SIZE > 1)
+# --------------------------------------------------------------------------
+def bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.lib().krylov_b200_set_device(local)
+    dist.init_process_group("nccl", device_id=dev)
+    N, iters = WORKLOADS[args.workload]
+    n, nnz = N ** 3, 7 * N ** 3 - 6 * N ** 2
+    csr, hr, ho, nloc = make_poisson_rank(N, rank, world, torch, dev)
+    dws = DistCgWorkspace(csr, hr, ho, rank, world)
+    b = torch.ones(nloc, dtype=torch.float64, device=dev)
+    kw = dict(atol=0.0, rtol=0.0, itmax=iters)
+    stream = torch.cuda.ExternalStream(_lib.lib().krylov_b200_stream(dws.ws._h), device=dev)
+    for _ in range(args.warmup):
+        dist.barrier()
+        dws.solve(b, **kw)
+    assert dws.stats.niter == iters, dws.stats
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = dws.ws.launches
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        dws.solve(b, **kw)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = torch.tensor([dws.ws.launches - l0], device=dev)
+    dist.all_reduce(launches)
+    rn = dws.stats
+    # end-to-end arm: host buffers for this rank's slice of b and x
+    from . import CgWorkspace  # noqa: F401
+    bh = torch.ones(nloc, dtype=torch.float64).pin_memory()
+    xh = torch.empty(nloc, dtype=torch.float64).pin_memory()
+    bd = torch.empty(nloc, dtype=torch.float64, device=dev)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        bd.copy_(bh, non_blocking=True)                         # H2D of this rank's slice of b
+        torch.cuda.synchronize()
+        dws.solve(bd, **kw)
+        xh.copy_(dws.x, non_blocking=False)                     # D2H of this rank's slice of x
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        its = args.steps * iters
+        value = its / (ms * 1e-3)
+        B = algorithmic_bytes_cg(n, nnz)
+        peak, src = hbm_peak()
+        achieved = B * its / (ms * 1e-3) / 1e9
+        line = dict(metric="CG iterations/s", value=value, unit="it/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+                    data="synthetic",
+                    config=dict(workload=f"cg! fused, get_div_grad({N},{N},{N}) Float64 int32-CSR row-partitioned in z-slabs over "
+                                         f"{world} GPUs, b=ones, atol=rtol=0, itmax={iters} per step", n=n, nnz=nnz,
+                                iters_per_step=iters, parallelism=f"rows/{world}: NVLink P2P halo loads + in-kernel all-reduce",
+                                l2="per-rank matrix slab %.0f MB" % (nnz * 12 / world / 1e6), final_rnorm=rn.status),
+                    roofline=dict(bound="hbm", achieved=achieved, peak=peak * world, unit="GB/s", frac=achieved / (peak * world),
+                                  traffic=None, peak_source=src + f" x {world} GPUs", bytes_per_iteration=B),
+                    clocks=clocks,
+                    e2e=dict(value=its / float(e2e_s.item()), unit="it/s", h2d_bytes_per_step=n * 8, d2h_bytes_per_step=n * 8),
+                    gpu_launches=int(launches.item()))
+        print(json.dumps(line))
+    dws.free()
+    dist.destroy_process_group()

@@ -1,0 +1,122 @@
+"""Host-side logic of the row-partitioned path, on CPU: slab bounds, column localisation (a bijection that keeps
+row order), a NumPy emulation of the halo gather + rank-ordered all-reduce reproducing the global CG iterates,
+and the handle-exchange plumbing under torch.distributed (gloo, world_size = 2)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from krylov_b200 import dist as D
+from krylov_b200 import problems as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_slab_bounds_cover_and_balance():
+    for n3, w in ((215, 8), (464, 8), (7, 3), (4, 4), (10, 1)):
+        b = D.slab_bounds(n3, w)
+        assert b[0][0] == 0 and b[-1][1] == n3 and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _blocks(N, world):
+    bounds = D.slab_bounds(N, world)
+    row_starts = np.array([b[0] * N * N for b in bounds] + [N ** 3], dtype=np.int64)
+    out = []
+    for r, (lo, hi) in enumerate(bounds):
+        rp, ci, va = P.div_grad_csr(N, k_lo=lo, k_hi=hi)
+        cl, hr, ho = D.localize_columns(ci, row_starts, r)
+        out.append((rp, ci, cl, va, hr, ho))
+    return bounds, row_starts, out
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_localize_columns_is_a_bijection(world):
+    N = 9 if world == 8 else 6
+    bounds, rs, blocks = _blocks(N, world)
+    for r, (rp, cg, cl, va, hr, ho) in enumerate(blocks):
+        nloc = len(rp) - 1
+        lo = rs[r]
+        back = np.where(cl < nloc, cl + lo, 0)
+        halo = cl >= nloc
+        back[halo] = rs[hr[cl[halo] - nloc]] + ho[cl[halo] - nloc]
+        assert np.array_equal(back, cg)                       # every (row, col, val) triplet is preserved
+        assert np.all(hr != r) and np.all(ho >= 0)
+        # slab neighbours only, one N^2 plane each
+        assert set(hr.tolist()) <= {r - 1, r + 1} and len(hr) == N * N * ((r > 0) + (r < world - 1))
+        for i in range(nloc):                                 # ascending order inside rows survives the map
+            seg = cg[rp[i]:rp[i + 1]]
+            assert np.all(np.diff(seg) > 0)
+
+
+def test_emulated_distributed_cg_matches_global(O):
+    """NumPy emulation of the kernels' data flow: per-rank SpMV with halo gather from the peers' vectors and a
+    rank-ordered sum of per-rank partial dots.  Must reproduce the oracle's global CG history to 1e-12."""
+    N, world = 6, 3
+    bounds, rs, blocks = _blocks(N, world)
+    n = N ** 3
+    xo, so = O.cg(O.get_div_grad(N, N, N), np.ones(n), atol=0.0, rtol=1e-10)
+    r = [np.ones(rs[k + 1] - rs[k]) for k in range(world)]
+    p = [v.copy() for v in r]
+    x = [np.zeros_like(v) for v in r]
+    gamma = sum(float(v @ v) for v in r)
+    hist = [np.sqrt(gamma)]
+    for it in range(so["niter"]):
+        Ap, pAp = [], 0.0
+        for k, (rp, cg, cl, va, hr, ho) in enumerate(blocks):
+            nloc = len(rp) - 1
+            ext = np.concatenate([p[k], np.array([p[hr[h]][ho[h]] for h in range(len(hr))])])
+            A = sp.csr_matrix((va, cl, rp), shape=(nloc, nloc + len(hr)))
+            Ap.append(A @ ext)
+        pAp = sum(float(p[k] @ Ap[k]) for k in range(world))
+        alpha = gamma / pAp
+        for k in range(world):
+            x[k] += alpha * p[k]
+            r[k] -= alpha * Ap[k]
+        g2 = sum(float(v @ v) for v in r)
+        hist.append(np.sqrt(g2))
+        beta = g2 / gamma
+        gamma = g2
+        for k in range(world):
+            p[k] = r[k] + beta * p[k]
+    assert np.allclose(hist, so["residuals"], rtol=1e-10)
+    assert np.allclose(np.concatenate(x), xo, rtol=1e-9)
+
+
+def test_handle_exchange_plumbing_gloo_world2(tmp_path):
+    """The Python side of the IPC exchange (all_gather_object of fixed-size blobs in rank order) under gloo."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path[:0] = [{ROOT!r}, {os.path.join(ROOT, 'krylov.jl_b200')!r}]
+        import numpy as np, torch.distributed as dist
+        from krylov_b200 import dist as D, problems as P
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        N = 6
+        bounds = D.slab_bounds(N, world)
+        rs = np.array([b[0] * N * N for b in bounds] + [N ** 3])
+        rp, ci, va = P.div_grad_csr(N, k_lo=bounds[rank][0], k_hi=bounds[rank][1])
+        cl, hr, ho = D.localize_columns(ci, rs, rank)
+        blob = bytes([rank]) * 256
+        blobs = [None] * world
+        dist.all_gather_object(blobs, blob)
+        allb = b"".join(blobs)
+        assert len(allb) == 256 * world and all(allb[256 * k] == k for k in range(world))
+        tot = [None] * world
+        dist.all_gather_object(tot, (len(rp) - 1, len(hr)))
+        assert sum(t[0] for t in tot) == N ** 3 and all(t[1] == N * N for t in tot)
+        dist.barrier(); dist.destroy_process_group()
+        print("ok", rank)
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
