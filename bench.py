@@ -204,7 +204,14 @@ def main():
     B = algorithmic_bytes_cg(n, nnz)
     peak, peak_src = hbm_peak()
     achieved = B * its / (ms * 1e-3) / 1e9
-    rnorm = ws.stats  # noqa: F841
+    # per-kernel breakdown: launches 8..39 of each fused kernel bracketed by CUDA events inside the library
+    ws.solve(None, b, time_kernels=True, **solve_kw)
+    k1_ms, k2_ms, timed = ws.kernel_times
+    B_k1 = nnz * 12 + (n + 1) * 4 + 4 * n * 8      # matrix + read r,p + write p,Ap
+    B_k2 = 6 * n * 8                               # read x,r,p,Ap + write x,r
+    kernels = dict(cg_k1_tma=dict(ms=k1_ms, bytes=B_k1, GBs=B_k1 / (k1_ms * 1e-3) / 1e9 if k1_ms else None),
+                   cg_k2=dict(ms=k2_ms, bytes=B_k2, GBs=B_k2 / (k2_ms * 1e-3) / 1e9 if k2_ms else None),
+                   timed_iterations=timed, share_k1=k1_ms / (k1_ms + k2_ms) if k1_ms else None)
 
     # ---- end-to-end arm: C ABI with pinned host buffers ---------------------
     wsh = kb.CgWorkspace(n, n, np.float64, device="host")
@@ -234,7 +241,8 @@ def main():
                             matrix_upload_s=round(upload_s, 3), matrix_generate_s=round(gen_s, 3)),
                 roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
                               peak_source=peak_src, bytes_per_iteration=B,
-                              note="unit = one fused CG iteration (cg_k1 + cg_k2); B_cg from SURVEY.md 8(d)"),
+                              note="unit = one fused CG iteration (cg_k1 + cg_k2); B_cg from SURVEY.md 8(d)",
+                              kernels=kernels),
                 clocks=clocks, e2e=e2e, gpu_launches=int(launches))
     if not args.no_cpu:
         try:

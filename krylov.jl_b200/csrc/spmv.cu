@@ -144,8 +144,10 @@ template <class T> void csr_plan(Ctx& c, Csr<T>& A) {
     const int s = atoi(es), cps = atoi(ec);
     if (s >= 1 && s <= 8 && cps >= 1 && cps <= 8 && L.total_bytes(s) * cps <= 226 * 1024) { A.tma_ok = true; A.stages = s; per_sm = cps; }
   }
-  // default: 3 CTAs/SM x 3 stages when it fits (27 warps/SM hide the gather latency better than 2 x 4)
-  if (!A.tma_ok && L.total_bytes(3) * 3 <= 226 * 1024) { A.tma_ok = true; A.stages = 3; per_sm = 3; }
+  // default: 3 CTAs/SM x 2 stages when it fits.  Measured on cfg2 (profiles/r1_sweep_k1.txt): K1 = 219 us at
+  // 2 stages x 3 CTAs, 227 us at 3x3, 284-298 us at any depth with 2 CTAs: the gather latency wants 27 warps/SM,
+  // and a shallower ring leaves more of the 228 KB to L1 for the gathered vectors.
+  if (!A.tma_ok && L.total_bytes(2) * 3 <= 226 * 1024) { A.tma_ok = true; A.stages = 2; per_sm = 3; }
   for (int s = 4; s >= 2 && !A.tma_ok; s--)
     if (L.total_bytes(s) <= two_cta) { A.tma_ok = true; A.stages = s; per_sm = 2; }
   for (int s = 4; s >= 2 && !A.tma_ok; s--)

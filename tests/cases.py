@@ -38,8 +38,10 @@ def build(name):
         A = _mat(P.div_grad_csr(16)); return "minres", A, np.ones(A.shape[0]), {}, f64
     if name == "minres_shift":
         A = _mat(P.div_grad_csr(10)); return "minres", A, np.ones(A.shape[0]), dict(lambda_=0.5, atol=1e-10, rtol=1e-10), f64
-    if name == "minres_indefinite":              # almost_singular family: A - 5I
-        A = sp.csr_matrix(_mat(P.div_grad_csr(8)) - 5 * sp.identity(512)); return "minres", A, A @ np.ones(512), dict(itmax=400), f64
+    if name == "minres_indefinite":              # symmetric_indefinite(40), test/test_utils.jl:26-31
+        n = 40
+        A = sp.csr_matrix(sp.diags([np.ones(n - 1), np.ones(n), np.ones(n - 1)], [-1, 0, 1]))
+        return "minres", A, A @ np.arange(1.0, n + 1), {}, f64
     raise KeyError(name)
 
 

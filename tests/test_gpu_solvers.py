@@ -36,7 +36,8 @@ def history_sensitivity(O, name):
     solver, A, b, kw, dt = cases.build(name)
     x0, s0 = getattr(O, solver)(A, b, dtype=dt, **kw)
     sign = np.random.default_rng(0).choice([-1.0, 1.0], size=len(b))
-    x1, s1 = getattr(O, solver)(A, b * (1 + 2e-16 * sign), dtype=dt, **kw)
+    ulp = 2e-16 if dt == np.float64 else 1.2e-7
+    x1, s1 = getattr(O, solver)(A, (b * (1 + ulp * sign)).astype(dt), dtype=dt, **kw)
     r0, r1 = np.asarray(s0["residuals"], float), np.asarray(s1["residuals"], float)
     k = min(len(r0), len(r1))
     sens = np.zeros(len(r0))
@@ -62,10 +63,14 @@ def check_against(st, x, g_res, g_niter, g_status, dt, xo=None, sens=None):
             xtol = 1e-6 if sens is None else max(1e-6, 10 * float(sens[np.isfinite(sens)].max()))
             assert np.linalg.norm(x - xo) <= xtol * np.linalg.norm(xo)
     else:
-        # Float32: sequential fp32 dots (oracle) vs tree reductions (GPU) differ by ~sqrt(n)*eps32 per dot
+        # Float32: sequential fp32 dots (oracle) vs tree reductions (GPU) differ by ~sqrt(n)*eps32 per dot.
+        # Bar: 1e-3 relative, or 10x the oracle's own sensitivity to a 1-ulp(fp32) perturbation of b where that
+        # is larger (fp32 BiCGSTAB histories are erratic); iteration count within +-2.
         assert abs(st.niter - g_niter) <= 2
-        k = min(len(res), len(g_res)) - 3
-        assert np.allclose(res[:k], g_res[:k], rtol=5e-2, atol=1e-5 * g_res[0])
+        k = min(len(res), len(g_res))
+        tol = np.maximum(1e-3, 10 * sens[:k]) if sens is not None else np.full(k, 5e-2)
+        ok = np.abs(res[:k] - g_res[:k]) <= tol * np.abs(g_res[:k]) + 1e-5 * abs(g_res[0])
+        assert np.all(ok), f"fp32 history deviates at iteration {np.argmax(~ok)}"
 
 
 @pytest.mark.parametrize("name", cases.NAMES)
@@ -74,7 +79,7 @@ def test_parity_with_golden_and_oracle(kb, O, name):
     x, st, launches = run_gpu(kb, name)
     g = GOLD[name]
     xo, so = cases.run_oracle(O, name)
-    sens = history_sensitivity(O, name) if dt == np.float64 else None
+    sens = history_sensitivity(O, name)
     check_against(st, x, np.asarray(g["residuals"]), g["niter"], g["status"], dt, xo if dt == np.float64 else None, sens)
     check_against(st, x, np.asarray(so["residuals"]), so["niter"], so["status"], dt, None, sens)
     assert st.solved == so["solved"] and st.inconsistent == so["inconsistent"]
@@ -149,7 +154,7 @@ def test_cg_radius_preconditioner_warmstart(kb, O):
     assert st.niter == so["niter"] and np.allclose(st.residuals, so["residuals"], rtol=1e-6, atol=1e-9 * so["residuals"][0])
     A, b = O.sparse_laplacian(10)
     x, st = kb.cg(A, b)
-    x0 = x + 1e-3 * np.sin(np.arange(len(x)))
+    x0 = x * (1 + 1e-4)                                # interfaces/test/C/test_api.c:259-284: warm start from ~x*
     xw, sw = kb.cg(A, b, x0, history=True)
     xo, so = O.cg(A, b, x0=x0)
     assert sw.niter == so["niter"] < st.niter and np.allclose(sw.residuals, so["residuals"], rtol=1e-6)
