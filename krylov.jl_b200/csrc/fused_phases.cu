@@ -1,0 +1,368 @@
+// fused_phases.cu -- fused iteration phases of bicgstab!, minres! and gmres!
+// (SURVEY.md section 8a phase structures).  Each phase is ONE launch: an SpMV
+// or a streaming pass whose epilogue applies the adjacent axpy/axpby/scal
+// updates and accumulates the dot products the next scalar needs; the CTA that
+// finishes the grid reduction derives that scalar on the device, so the phases
+// of one iteration chain through device memory and the host reads the scalar
+// block back once (BiCGSTAB, GMRES) or twice (MINRES) per iteration to run the
+// reference's stopping logic unchanged.
+//
+// Arithmetic is the reference's, operation by operation (non-contracted
+// mul/add in the same order as the kaxpy!/kaxpby!/kscal! sequence it replaces),
+// so these paths produce the same vectors as the primitive path given the same
+// scalars; tests assert that equality.
+#include "kb_internal.h"
+#include "spmv_tiles.cuh"
+
+namespace kb {
+
+// ---------------------------------------------------------------------------
+// generic launchers
+// ---------------------------------------------------------------------------
+template <class T, int K, class Epi, class Fin>
+__global__ void __launch_bounds__(kTileThreads) spmv_epi_tma(Csr<T> A, const T* __restrict__ x, Epi epi, Fin fin, T* part,
+                                                             unsigned* ticket) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ T sm[32];
+  T d[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) d[k] = T(0);
+  spmv_tiles_run<T>(
+      A, smem, [&](int j) { return __ldg(&x[j]); }, NoRowBegin(), [&](int row, T acc, int) { epi(row, acc, d); });
+  T mine[K], tot[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) mine[k] = block_sum(d[k], sm);
+  if (grid_sum_last<T, K>(mine, part, ticket, sm, tot) && threadIdx.x == 0) fin(tot);
+}
+
+template <class T, int K, class Epi, class Fin>
+__global__ void __launch_bounds__(kBlock) spmv_epi_rows(Csr<T> A, const T* __restrict__ x, Epi epi, Fin fin, T* part,
+                                                        unsigned* ticket) {
+  __shared__ T sm[32];
+  T d[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) d[k] = T(0);
+  const int stride = gridDim.x * blockDim.x;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < A.n; row += stride) {
+    const int kb = A.rowptr[row], ke = A.rowptr[row + 1];
+    T acc = T(0);
+    for (int k = kb; k < ke; k++) acc = add_rn(acc, mul_rn(A.val[k], __ldg(&x[A.colind[k]])));
+    epi(row, acc, d);
+  }
+  T mine[K], tot[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) mine[k] = block_sum(d[k], sm);
+  if (grid_sum_last<T, K>(mine, part, ticket, sm, tot) && threadIdx.x == 0) fin(tot);
+}
+
+template <class T, int K, class Body, class Fin>
+__global__ void __launch_bounds__(kBlock) stream_epi(int n, Body body, Fin fin, T* part, unsigned* ticket) {
+  __shared__ T sm[32];
+  T d[K > 0 ? K : 1];
+#pragma unroll
+  for (int k = 0; k < (K > 0 ? K : 1); k++) d[k] = T(0);
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < n; i += 2 * stride) {      // two independent elements per trip
+    body(i, d);
+    body(i + stride, d);
+  }
+  if (i < n) body(i, d);
+  if (K > 0) {
+    T mine[K > 0 ? K : 1], tot[K > 0 ? K : 1];
+#pragma unroll
+    for (int k = 0; k < K; k++) mine[k] = block_sum(d[k], sm);
+    if (grid_sum_last<T, (K > 0 ? K : 1)>(mine, part, ticket, sm, tot) && threadIdx.x == 0) fin(tot);
+  }
+}
+
+struct NoFin {
+  template <class T> __device__ void operator()(const T*) const {}
+};
+
+template <class T, int K, class Epi, class Fin>
+static void launch_spmv_epi(Ctx& c, const Csr<T>& A, const T* x, Epi epi, Fin fin, int ticket) {
+  if (A.n <= 0) return;
+  if (A.tma_ok) {
+    static bool attr = false;
+    if (!attr) { KB_CUDA(cudaFuncSetAttribute(spmv_epi_tma<T, K, Epi, Fin>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+    spmv_epi_tma<T, K, Epi, Fin><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, x, epi, fin, (T*)c.partials, c.tickets + ticket);
+  } else {
+    spmv_epi_rows<T, K, Epi, Fin><<<stream_grid(A.n, 1, 8), kBlock, 0, c.stream>>>(A, x, epi, fin, (T*)c.partials, c.tickets + ticket);
+  }
+  KB_CUDA(cudaGetLastError());
+  c.launches++;
+}
+
+template <class T, int K, class Body, class Fin>
+static void launch_stream(Ctx& c, int n, Body body, Fin fin, int ticket) {
+  if (n <= 0) return;
+  stream_epi<T, K, Body, Fin><<<stream_grid(n, 2, 8), kBlock, 0, c.stream>>>(n, body, fin, (T*)c.partials, c.tickets + ticket);
+  KB_CUDA(cudaGetLastError());
+  c.launches++;
+}
+
+template <class S> static S* state_buf(void*& dev, void*& host) {
+  if (!dev) {
+    KB_CUDA(cudaMalloc(&dev, 1024));
+    KB_CUDA(cudaMemset(dev, 0, 1024));
+    KB_CUDA(cudaHostAlloc(&host, 2048, cudaHostAllocDefault));
+  }
+  static_assert(sizeof(S) <= 1024, "state block too large");
+  return (S*)dev;
+}
+
+// ===========================================================================
+// BiCGSTAB  (src/bicgstab.jl:215-256, M = N = I)
+// ===========================================================================
+template <class T> struct BicgState { T rho, alpha, omega, beta, next_rho, rNorm, cv, ts, tt, cr, rr; };
+
+template <class T> struct BicgK1Epi {   // v = A p ; <c, v>
+  T* v; const T* c;
+  __device__ __forceinline__ void operator()(int row, T acc, T* d) const { v[row] = acc; d[0] += __ldg(&c[row]) * acc; }
+};
+template <class T> struct BicgK1Fin {   // alpha = rho / <c, v>          (bicgstab.jl:223)
+  BicgState<T>* s;
+  __device__ void operator()(const T* tot) const { s->cv = tot[0]; s->alpha = div_rn(s->rho, tot[0]); }
+};
+template <class T> struct BicgK2Body {  // s = r - alpha v               (bicgstab.jl:224-225)
+  const T* r; const T* v; T* sv; const BicgState<T>* s;
+  __device__ __forceinline__ void operator()(int i, T*) const { sv[i] = add_rn(r[i], mul_rn(-s->alpha, v[i])); }
+};
+template <class T> struct BicgK3Epi {   // t = A s ; <t,s>, <t,t>
+  T* t; const T* sv;
+  __device__ __forceinline__ void operator()(int row, T acc, T* d) const {
+    t[row] = acc; d[0] += acc * __ldg(&sv[row]); d[1] += acc * acc;
+  }
+};
+template <class T> struct BicgK3Fin {   // omega = <t,s>/<t,t>           (bicgstab.jl:230)
+  BicgState<T>* s;
+  __device__ void operator()(const T* tot) const { s->ts = tot[0]; s->tt = tot[1]; s->omega = div_rn(tot[0], tot[1]); }
+};
+template <class T> struct BicgK4Body {  // x += alpha p ; x += omega s ; r = s - omega t ; <c,r>, <r,r>   (:226,231-234,240)
+  T* x; const T* p; const T* sv; const T* t; const T* c; T* r; const BicgState<T>* s;
+  __device__ __forceinline__ void operator()(int i, T* d) const {
+    const T si = sv[i];
+    x[i] = add_rn(add_rn(x[i], mul_rn(s->alpha, p[i])), mul_rn(s->omega, si));
+    const T rn = add_rn(si, mul_rn(-s->omega, t[i]));
+    r[i] = rn;
+    d[0] += c[i] * rn;
+    d[1] += rn * rn;
+  }
+};
+template <class T> struct BicgK4Fin {   // next_rho, beta = (next_rho/rho)(alpha/omega), rNorm   (:234-235,240)
+  BicgState<T>* s;
+  __device__ void operator()(const T* tot) const {
+    s->cr = tot[0]; s->rr = tot[1];
+    s->next_rho = tot[0];
+    s->beta = mul_rn(div_rn(tot[0], s->rho), div_rn(s->alpha, s->omega));
+    s->rNorm = sqrt_rn(tot[1]);
+    s->rho = tot[0];                       // loop top of the next iteration: rho = next_rho (:218)
+  }
+};
+template <class T> struct BicgK5Body {  // p -= omega v ; p = r + beta p   (bicgstab.jl:236-237)
+  T* p; const T* r; const T* v; const BicgState<T>* s;
+  __device__ __forceinline__ void operator()(int i, T*) const {
+    p[i] = add_rn(r[i], mul_rn(s->beta, add_rn(p[i], mul_rn(-s->omega, v[i]))));
+  }
+};
+
+// One fused BiCGSTAB iteration.  In: next_rho of the previous iteration (host value, written to the device
+// block at iteration 1 only).  Out (host): alpha, omega, next_rho, rNorm -- one read-back.
+template <class T>
+void bicgstab_fused_iteration(Workspace<T>& ws, const Csr<T>& A, const T* cvec, bool first, T rho_in, T* alpha, T* omega,
+                              T* next_rho, T* rNorm) {
+  Ctx& c = ws.ctx;
+  const int n = ws.n;
+  typedef BicgState<T> St;
+  St* S = state_buf<St>(ws.fused_state, ws.fused_host);
+  St* H = (St*)ws.fused_host;
+  if (first) {
+    memset(H, 0, sizeof(St));
+    H->rho = rho_in;
+    KB_CUDA(cudaMemcpyAsync(S, H, sizeof(St), cudaMemcpyHostToDevice, c.stream));
+  }
+  T* t = ws.qd;    // t == d == qd when M = I  (bicgstab.jl:153-154)
+  launch_spmv_epi<T, 1>(c, A, ws.p, BicgK1Epi<T>{ws.v, cvec}, BicgK1Fin<T>{S}, 4);
+  launch_stream<T, 0>(c, n, BicgK2Body<T>{ws.r, ws.v, ws.s, S}, NoFin(), 5);
+  launch_spmv_epi<T, 2>(c, A, ws.s, BicgK3Epi<T>{t, ws.s}, BicgK3Fin<T>{S}, 4);
+  launch_stream<T, 2>(c, n, BicgK4Body<T>{ws.x, ws.p, ws.s, t, cvec, ws.r, S}, BicgK4Fin<T>{S}, 5);
+  KB_CUDA(cudaMemcpyAsync(H + 1, S, sizeof(St), cudaMemcpyDeviceToHost, c.stream));   // scalars of this iteration
+  launch_stream<T, 0>(c, n, BicgK5Body<T>{ws.p, ws.r, ws.v, S}, NoFin(), 5);
+  c.sync();
+  *alpha = H[1].alpha; *omega = H[1].omega; *next_rho = H[1].next_rho; *rNorm = H[1].rNorm;
+}
+
+// ===========================================================================
+// MINRES  (src/minres.jl:285-333,389-409, M = I)
+// ===========================================================================
+template <class T> struct MinresState { T vy, alpha, beta2, xx; };
+
+template <class T> struct MinresK1Epi {  // y = (A v [+ lambda v]) / beta [- (beta/oldbeta) r1] ; <v, y>   (:289-294)
+  T* y; const T* v; const T* r1; T lambda, inv_beta, c1; int iter;
+  __device__ __forceinline__ void operator()(int row, T acc, T* d) const {
+    const T vr = __ldg(&v[row]);
+    T t = acc;
+    if (lambda != T(0)) t = add_rn(t, mul_rn(lambda, vr));
+    t = mul_rn(inv_beta, t);
+    if (iter >= 2) t = add_rn(t, mul_rn(c1, __ldg(&r1[row])));
+    y[row] = t;
+    d[0] += vr * t;
+  }
+};
+template <class T> struct MinresK1Fin {  // alpha = <v,y> / beta
+  MinresState<T>* s; T beta;
+  __device__ void operator()(const T* tot) const { s->vy = tot[0]; s->alpha = div_rn(tot[0], beta); }
+};
+template <class T> struct MinresK2Body { // y -= (alpha/beta) r2 ; w update (:295-307) ; <y,y> (:313, v == r2 <- y)
+  T* y; const T* r2; T* w; const T* w2; const MinresState<T>* s;
+  T beta, inv_beta, cs, sn, deltabar, eps; int iter;
+  __device__ __forceinline__ void operator()(int i, T* d) const {
+    const T alpha = s->alpha;
+    const T vi = r2[i];                                     // v == r2 (M = I), value BEFORE r2 <- y
+    const T yn = add_rn(y[i], mul_rn(div_rn(-alpha, beta), vi));
+    y[i] = yn;
+    d[0] += yn * yn;
+    if (iter == 1) {
+      w[i] = div_rn(vi, beta);                              // kdivcopy!(n, w, v, beta), w == w2
+    } else {
+      const T delta = add_rn(mul_rn(cs, deltabar), mul_rn(sn, alpha));
+      T wv = w[i];                                          // w == w1
+      if (iter >= 3) wv = mul_rn(-eps, wv);
+      wv = add_rn(wv, mul_rn(-delta, w2[i]));
+      wv = add_rn(wv, mul_rn(inv_beta, vi));
+      w[i] = wv;
+    }
+  }
+};
+template <class T> struct MinresK2Fin {
+  MinresState<T>* s;
+  __device__ void operator()(const T* tot) const { s->beta2 = tot[0]; }
+};
+template <class T> struct MinresK3Body { // w /= gamma ; x += phi w ; <x,x>   (:333,389,409)
+  T* w; T* x; T inv_gamma, phi;
+  __device__ __forceinline__ void operator()(int i, T* d) const {
+    const T wv = mul_rn(inv_gamma, w[i]);
+    w[i] = wv;
+    const T xn = add_rn(x[i], mul_rn(phi, wv));
+    x[i] = xn;
+    d[0] += xn * xn;
+  }
+};
+template <class T> struct MinresK3Fin {
+  MinresState<T>* s;
+  __device__ void operator()(const T* tot) const { s->xx = tot[0]; }
+};
+
+// Phase A of a fused MINRES iteration: Lanczos step.  Rotates r1/r2/y by pointer (the reference copies).
+// Returns alpha and beta_new^2 = <r2,r2>.
+template <class T>
+void minres_fused_lanczos(Workspace<T>& ws, const Csr<T>& A, int iter, T lambda, T beta, T oldbeta, T cs, T sn, T deltabar,
+                          T eps_rot, T* w, T* alpha, T* beta2) {
+  Ctx& c = ws.ctx;
+  const int n = ws.n;
+  typedef MinresState<T> St;
+  St* S = state_buf<St>(ws.fused_state, ws.fused_host);
+  St* H = (St*)ws.fused_host;
+  const T inv_beta = T(1) / beta;
+  const T c1 = iter >= 2 ? -beta / oldbeta : T(0);
+  launch_spmv_epi<T, 1>(c, A, ws.r2, MinresK1Epi<T>{ws.y, ws.r2, ws.r1, lambda, inv_beta, c1, iter}, MinresK1Fin<T>{S, beta}, 4);
+  launch_stream<T, 1>(c, n, MinresK2Body<T>{ws.y, ws.r2, w, ws.w2, S, beta, inv_beta, cs, sn, deltabar, eps_rot, iter},
+                      MinresK2Fin<T>{S}, 5);
+  KB_CUDA(cudaMemcpyAsync(H, S, sizeof(St), cudaMemcpyDeviceToHost, c.stream));
+  c.sync();
+  *alpha = H->alpha; *beta2 = H->beta2;
+  T* old_r1 = ws.r1;          // r1 <- r2 ; r2 <- y   (minres.jl:309-310) by rotating the bindings
+  ws.r1 = ws.r2; ws.r2 = ws.y; ws.y = old_r1;
+}
+
+// Phase B: w /= gamma ; x += phi w ; returns ||x||.
+template <class T>
+T minres_fused_update(Workspace<T>& ws, T* w, T gamma, T phi) {
+  Ctx& c = ws.ctx;
+  typedef MinresState<T> St;
+  St* S = state_buf<St>(ws.fused_state, ws.fused_host);
+  St* H = (St*)ws.fused_host;
+  launch_stream<T, 1>(c, ws.n, MinresK3Body<T>{w, ws.x, T(1) / gamma, phi}, MinresK3Fin<T>{S}, 5);
+  KB_CUDA(cudaMemcpyAsync(H, S, sizeof(St), cudaMemcpyDeviceToHost, c.stream));
+  c.sync();
+  return std::sqrt(H->xx);
+}
+
+// ===========================================================================
+// GMRES  (src/gmres.jl:255-262,274, M = N = I, no reorthogonalization)
+// ===========================================================================
+constexpr int kGmresMaxFused = 120;    // h[] slots in the state block
+template <class T> struct GmresState { T hbis2; T h[kGmresMaxFused]; };
+
+template <class T> struct GmresSpmvEpi {  // w = A v_k ; h_1 = <v_1, w>
+  T* w; const T* v1;
+  __device__ __forceinline__ void operator()(int row, T acc, T* d) const { w[row] = acc; d[0] += __ldg(&v1[row]) * acc; }
+};
+template <class T> struct GmresHFin {
+  GmresState<T>* s; int slot;            // slot < 0: ||q||^2
+  __device__ void operator()(const T* tot) const { if (slot >= 0) s->h[slot] = tot[0]; else s->hbis2 = tot[0]; }
+};
+template <class T> struct GmresMgsBody {  // q -= h_i v_i ; then <v_{i+1}, q> or <q, q>   (gmres.jl:259-262,274)
+  T* q; const T* vi; const T* vnext; const GmresState<T>* s; int i;
+  __device__ __forceinline__ void operator()(int j, T* d) const {
+    const T qn = add_rn(q[j], mul_rn(-s->h[i], vi[j]));
+    q[j] = qn;
+    d[0] += (vnext ? vnext[j] : qn) * qn;
+  }
+};
+
+// Arnoldi step k (1-based inner_iter): w = A V[k]; MGS against V[1..k]; returns h[0..k-1] and Hbis.
+template <class T>
+void gmres_fused_arnoldi(Workspace<T>& ws, const Csr<T>& A, int k, T* h_out, T* Hbis) {
+  Ctx& c = ws.ctx;
+  const int n = ws.n;
+  typedef GmresState<T> St;
+  St* S = state_buf<St>(ws.fused_state, ws.fused_host);
+  St* H = (St*)ws.fused_host;
+  T* q = ws.w;                                              // q == w when M = I (gmres.jl:150)
+  launch_spmv_epi<T, 1>(c, A, ws.V[k - 1], GmresSpmvEpi<T>{q, ws.V[0]}, GmresHFin<T>{S, 0}, 4);
+  for (int i = 0; i < k; i++) {
+    const T* vnext = (i + 1 < k) ? ws.V[i + 1] : nullptr;
+    launch_stream<T, 1>(c, n, GmresMgsBody<T>{q, ws.V[i], vnext, S, i}, GmresHFin<T>{S, (i + 1 < k) ? i + 1 : -1}, 5);
+  }
+  KB_CUDA(cudaMemcpyAsync(H, S, sizeof(T) * (size_t)(k + 1), cudaMemcpyDeviceToHost, c.stream));
+  c.sync();
+  for (int i = 0; i < k; i++) h_out[i] = H->h[i];
+  *Hbis = std::sqrt(H->hbis2);
+}
+
+// xr += sum_i y_i V[i], accumulated in index order in one pass (gmres.jl:348-350)
+template <class T, int NV> struct MultiAxpyBody {
+  T* xr; const T* v[NV]; T y[NV]; int cnt;
+  __device__ __forceinline__ void operator()(int j, T*) const {
+    T acc = xr[j];
+#pragma unroll
+    for (int i = 0; i < NV; i++) if (i < cnt) acc = add_rn(acc, mul_rn(y[i], v[i][j]));
+    xr[j] = acc;
+  }
+};
+template <class T>
+void gmres_fused_update_x(Workspace<T>& ws, T* xr, int k, const T* y) {
+  constexpr int NV = 8;
+  for (int base = 0; base < k; base += NV) {
+    MultiAxpyBody<T, NV> body;
+    body.xr = xr; body.cnt = std::min(NV, k - base);
+    for (int i = 0; i < NV; i++) { body.v[i] = ws.V[std::min(base + i, k - 1)]; body.y[i] = (base + i < k) ? y[base + i] : T(0); }
+    launch_stream<T, 0>(ws.ctx, ws.n, body, NoFin(), 5);
+  }
+}
+
+int gmres_fused_max() { return kGmresMaxFused; }
+
+#define INST(T)                                                                                                      \
+  template void bicgstab_fused_iteration<T>(Workspace<T>&, const Csr<T>&, const T*, bool, T, T*, T*, T*, T*);         \
+  template void minres_fused_lanczos<T>(Workspace<T>&, const Csr<T>&, int, T, T, T, T, T, T, T, T*, T*, T*);          \
+  template T minres_fused_update<T>(Workspace<T>&, T*, T, T);                                                        \
+  template void gmres_fused_arnoldi<T>(Workspace<T>&, const Csr<T>&, int, T*, T*);                                   \
+  template void gmres_fused_update_x<T>(Workspace<T>&, T*, int, const T*);
+INST(double)
+INST(float)
+#undef INST
+
+}  // namespace kb

@@ -203,6 +203,17 @@ template <class T> void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const S
                                       double start_time, bool& solved, bool& tired, bool& zero_curvature,
                                       bool& inconsistent, bool& user_exit, bool& overtimed, int& iter);
 
+// Fused iteration phases of BiCGSTAB / MINRES / GMRES (fused_phases.cu); eligible when A is a CSR operator,
+// M = N = I (and for GMRES no reorthogonalization).
+template <class T> void bicgstab_fused_iteration(Workspace<T>& ws, const Csr<T>& A, const T* cvec, bool first, T rho_in, T* alpha,
+                                                 T* omega, T* next_rho, T* rNorm);
+template <class T> void minres_fused_lanczos(Workspace<T>& ws, const Csr<T>& A, int iter, T lambda, T beta, T oldbeta, T cs, T sn,
+                                             T deltabar, T eps_rot, T* w, T* alpha, T* beta2);
+template <class T> T minres_fused_update(Workspace<T>& ws, T* w, T gamma, T phi);
+template <class T> void gmres_fused_arnoldi(Workspace<T>& ws, const Csr<T>& A, int k, T* h_out, T* Hbis);
+template <class T> void gmres_fused_update_x(Workspace<T>& ws, T* xr, int k, const T* y);
+int gmres_fused_max();
+
 double now_seconds();
 
 }  // namespace kb

@@ -329,10 +329,15 @@ void bicgstab_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c_
   if (next_rho == 0) { finish_early(false, "Breakdown bᴴc = 0"); return; }
   bool solved = rNorm <= eps_tol, tired = iter >= itmax, breakdown = false, user_exit = false, overtimed = false;
   std::string status = "unknown";
+  const bool fusedB = o.fused && A.kind == LinOp<T>::CSR && MisI && NisI;
 
   while (!(solved || tired || breakdown || user_exit || overtimed)) {
     iter = iter + 1;
     rho = next_rho;
+    if (fusedB) {
+      // 5 launches, scalars chained on the device, one read-back (fused_phases.cu)
+      bicgstab_fused_iteration<T>(ws, *A.csr, cvec, iter == 1, rho, &alpha, &omega, &next_rho, &rNorm);
+    } else {
     if (!NisI) op_apply(c, N, p, y, ldiv);
     op_apply(c, A, y, q);
     if (MisI) k_copy<T>(c, n, v, q); else op_apply(c, M, q, v, ldiv);    // bicgstab.jl:222 (unguarded mulorldiv!)
@@ -352,6 +357,7 @@ void bicgstab_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c_
     k_axpy<T>(c, n, -omega, v, p);
     k_axpby<T>(c, n, T(1), r, beta, p);
     rNorm = k_nrm2<T>(c, n, r);
+    }
     if (history) stats.residuals.push_back(rNorm);
     const bool resid_decrease_mach = (rNorm + T(1) <= T(1));
     if (o.callback) { c.sync(); stats.niter = iter; user_exit = o.callback(&ws, o.callback_user) != 0; }
@@ -444,6 +450,7 @@ void gmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>
   if (o.verbose > 0) printf("%5s  %5s  %7s  %7s  %5s\n", "pass", "k", "‖rₖ‖", "hₖ₊₁.ₖ", "timer");
   if (kdisplay(iter, o.verbose)) printf("%5d  %5d  %7.1e  %7s  %.2fs\n", npass, iter, (double)rNorm, "✗ ✗ ✗ ✗", now_seconds() - start_time);
   const T btol = std::pow(eps_of<T>(), T(0.75));              // gmres.jl:195
+  const bool fusedG = o.fused && A.kind == LinOp<T>::CSR && MisI && NisI && !reorth;
   bool breakdown = false, inconsistent = false, solved = rNorm <= eps_tol, tired = iter >= itmax;
   bool inner_tired = inner_iter >= inner_itmax, user_exit = false, overtimed = false;
   std::string status = "unknown";
@@ -483,6 +490,12 @@ void gmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>
         s.push_back(T(0)); c.push_back(T(0));
         stats.allocation_timer += now_seconds() - t0;
       }
+      T Hbis;
+      if (fusedG && inner_iter <= gmres_fused_max()) {
+        // 1 + k launches: SpMV fused with the first MGS dot, then one launch per MGS step that applies
+        // q -= h_i v_i and accumulates the next dot (or ||q||^2); one read-back of the whole R column.
+        gmres_fused_arnoldi<T>(ws, *A.csr, inner_iter, &R[nr], &Hbis);
+      } else {
       T* vk = V[inner_iter - 1];
       T* p = NisI ? vk : ws.pp;
       if (!NisI) op_apply(cx, N, vk, p, ldiv);
@@ -499,7 +512,8 @@ void gmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>
           k_axpy<T>(cx, n, -Htmp, V[i], q);
         }
       }
-      const T Hbis = k_nrm2<T>(cx, n, q);
+      Hbis = k_nrm2<T>(cx, n, q);
+      }
       for (int i = 0; i < inner_iter - 1; i++) {              // gmres.jl:280-284
         const T Rtmp = c[i] * R[nr + i] + s[i] * R[nr + i + 1];
         R[nr + i + 1] = s[i] * R[nr + i] - c[i] * R[nr + i + 1];
@@ -541,7 +555,8 @@ void gmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>
       if (std::fabs(R[pos - 1]) <= btol) { y[i - 1] = T(0); inconsistent = true; }
       else y[i - 1] = y[i - 1] / R[pos - 1];
     }
-    for (int i = 0; i < inner_iter; i++) k_axpy<T>(cx, n, y[i], V[i], xr);
+    if (fusedG) gmres_fused_update_x<T>(ws, xr, inner_iter, y.data());      // same sums, same order, one pass per 8 vectors
+    else for (int i = 0; i < inner_iter; i++) k_axpy<T>(cx, n, y[i], V[i], xr);
     if (!NisI) { k_copy<T>(cx, n, ws.pp, xr); op_apply(cx, N, ws.pp, xr, ldiv); }
     if (restart) k_axpy<T>(cx, n, T(1), xr, x);
     inner_itmax = inner_itmax - inner_iter;
@@ -640,17 +655,30 @@ void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T
   stats.indefinite = false;
   T delta_w = 0, beta_w = 0, zeta_k = 0, zeta_km1 = 0;
   std::string status = "unknown";
+  const bool fusedM = o.fused && A.kind == LinOp<T>::CSR && MisI && !linesearch;
 
   while (!(solved || tired || ill_cond || user_exit || overtimed)) {
     iter = iter + 1;
+    T alpha, delta;
+    T* w;
+    if (fusedM) {
+      // 2 launches + 1 read-back: SpMV with the y recurrence and <v,y>; then y -= (alpha/beta) r2, the w update
+      // and <y,y>; r1/r2/y rotate by pointer instead of the two copies (fused_phases.cu)
+      w = (iter == 1) ? ws.w2 : ws.w1;
+      T beta2;
+      minres_fused_lanczos<T>(ws, *A.csr, iter, lambda, beta, oldbeta, cs, sn, deltabar, eps_rot, w, &alpha, &beta2);
+      r1 = ws.r1; r2 = ws.r2; y = ws.y; v = r2;
+      delta = cs * deltabar + sn * alpha;
+      oldbeta = beta;
+      beta = beta2;
+    } else {
     op_apply(c, A, v, y);
     if (lambda != 0) k_axpy<T>(c, n, lambda, v, y);
     k_scal<T>(c, n, T(1) / beta, y);                          // kdiv!(n, y, β)
     if (iter >= 2) k_axpy<T>(c, n, -beta / oldbeta, r1, y);
-    const T alpha = k_dot<T>(c, n, v, y) / beta;
+    alpha = k_dot<T>(c, n, v, y) / beta;
     k_axpy<T>(c, n, -alpha / beta, r2, y);
-    const T delta = cs * deltabar + sn * alpha;
-    T* w;
+    delta = cs * deltabar + sn * alpha;
     if (iter == 1) {
       w = ws.w2;
       k_divcopy<T>(c, n, w, v, beta);
@@ -665,6 +693,7 @@ void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T
     if (!MisI) op_apply(c, M, r2, v, ldiv);
     oldbeta = beta;
     beta = k_dot<T>(c, n, r2, v);
+    }
     if (beta < 0) throw std::runtime_error("Preconditioner is not positive definite");
     beta = std::sqrt(beta);
     ANorm2 = ANorm2 + alpha * alpha + oldbeta * oldbeta + beta * beta;
@@ -676,7 +705,7 @@ void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T
     if (history) stats.Aresiduals.push_back(ArNorm);
     T gamma = std::sqrt(gbar * gbar + beta * beta);
     gamma = gamma > epsM ? gamma : epsM;
-    k_scal<T>(c, n, T(1) / gamma, w);                         // kdiv!(n, w, γ)
+    if (!fusedM) k_scal<T>(c, n, T(1) / gamma, w);            // kdiv!(n, w, γ)  (fused: folded into the x update below)
     if (linesearch) {                                         // minres.jl:336-373
       const T cg_ = cs * gbar;
       if (iter > 1) {
@@ -708,7 +737,9 @@ void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T
       k_scal<T>(c, n, sn * sn, npc_dir);
       k_axpy<T>(c, n, -phibar * cs / beta, v, npc_dir);
     }
-    k_axpy<T>(c, n, phi, w, x);
+    T xNorm_fused = 0;
+    if (fusedM) xNorm_fused = minres_fused_update<T>(ws, w, gamma, phi);   // w /= γ ; x += ϕ w ; ‖x‖ in one pass
+    else k_axpy<T>(c, n, phi, w, x);
     xENorm2 = xENorm2 + phi * phi;
     if (iter >= 2) { T* tmp = ws.w1; ws.w1 = ws.w2; ws.w2 = tmp; }   // @kswap!(w1, w2)
     err_vec[iter % window] = phi;
@@ -723,7 +754,7 @@ void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T
     rhs1 = rhs2 - delta * zeta;
     rhs2 = -eps_rot * zeta;
     ANorm = std::sqrt(ANorm2);
-    xNorm = k_nrm2<T>(c, n, x);
+    xNorm = fusedM ? xNorm_fused : k_nrm2<T>(c, n, x);
     rNorm = phibar;
     const T test1 = rNorm / (ANorm * xNorm);
     const T test2 = root / ANorm;

@@ -107,7 +107,8 @@ __global__ void plan_kernel(int n, int ntiles, const int* __restrict__ rowptr, i
   for (int i = t; i < n; i += stride) {
     const int kb = rowptr[i], ke = rowptr[i + 1];
     mr = max(mr, ke - kb);
-    for (int k = kb + 1; k < ke; k++) uns |= (colind[k] <= colind[k - 1]);
+    // halo columns (index >= n, row-partitioned operators) keep their global position in the row: skip them
+    for (int k = kb + 1; k < ke; k++) uns |= (colind[k] <= colind[k - 1]) && colind[k] < n && colind[k - 1] < n;
   }
   atomicMax(&out[0], cap);
   atomicMax(&out[1], mr);

@@ -1,0 +1,57 @@
+"""GPU: the fused iteration phases of bicgstab!/minres!/gmres! (csrc/fused_phases.cu) run the same arithmetic as
+the primitive path (one kernel per k* call): same iteration count, same history, fewer launches."""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ["bicgstab_kron10", "bicgstab_random3000_f32", "minres_divgrad16", "minres_shift", "minres_indefinite",
+         "gmres_kron10_restart30", "gmres_divgrad16_mem10_restart", "gmres_divgrad16_mem10_norestart"]
+
+
+def run(kb, name, fused):
+    solver, A, b, kw, dt = cases.build(name)
+    kw = dict(kw)
+    mem = kw.pop("memory", 0)
+    ws = kb.krylov_workspace(solver, A.shape[0], A.shape[1], dt, memory=mem)
+    ws.solve(A, b.astype(dt), history=True, fused=fused, **kw)
+    out = ws.x, ws.stats, ws.launches
+    ws.free()
+    return out
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_fused_phases_equal_primitive_path(kb, name):
+    x1, s1, l1 = run(kb, name, True)
+    x0, s0, l0 = run(kb, name, False)
+    dt = cases.build(name)[4]
+    assert s1.status == s0.status
+    if dt == np.float64:
+        assert s1.niter == s0.niter
+        tight = 1e-9 if "mem10_restart" not in name else 1e-3      # restarted GMRES(10) amplifies reduction-order noise
+        assert np.allclose(s1.residuals, s0.residuals, rtol=tight, atol=1e-9 * s0.residuals[0])
+        assert np.linalg.norm(x1 - x0) <= max(tight, 1e-8) * np.linalg.norm(x0)
+    else:
+        assert abs(s1.niter - s0.niter) <= 2
+    assert l1 < l0, (l1, l0)
+
+
+def test_minres_history_vectors_fused(kb, O):
+    A, b = O.sparse_laplacian(10)
+    x, st = kb.minres(A, b, history=True)
+    xo, so = O.minres(A, b)
+    assert st.niter == so["niter"] and np.allclose(st.residuals, so["residuals"], rtol=1e-6)
+    assert np.allclose(st.Aresiduals, so["Aresiduals"], rtol=1e-5, atol=1e-12) and np.allclose(st.Acond, so["Acond"], rtol=1e-6)
+    assert np.allclose(x, xo, rtol=1e-7)
+
+
+def test_gmres_fused_beyond_state_capacity(kb, O):
+    """Non-restarted GMRES past the 120 h-slots of the fused state block falls back to the primitive path mid-solve."""
+    A, b = O.kron_unsymmetric(7)
+    x, st = kb.gmres(A, b, memory=5, rtol=1e-13, atol=0.0, itmax=160, history=True)
+    xo, so = O.gmres(A, b, memory=5, rtol=1e-13, atol=0.0, itmax=160)
+    assert st.niter == so["niter"]
+    k = min(60, len(so["residuals"]))
+    assert np.allclose(st.residuals[:k], so["residuals"][:k], rtol=1e-6)
