@@ -41,6 +41,7 @@ struct CgPeers {           // peers' vectors for the halo gather (DIST only)
   HaloMap halo;
   const T* r[kMaxRanks];
   const T* p_old[kMaxRanks];
+  const T* mdiag;          // diagonal of M (nullptr: M = I); rides along in this kernel-parameter block
 };
 
 template <class T>
@@ -88,26 +89,31 @@ __device__ __forceinline__ bool cg_global_sum(CgState<T>* st, DistComm* dc, T& v
 template <class T, bool DIST>
 struct PVal {               // p_j = z_j + beta p_j, for local and (DIST) halo columns
   const T* r; const T* p_old; T beta; const CgPeers<T>* peers;
+  const T* mdiag;           // Jacobi / Diagonal M (cg.jl:241 z = M r applied on the fly); nullptr: M = I, z == r
   __device__ __forceinline__ T operator()(int j) const {
     if (DIST && j >= peers->halo.nloc) {
       const int h = j - peers->halo.nloc;
       const int rk = __ldg(&peers->halo.src_rank[h]), off = __ldg(&peers->halo.src_off[h]);
       return add_rn(__ldg(&peers->r[rk][off]), mul_rn(beta, __ldg(&peers->p_old[rk][off])));
     }
-    return add_rn(__ldg(&r[j]), mul_rn(beta, __ldg(&p_old[j])));
+    T z = __ldg(&r[j]);
+    if (mdiag) z = mul_rn(__ldg(&mdiag[j]), z);
+    return add_rn(z, mul_rn(beta, __ldg(&p_old[j])));
   }
 };
 
 // ---- K1, TMA-staged -------------------------------------------------------
-template <class T, bool DIST>
-__global__ void __launch_bounds__(kTileThreads) cg_k1_tma(Csr<T> A, const T* __restrict__ r, const T* __restrict__ p_old,
+// MINB = 4 caps the kernel at 56 registers so four CTAs fit on an SM (a few bytes of spill); MINB = 1 leaves
+// ptxas free (72 registers, three CTAs).  The plan's CTAs-per-SM choice selects the variant.
+template <class T, bool DIST, int MINB>
+__global__ void __launch_bounds__(kTileThreads, MINB) cg_k1_tma(Csr<T> A, const T* __restrict__ r, const T* __restrict__ p_old,
                                                           T* __restrict__ p_new, T* __restrict__ Ap, CgState<T>* st,
                                                           T* part, unsigned* ticket, DistComm* dc, CgPeers<T> peers) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ T sm[32];
   if (*(volatile int*)&st->done) return;
   T dacc = T(0);
-  const PVal<T, DIST> pval{r, p_old, st->beta, &peers};
+  const PVal<T, DIST> pval{r, p_old, st->beta, &peers, peers.mdiag};
   spmv_tiles_run<T>(A, smem, pval, pval, [&](int row, T acc, T pn) {
     p_new[row] = pn;
     Ap[row] = acc;
@@ -127,7 +133,7 @@ __global__ void __launch_bounds__(kBlock) cg_k1_rows(Csr<T> A, const T* __restri
   __shared__ T sm[32];
   if (*(volatile int*)&st->done) return;
   T dacc = T(0);
-  const PVal<T, DIST> pval{r, p_old, st->beta, &peers};
+  const PVal<T, DIST> pval{r, p_old, st->beta, &peers, peers.mdiag};
   const int stride = gridDim.x * blockDim.x;
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < A.n; row += stride) {
     const int kb = A.rowptr[row], ke = A.rowptr[row + 1];
@@ -148,34 +154,39 @@ __global__ void __launch_bounds__(kBlock) cg_k1_rows(Csr<T> A, const T* __restri
 template <class T>
 __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p,
                                                 const T* __restrict__ Ap, CgState<T>* st, T* part, unsigned* ticket,
-                                                DistComm* dc) {
+                                                DistComm* dc, const T* __restrict__ mdiag) {
   __shared__ T sm[32];
   if (*(volatile int*)&st->done) return;
   const T alpha = st->alpha, nalpha = -alpha;
   T acc = T(0);
+  // K1 walks the rows upwards and leaves the tails of p and Ap (and of r, which it read) in the 126 MB L2;
+  // K2 therefore walks DOWNWARDS from the last row, and finishes at row 0 where the next K1 starts reading
+  // r and p.  x is touched once per iteration: streaming (evict-first) loads/stores keep it out of the way.
   const int stride = gridDim.x * blockDim.x;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int last = n - 1;
   for (; i + 3 * stride < n; i += 4 * stride) {
     T xv[4], rv[4], pv[4], av[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const int j = i + u * stride;
-      xv[u] = x[j]; rv[u] = r[j]; pv[u] = __ldg(&p[j]); av[u] = __ldg(&Ap[j]);
+      const int j = last - (i + u * stride);
+      xv[u] = __ldcs(&x[j]); rv[u] = r[j]; pv[u] = __ldg(&p[j]); av[u] = __ldg(&Ap[j]);
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const int j = i + u * stride;
-      x[j] = add_rn(xv[u], mul_rn(alpha, pv[u]));
+      const int j = last - (i + u * stride);
+      __stcs(&x[j], add_rn(xv[u], mul_rn(alpha, pv[u])));
       const T rn = add_rn(rv[u], mul_rn(nalpha, av[u]));
       r[j] = rn;
-      acc += rn * rn;
+      acc += rn * (mdiag ? mul_rn(__ldg(&mdiag[j]), rn) : rn);      // <r, z>, z = M r (cg.jl:241-242)
     }
   }
   for (; i < n; i += stride) {
-    x[i] = add_rn(x[i], mul_rn(alpha, p[i]));
-    const T rn = add_rn(r[i], mul_rn(nalpha, Ap[i]));
-    r[i] = rn;
-    acc += rn * rn;
+    const int j = last - i;
+    __stcs(&x[j], add_rn(__ldcs(&x[j]), mul_rn(alpha, p[j])));
+    const T rn = add_rn(r[j], mul_rn(nalpha, Ap[j]));
+    r[j] = rn;
+    acc += rn * (mdiag ? mul_rn(__ldg(&mdiag[j]), rn) : rn);
   }
   T mine[1] = {block_sum(acc, sm)}, tot[1];
   if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) {
@@ -185,7 +196,9 @@ __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __r
 
 // ---------------------------------------------------------------------------
 template <class T> bool cg_fused_eligible(const LinOp<T>& A, const LinOp<T>& M, const SolveOpts& o) {
-  return o.fused && A.kind == LinOp<T>::CSR && M.is_identity() && o.radius == 0;
+  // M = I, or a Diagonal M applied with mul! (the Jacobi case of SURVEY.md 8f-1), folded into the two kernels
+  const bool m_ok = M.is_identity() || (M.kind == LinOp<T>::DIAG && !o.ldiv);
+  return o.fused && A.kind == LinOp<T>::CSR && m_ok && o.radius == 0;
 }
 
 template <class T>
@@ -214,8 +227,9 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
 
   static bool attr_set = false;
   if (A.tma_ok && !attr_set) {
-    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
   const int g2 = stream_grid(n, 4, 8);
@@ -225,6 +239,8 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   // peers' direction buffers in the same order as P[]
   CgPeers<T> peersP[2];
   memset(peersP, 0, sizeof(peersP));
+  const T* md = ws.mdiag_fused;
+  peersP[0].mdiag = md; peersP[1].mdiag = md;
   if (dist) {
     for (int b = 0; b < 2; b++) {
       peersP[b].halo = ws.dist.halo;
@@ -261,14 +277,15 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
       const bool timed = o.time_kernels && ti >= 0 && ti < kTimedCount;
       if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti], c.stream));
       if (A.tma_ok) {
-        if (dist) cg_k1_tma<T, true><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
-        else cg_k1_tma<T, false><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
+        if (dist) cg_k1_tma<T, true, 1><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
+        else if (A.ctas_per_sm >= 4) cg_k1_tma<T, false, 4><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
+        else cg_k1_tma<T, false, 1><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
       } else {
         if (dist) cg_k1_rows<T, true><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
         else cg_k1_rows<T, false><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
       }
       if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti + 1], c.stream));
-      cg_k2<T><<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3, dist ? c.dcomm : nullptr);
+      cg_k2<T><<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3, dist ? c.dcomm : nullptr, md);
       if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti + 2], c.stream));
       c.launches += 2;
     }

@@ -79,6 +79,7 @@ struct Csr {
   int stages = 0;           // pipeline depth chosen for tile_cap
   size_t smem_bytes = 0;    // dynamic smem of the staged kernels
   int grid = 0;             // persistent grid (multiple of the SM count)
+  int ctas_per_sm = 0;      // resident CTAs per SM the ring was sized for
 };
 
 template <class T> void csr_upload(Ctx& c, Csr<T>& A, int n, long long nnz, const void* rowptr, const void* colind,
@@ -166,6 +167,7 @@ struct Workspace {
   std::vector<T> err_vec;              // MINRES window
   int memory = 20, window = 5;
   int inner_iter = 0;
+  const T* mdiag_fused = nullptr;      // diagonal of M for the fused CG kernels (set per solve; nullptr: M = I)
   double k1_ms = 0, k2_ms = 0;         // average event-timed duration of the fused kernels (time_kernels)
   int timed_pairs = 0;
   void* fused_state = nullptr;         // device scalar block of the fused paths

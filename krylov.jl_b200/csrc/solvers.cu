@@ -105,7 +105,7 @@ void cg_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
   if (ws.warm_start && linesearch) throw std::runtime_error("warm_start and linesearch cannot be used together");
   if (o.verbose > 0) printf("CG: system of %d equations in %d variables\n", n, n);
   const bool MisI = M.is_identity();
-  if (ws.dist.world > 1 && (ws.warm_start || !cg_fused_eligible(A, M, o) || o.callback))
+  if (ws.dist.world > 1 && (ws.warm_start || !cg_fused_eligible(A, M, o) || !MisI || o.callback))
     throw std::runtime_error("row-partitioned cg!: only the fused path (CSR operator, M = I, radius = 0, no warm start, no callback) is distributed");
   allocate_if(!MisI, ws, ws.z);
   allocate_if(linesearch || radius > 0, ws, ws.npc_dir);
@@ -148,6 +148,7 @@ void cg_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
   std::string status = "unknown";
 
   if (cg_fused_eligible(A, M, o) && !(solved || tired)) {
+    ws.mdiag_fused = MisI ? nullptr : M.diag;      // Diagonal M is applied inside K1/K2 (z is not materialised)
     cg_fused_loop<T>(ws, *A.csr, o, gamma, eps_tol, itmax, start_time, solved, tired, zero_curvature, inconsistent,
                      user_exit, overtimed, iter);
   } else {

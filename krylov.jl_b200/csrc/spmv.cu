@@ -157,6 +157,7 @@ template <class T> void csr_plan(Ctx& c, Csr<T>& A) {
     A.smem_bytes = L.total_bytes(A.stages);
     int g = sm_count() * per_sm;
     A.grid = g < A.ntiles ? g : (A.ntiles > 0 ? A.ntiles : 1);
+    A.ctas_per_sm = per_sm;
   } else {
     A.stages = 0; A.smem_bytes = 0; A.grid = 0;
   }

@@ -55,3 +55,23 @@ def test_gmres_fused_beyond_state_capacity(kb, O):
     assert st.niter == so["niter"]
     k = min(60, len(so["residuals"]))
     assert np.allclose(st.residuals[:k], so["residuals"][:k], rtol=1e-6)
+
+
+def test_fused_cg_with_jacobi_preconditioner(kb, O):
+    """Diagonal M folded into the two CG kernels == primitive path == oracle."""
+    import scipy.sparse as sp
+    A, b = O.sparse_laplacian(12)
+    A = sp.csr_matrix(A + sp.diags(np.linspace(0.0, 5.0, A.shape[0])))      # non-constant diagonal
+    d = 1.0 / A.diagonal()
+    out = {}
+    for fused in (True, False):
+        ws = kb.CgWorkspace(A, b)
+        ws.solve(A, b, M=d, history=True, fused=fused)
+        out[fused] = (ws.x, ws.stats, ws.launches)
+        ws.free()
+    xo, so = O.cg(A, b, M=d)
+    for fused in (True, False):
+        x, st, _ = out[fused]
+        assert st.niter == so["niter"] and np.allclose(st.residuals, so["residuals"], rtol=1e-6)
+        assert np.linalg.norm(x - xo) <= 1e-7 * np.linalg.norm(xo)
+    assert out[True][2] < out[False][2]
