@@ -159,31 +159,29 @@ __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __r
   if (*(volatile int*)&st->done) return;
   const T alpha = st->alpha, nalpha = -alpha;
   T acc = T(0);
-  // K1 walks the rows upwards and leaves the tails of p and Ap (and of r, which it read) in the 126 MB L2;
-  // K2 therefore walks DOWNWARDS from the last row, and finishes at row 0 where the next K1 starts reading
-  // r and p.  x is touched once per iteration: streaming (evict-first) loads/stores keep it out of the way.
+  // (Measured and rejected, profiles/r1_sweep_k1.txt: walking K2 downwards with evict-first x accesses to reuse
+  //  the L2 tails left by K1 made K2 13 % and the following K1 8 % SLOWER -- ascending plain accesses stay.)
   const int stride = gridDim.x * blockDim.x;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int last = n - 1;
   for (; i + 3 * stride < n; i += 4 * stride) {
     T xv[4], rv[4], pv[4], av[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const int j = last - (i + u * stride);
-      xv[u] = __ldcs(&x[j]); rv[u] = r[j]; pv[u] = __ldg(&p[j]); av[u] = __ldg(&Ap[j]);
+      const int j = i + u * stride;
+      xv[u] = x[j]; rv[u] = r[j]; pv[u] = __ldg(&p[j]); av[u] = __ldg(&Ap[j]);
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const int j = last - (i + u * stride);
-      __stcs(&x[j], add_rn(xv[u], mul_rn(alpha, pv[u])));
+      const int j = i + u * stride;
+      x[j] = add_rn(xv[u], mul_rn(alpha, pv[u]));
       const T rn = add_rn(rv[u], mul_rn(nalpha, av[u]));
       r[j] = rn;
       acc += rn * (mdiag ? mul_rn(__ldg(&mdiag[j]), rn) : rn);      // <r, z>, z = M r (cg.jl:241-242)
     }
   }
   for (; i < n; i += stride) {
-    const int j = last - i;
-    __stcs(&x[j], add_rn(__ldcs(&x[j]), mul_rn(alpha, p[j])));
+    const int j = i;
+    x[j] = add_rn(x[j], mul_rn(alpha, p[j]));
     const T rn = add_rn(r[j], mul_rn(nalpha, Ap[j]));
     r[j] = rn;
     acc += rn * (mdiag ? mul_rn(__ldg(&mdiag[j]), rn) : rn);
