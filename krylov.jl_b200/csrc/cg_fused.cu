@@ -100,6 +100,12 @@ struct PVal {               // p_j = z_j + beta p_j, for local and (DIST) halo c
     if (mdiag) z = mul_rn(__ldg(&mdiag[j]), z);
     return add_rn(z, mul_rn(beta, __ldg(&p_old[j])));
   }
+  __device__ __forceinline__ void prefetch(int j) const {      // L2 prefetch hook of the tile pipeline
+    if (DIST && j >= peers->halo.nloc) return;
+    prefetch_l2(&r[j]);
+    prefetch_l2(&p_old[j]);
+    if (mdiag) prefetch_l2(&mdiag[j]);
+  }
 };
 
 // ---- K1, TMA-staged -------------------------------------------------------
@@ -225,10 +231,22 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
 
   static bool attr_set = false;
   if (A.tma_ok && !attr_set) {
-    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
+  }
+  // The persistent grid must equal what is actually co-resident: a register count that silently drops the
+  // occupancy below the plan's CTAs/SM would otherwise run the tiles in 1.5 waves (measured: K1 2.2x slower).
+  int k1_grid = A.grid;
+  if (A.tma_ok) {
+    int occ = 0;
+    if (dist) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, true, 3>, kTileThreads, A.smem_bytes));
+    else if (A.ctas_per_sm >= 4) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, false, 4>, kTileThreads, A.smem_bytes));
+    else KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, false, 3>, kTileThreads, A.smem_bytes));
+    if (occ < 1) throw std::runtime_error("cg_k1_tma does not fit on an SM with the planned shared-memory ring");
+    const int resident = std::min(occ, A.ctas_per_sm) * sm_count();
+    k1_grid = std::min(resident, std::max(1, A.ntiles));
   }
   const int g2 = stream_grid(n, 4, 8);
   const int g1r = stream_grid(n, 1, 8);
@@ -275,9 +293,9 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
       const bool timed = o.time_kernels && ti >= 0 && ti < kTimedCount;
       if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti], c.stream));
       if (A.tma_ok) {
-        if (dist) cg_k1_tma<T, true, 1><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
-        else if (A.ctas_per_sm >= 4) cg_k1_tma<T, false, 4><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
-        else cg_k1_tma<T, false, 1><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
+        if (dist) cg_k1_tma<T, true, 3><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
+        else if (A.ctas_per_sm >= 4) cg_k1_tma<T, false, 4><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
+        else cg_k1_tma<T, false, 3><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
       } else {
         if (dist) cg_k1_rows<T, true><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
         else cg_k1_rows<T, false><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);

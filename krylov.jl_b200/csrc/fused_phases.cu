@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(kTileThreads) spmv_epi_tma(Csr<T> A, const T* 
 #pragma unroll
   for (int k = 0; k < K; k++) d[k] = T(0);
   spmv_tiles_run<T>(
-      A, smem, [&](int j) { return __ldg(&x[j]); }, NoRowBegin(), [&](int row, T acc, int) { epi(row, acc, d); });
+      A, smem, XGather<T>{x}, NoRowBegin(), [&](int row, T acc, int) { epi(row, acc, d); });
   T mine[K], tot[K];
 #pragma unroll
   for (int k = 0; k < K; k++) mine[k] = block_sum(d[k], sm);
@@ -86,7 +86,11 @@ static void launch_spmv_epi(Ctx& c, const Csr<T>& A, const T* x, Epi epi, Fin fi
   if (A.tma_ok) {
     static bool attr = false;
     if (!attr) { KB_CUDA(cudaFuncSetAttribute(spmv_epi_tma<T, K, Epi, Fin>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
-    spmv_epi_tma<T, K, Epi, Fin><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, x, epi, fin, (T*)c.partials, c.tickets + ticket);
+    int occ = 0;          // persistent grid = what is really co-resident (never more than one wave)
+    KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_epi_tma<T, K, Epi, Fin>, kTileThreads, A.smem_bytes));
+    if (occ < 1) throw std::runtime_error("spmv_epi_tma does not fit on an SM with the planned shared-memory ring");
+    const int grid = std::min(std::min(occ, A.ctas_per_sm) * sm_count(), std::max(1, A.ntiles));
+    spmv_epi_tma<T, K, Epi, Fin><<<grid, kTileThreads, A.smem_bytes, c.stream>>>(A, x, epi, fin, (T*)c.partials, c.tickets + ticket);
   } else {
     spmv_epi_rows<T, K, Epi, Fin><<<stream_grid(A.n, 1, 8), kBlock, 0, c.stream>>>(A, x, epi, fin, (T*)c.partials, c.tickets + ticket);
   }

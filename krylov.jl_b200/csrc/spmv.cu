@@ -158,6 +158,8 @@ template <class T> void csr_plan(Ctx& c, Csr<T>& A) {
     int g = sm_count() * per_sm;
     A.grid = g < A.ntiles ? g : (A.ntiles > 0 ? A.ntiles : 1);
     A.ctas_per_sm = per_sm;
+    const char* ep = getenv("KB200_PREFETCH");
+    A.prefetch_x = !(ep && atoi(ep) == 0);
   } else {
     A.stages = 0; A.smem_bytes = 0; A.grid = 0;
   }
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(kTileThreads) spmv_tma_kernel(Csr<T> A, const 
   __shared__ T sm[32];
   T dacc = T(0);
   spmv_tiles_run<T>(
-      A, smem, [&](int j) { return __ldg(&x[j]); }, [&](int row) { return DOT ? __ldg(&x[row]) : T(0); },
+      A, smem, XGather<T>{x}, [&](int row) { return DOT ? __ldg(&x[row]) : T(0); },
       [&](int row, T acc, T xr) {
         y[row] = acc;
         if (DOT) dacc += xr * acc;
@@ -217,7 +219,11 @@ static void spmv_launch(Ctx& c, const Csr<T>& A, const T* x, T* y, int slot, int
       KB_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<T, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       attr_set[DOT] = true;
     }
-    spmv_tma_kernel<T, DOT><<<A.grid, kTileThreads, A.smem_bytes, c.stream>>>(A, x, y, (T*)c.partials, c.tickets + 1, out);
+    int occ = 0;   // persistent grid = what is really co-resident (never more than one wave)
+    KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_tma_kernel<T, DOT>, kTileThreads, A.smem_bytes));
+    if (occ < 1) throw std::runtime_error("spmv_tma_kernel does not fit on an SM with the planned shared-memory ring");
+    const int grid = std::min(std::min(occ, A.ctas_per_sm) * sm_count(), std::max(1, A.ntiles));
+    spmv_tma_kernel<T, DOT><<<grid, kTileThreads, A.smem_bytes, c.stream>>>(A, x, y, (T*)c.partials, c.tickets + 1, out);
   } else {
     const int grid = stream_grid(A.n, 1, 8);
     spmv_rows_kernel<T, DOT><<<grid, kBlock, 0, c.stream>>>(A, x, y, (T*)c.partials, c.tickets + 1, out);
