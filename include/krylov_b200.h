@@ -196,6 +196,11 @@ void *krylov_b200_stream(void *ws);
  * krylov_solve with the same options. */
 int krylov_b200_dist_handle_bytes(void);
 int krylov_b200_dist_init(void *ws, int rank, int world, int nhalo, const int *halo_rank, const int *halo_off);
+/* Optional push mode (after dist_init, any time before the first solve): `ranges4` holds nranges (<= 4) quadruples
+ * (first local row, count, peer rank, first slot in the peer's halo) describing which contiguous blocks of this
+ * rank's rows each peer needs; nhalo_all[world] = every rank's halo length.  The producing kernels then store
+ * those entries directly into the peers' halo buffers and nobody issues fine-grained P2P loads. */
+int krylov_b200_dist_set_push(void *ws, int nranges, const int *ranges4, const int *nhalo_all);
 int krylov_b200_dist_export(void *ws, void *handles_out);
 int krylov_b200_dist_import(void *ws, const void *all_handles);
 

@@ -462,7 +462,7 @@ void* krylov_b200_stream(void* ws) {
 // ------------------------------ row-partitioned solves --------------------
 }  // extern "C" (templates below need C++ linkage)
 namespace {
-constexpr int kIpcHandles = 4;   // r, p, p2, mailbox
+constexpr int kIpcHandles = 5;   // r, p, p2, mailbox, halo_buf
 constexpr size_t kMailDoubles = 2 * kMaxRanks;
 constexpr size_t kMailBytes = kMailDoubles * sizeof(double) + kMailDoubles * sizeof(unsigned long long);
 
@@ -484,6 +484,10 @@ template <class T> int dist_init_t(Handle* h, int rank, int world, int nhalo, co
   ws->dist.halo = HaloMap{ws->n, nhalo, dr, dof};
   KB_CUDA(cudaMalloc(&ws->dist.mailbox, kMailBytes));
   KB_CUDA(cudaMemset(ws->dist.mailbox, 0, kMailBytes));
+  // local halo buffers of the push mode: [r | p(bufA) | p(bufB)]
+  ws->dist.halo_buf = dev_alloc<T>(3 * (size_t)(nhalo > 0 ? nhalo : 1));
+  KB_CUDA(cudaMemset(ws->dist.halo_buf, 0, sizeof(T) * 3 * (size_t)(nhalo > 0 ? nhalo : 1)));
+  ws->dist.npush = 0;
   return 0;
 }
 
@@ -492,7 +496,7 @@ template <class T> int dist_export_t(Handle* h, void* out) {
   if (!ws->dist.mailbox) throw std::runtime_error("call krylov_b200_dist_init first");
   KB_CUDA(cudaSetDevice(ws->ctx.device));
   cudaIpcMemHandle_t* hs = (cudaIpcMemHandle_t*)out;
-  void* ptrs[kIpcHandles] = {ws->r, ws->p, ws->p2, ws->dist.mailbox};
+  void* ptrs[kIpcHandles] = {ws->r, ws->p, ws->p2, ws->dist.mailbox, ws->dist.halo_buf};
   for (int i = 0; i < kIpcHandles; i++) KB_CUDA(cudaIpcGetMemHandle(&hs[i], ptrs[i]));
   return 0;
 }
@@ -508,7 +512,7 @@ template <class T> int dist_import_t(Handle* h, const void* all) {
   for (int k = 0; k < D.world; k++) {
     void* ptr[kIpcHandles];
     if (k == D.rank) {
-      ptr[0] = ws->r; ptr[1] = ws->p; ptr[2] = ws->p2; ptr[3] = D.mailbox;
+      ptr[0] = ws->r; ptr[1] = ws->p; ptr[2] = ws->p2; ptr[3] = D.mailbox; ptr[4] = D.halo_buf;
     } else {
       for (int i = 0; i < kIpcHandles; i++) {
         KB_CUDA(cudaIpcOpenMemHandle(&ptr[i], hs[k * kIpcHandles + i], cudaIpcMemLazyEnablePeerAccess));
@@ -516,6 +520,7 @@ template <class T> int dist_import_t(Handle* h, const void* all) {
       }
     }
     D.r_peer[k] = (T*)ptr[0]; D.bufA_peer[k] = (T*)ptr[1]; D.bufB_peer[k] = (T*)ptr[2];
+    D.halo_buf_peer[k] = (T*)ptr[4];
     hc.mail_val[k] = (double*)ptr[3];
     hc.mail_seq[k] = (unsigned long long*)((double*)ptr[3] + kMailDoubles);
   }
@@ -536,6 +541,20 @@ int krylov_b200_dist_init(void* ws, int rank, int world, int nhalo, const int* h
     return h->dtype == KRYLOV_FLOAT64 ? dist_init_t<double>(h, rank, world, nhalo, halo_rank, halo_off)
                                       : dist_init_t<float>(h, rank, world, nhalo, halo_rank, halo_off);
   } catch (const std::exception& e) { return fail("krylov_b200_dist_init", e); }
+}
+int krylov_b200_dist_set_push(void* ws, int nranges, const int* ranges4, const int* nhalo_all) {
+  try {
+    Handle* h = lookup(ws);
+    if (!h) return fail("krylov_b200_dist_set_push", "unknown workspace handle");
+    if (nranges < 0 || nranges > kMaxPushRanges) return fail("krylov_b200_dist_set_push", "too many ranges (pull mode stays on)");
+    auto apply = [&](auto* w) {
+      for (int q = 0; q < nranges; q++) w->dist.push[q] = PushRange{ranges4[4 * q], ranges4[4 * q + 1], ranges4[4 * q + 2], ranges4[4 * q + 3]};
+      for (int k = 0; k < w->dist.world; k++) w->dist.nhalo_peer[k] = nhalo_all[k];
+      w->dist.npush = nranges;
+    };
+    if (h->dtype == KRYLOV_FLOAT64) apply(W<double>(h)); else apply(W<float>(h));
+    return 0;
+  } catch (const std::exception& e) { return fail("krylov_b200_dist_set_push", e); }
 }
 int krylov_b200_dist_export(void* ws, void* handles_out) {
   try {

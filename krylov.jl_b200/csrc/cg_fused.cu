@@ -42,6 +42,9 @@ struct CgPeers {           // peers' vectors for the halo gather (DIST only)
   const T* r[kMaxRanks];
   const T* p_old[kMaxRanks];
   const T* mdiag;          // diagonal of M (nullptr: M = I); rides along in this kernel-parameter block
+  const T* r_halo;         // push mode: LOCAL halo copies kept current by the peers' K2 / K1 (nullptr: pull mode)
+  const T* p_halo_old;
+  PushPlan<T> push_p;      // where this rank's new p entries go (peers' p_halo of the new parity)
 };
 
 template <class T>
@@ -93,6 +96,8 @@ struct PVal {               // p_j = z_j + beta p_j, for local and (DIST) halo c
   __device__ __forceinline__ T operator()(int j) const {
     if (DIST && j >= peers->halo.nloc) {
       const int h = j - peers->halo.nloc;
+      if (peers->r_halo)     // push mode: the owners stored these entries into my halo buffers
+        return add_rn(__ldg(&peers->r_halo[h]), mul_rn(beta, __ldg(&peers->p_halo_old[h])));
       const int rk = __ldg(&peers->halo.src_rank[h]), off = __ldg(&peers->halo.src_off[h]);
       return add_rn(__ldg(&peers->r[rk][off]), mul_rn(beta, __ldg(&peers->p_old[rk][off])));
     }
@@ -122,6 +127,7 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_k1_tma(Csr<T> A, const 
   const PVal<T, DIST> pval{r, p_old, st->beta, &peers, peers.mdiag};
   spmv_tiles_run<T>(A, smem, pval, pval, [&](int row, T acc, T pn) {
     p_new[row] = pn;
+    if (DIST) peers.push_p(row, pn);
     Ap[row] = acc;
     dacc += pn * acc;
   });
@@ -147,6 +153,7 @@ __global__ void __launch_bounds__(kBlock) cg_k1_rows(Csr<T> A, const T* __restri
     for (int k = kb; k < ke; k++) acc = add_rn(acc, mul_rn(A.val[k], pval(A.colind[k])));
     const T pn = pval(row);
     p_new[row] = pn;
+    if (DIST) peers.push_p(row, pn);
     Ap[row] = acc;
     dacc += pn * acc;
   }
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(kBlock) cg_k1_rows(Csr<T> A, const T* __restri
 template <class T>
 __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p,
                                                 const T* __restrict__ Ap, CgState<T>* st, T* part, unsigned* ticket,
-                                                DistComm* dc, const T* __restrict__ mdiag) {
+                                                DistComm* dc, const T* __restrict__ mdiag, PushPlan<T> push_r) {
   __shared__ T sm[32];
   if (*(volatile int*)&st->done) return;
   const T alpha = st->alpha, nalpha = -alpha;
@@ -182,6 +189,7 @@ __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __r
       x[j] = add_rn(xv[u], mul_rn(alpha, pv[u]));
       const T rn = add_rn(rv[u], mul_rn(nalpha, av[u]));
       r[j] = rn;
+      if (push_r.nranges) push_r(j, rn);                            // row-partitioned: neighbours' halo copy of r
       acc += rn * (mdiag ? mul_rn(__ldg(&mdiag[j]), rn) : rn);      // <r, z>, z = M r (cg.jl:241-242)
     }
   }
@@ -190,12 +198,34 @@ __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __r
     x[j] = add_rn(x[j], mul_rn(alpha, p[j]));
     const T rn = add_rn(r[j], mul_rn(nalpha, Ap[j]));
     r[j] = rn;
+    if (push_r.nranges) push_r(j, rn);
     acc += rn * (mdiag ? mul_rn(__ldg(&mdiag[j]), rn) : rn);
   }
   T mine[1] = {block_sum(acc, sm)}, tot[1];
   if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) {
     if (cg_global_sum(st, dc, tot[0])) cg_k2_finalize(st, tot[0]);
   }
+}
+
+// Prologue of a row-partitioned solve in push mode: send the boundary entries of r_0 to the neighbours' halo
+// buffers.  The all-reduce of the prologue's <r,z> (launched next on the same stream) orders it before any K1.
+template <class T>
+__global__ void push_ranges_kernel(const T* __restrict__ v, PushPlan<T> plan) {
+  const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int q = 0; q < plan.nranges; q++)
+    for (int d = tid; d < plan.rg[q].count; d += stride) plan.dst[q][plan.rg[q].slot + d] = v[plan.rg[q].start + d];
+  __threadfence_system();
+}
+
+template <class T> void cg_dist_push_r(Workspace<T>& ws) {
+  if (ws.dist.world <= 1 || ws.dist.npush <= 0) return;
+  PushPlan<T> plan;
+  memset(&plan, 0, sizeof(plan));
+  plan.nranges = ws.dist.npush;
+  for (int q = 0; q < ws.dist.npush; q++) { plan.rg[q] = ws.dist.push[q]; plan.dst[q] = ws.dist.halo_buf_peer[plan.rg[q].peer]; }
+  push_ranges_kernel<T><<<sm_count(), kBlock, 0, ws.ctx.stream>>>(ws.r, plan);
+  KB_CUDA(cudaGetLastError());
+  ws.ctx.launches++;
 }
 
 // ---------------------------------------------------------------------------
@@ -257,6 +287,8 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   memset(peersP, 0, sizeof(peersP));
   const T* md = ws.mdiag_fused;
   peersP[0].mdiag = md; peersP[1].mdiag = md;
+  PushPlan<T> push_r;
+  memset(&push_r, 0, sizeof(push_r));
   if (dist) {
     for (int b = 0; b < 2; b++) {
       peersP[b].halo = ws.dist.halo;
@@ -264,6 +296,22 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
       for (int k = 0; k < ws.dist.world; k++) {
         peersP[b].r[k] = ws.dist.r_peer[k];
         peersP[b].p_old[k] = wantB ? ws.dist.bufB_peer[k] : ws.dist.bufA_peer[k];
+      }
+      if (ws.dist.npush > 0) {
+        // push mode: halo_buf = [r | p(bufA) | p(bufB)], nhalo entries each (every rank with its own nhalo)
+        const size_t nh = (size_t)ws.dist.halo.nhalo;
+        peersP[b].r_halo = ws.dist.halo_buf;
+        peersP[b].p_halo_old = ws.dist.halo_buf + (wantB ? 2 : 1) * nh;
+        peersP[b].push_p.nranges = ws.dist.npush;
+        for (int q = 0; q < ws.dist.npush; q++) {
+          const PushRange& rg = ws.dist.push[q];
+          peersP[b].push_p.rg[q] = rg;
+          // K1 with p_old = P[b] writes P[b^1]: the OTHER allocation's section of the peer's halo buffer
+          peersP[b].push_p.dst[q] = ws.dist.halo_buf_peer[rg.peer] + (wantB ? 1 : 2) * (size_t)ws.dist.nhalo_peer[rg.peer];
+          push_r.rg[q] = rg;
+          push_r.dst[q] = ws.dist.halo_buf_peer[rg.peer];
+        }
+        push_r.nranges = ws.dist.npush;
       }
     }
   }
@@ -301,7 +349,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
         else cg_k1_rows<T, false><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
       }
       if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti + 1], c.stream));
-      cg_k2<T><<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3, dist ? c.dcomm : nullptr, md);
+      cg_k2<T><<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3, dist ? c.dcomm : nullptr, md, push_r);
       if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti + 2], c.stream));
       c.launches += 2;
     }
@@ -378,6 +426,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
 
 #define INST(T)                                                                                              \
   template bool cg_fused_eligible<T>(const LinOp<T>&, const LinOp<T>&, const SolveOpts&);                    \
+  template void cg_dist_push_r<T>(Workspace<T>&);                                                            \
   template void cg_fused_loop<T>(Workspace<T>&, const Csr<T>&, const SolveOpts&, T, T, int, double, bool&, bool&, \
                                  bool&, bool&, bool&, bool&, int&);
 INST(double)

@@ -42,6 +42,29 @@ struct HaloMap {
   const int* src_off;
 };
 
+// Push plan: when the entries a peer needs from this rank form contiguous row ranges (slab partitions of
+// banded matrices), the kernels that PRODUCE those entries store them straight into the peer's halo buffer
+// (posted P2P writes, no round trip) and the consumers gather halo columns from their LOCAL halo buffer.
+// Without a push plan the consumers pull halo entries from the owners' vectors (fine-grained P2P loads:
+// measured ~60 GB/s effective, 25 us per 46k-entry plane pair).
+constexpr int kMaxPushRanges = 4;
+struct PushRange { int start, count, peer, slot; };   // local rows [start, start+count) -> peer's halo slots [slot, ...)
+template <class T>
+struct PushPlan {
+  int nranges;                       // 0: pull mode
+  PushRange rg[kMaxPushRanges];
+  T* dst[kMaxPushRanges];            // peer halo buffer (for the vector being produced) per range
+  __device__ __forceinline__ void operator()(int row, T v) const {
+    for (int q = 0; q < nranges; q++) {
+      const unsigned d = (unsigned)(row - rg[q].start);
+      if (d < (unsigned)rg[q].count) {
+        dst[q][rg[q].slot + d] = v;
+        __threadfence_system();      // visible to the peer before this CTA's partial can reach the all-reduce
+      }
+    }
+  }
+};
+
 __device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }

@@ -185,6 +185,11 @@ struct Workspace {
     T* r_peer[kMaxRanks] = {};
     std::vector<void*> opened;                  // cudaIpcOpenMemHandle results to close
     bool swapped = false;                       // ws.p currently points at the bufB allocation
+    T* halo_buf = nullptr;                      // local halo buffers [r | p(bufA) | p(bufB)], nhalo entries each
+    T* halo_buf_peer[kMaxRanks] = {};           // every rank's halo_buf
+    int nhalo_peer[kMaxRanks] = {};             // every rank's halo length (section stride inside its halo_buf)
+    int npush = 0;                              // > 0: push mode (contiguous send ranges), else pull mode
+    PushRange push[kMaxPushRanges];
   } dist;
 };
 
@@ -202,6 +207,7 @@ template <class T> void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const 
 // Fused CG (cg_fused.cu).  Returns false if the configuration is not eligible
 // (caller falls back to the generic primitive path, still on the GPU).
 template <class T> bool cg_fused_eligible(const LinOp<T>& A, const LinOp<T>& M, const SolveOpts& o);
+template <class T> void cg_dist_push_r(Workspace<T>& ws);
 template <class T> void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamma0, T eps_tol, int itmax,
                                       double start_time, bool& solved, bool& tired, bool& zero_curvature,
                                       bool& inconsistent, bool& user_exit, bool& overtimed, int& iter);

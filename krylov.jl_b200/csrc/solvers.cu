@@ -65,6 +65,7 @@ template <class T> void ws_destroy(Workspace<T>* ws) {
   if (ws->fused_host) cudaFreeHost(ws->fused_host);
   for (void* p : ws->dist.opened) cudaIpcCloseMemHandle(p);
   if (ws->dist.mailbox) cudaFree(ws->dist.mailbox);
+  dev_free(ws->dist.halo_buf);
   if (ws->dist.halo.src_rank) cudaFree((void*)ws->dist.halo.src_rank);
   if (ws->dist.halo.src_off) cudaFree((void*)ws->dist.halo.src_off);
   if (ws->ctx.dcomm) cudaFree(ws->ctx.dcomm);
@@ -122,6 +123,7 @@ void cg_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
   } else {
     k_copy<T>(c, n, r, b);
   }
+  cg_dist_push_r<T>(ws);                                    // row-partitioned push mode: neighbours' halo copy of r_0
   if (!MisI) op_apply(c, M, r, z, ldiv);
   k_copy<T>(c, n, ws.p, z);
   T gamma = k_dot<T>(c, n, r, z);

@@ -12,7 +12,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_PKG)                      # krylov.jl_b200/
-SO_PATH = os.path.join(ROOT, "lib", "libkrylov_b200.so")
+SO_PATH = os.environ.get("KB200_LIB") or os.path.join(ROOT, "lib", "libkrylov_b200.so")   # KB200_LIB: A/B builds
 
 KRYLOV_FLOAT32, KRYLOV_FLOAT64 = 0, 1
 KRYLOV_CPU, KRYLOV_CUDA = 0, 1
@@ -87,6 +87,7 @@ SIGNATURES = {
     "krylov_b200_stream": (_P, [_P]),
     "krylov_b200_dist_handle_bytes": (_I, []),
     "krylov_b200_dist_init": (_I, [_P, _I, _I, _I, _P, _P]),
+    "krylov_b200_dist_set_push": (_I, [_P, _I, _P, _P]),
     "krylov_b200_dist_export": (_I, [_P, _P]),
     "krylov_b200_dist_import": (_I, [_P, _P]),
     "kb200_ctx_create": (_P, [_I]),
@@ -129,7 +130,12 @@ def lib() -> C.CDLL:
                                "(there is no CPU fallback)")
         L = C.CDLL(SO_PATH)
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(L, name)
+            try:
+                fn = getattr(L, name)
+            except AttributeError:
+                if os.environ.get("KB200_LIB"):      # an older A/B build may lack newer entry points
+                    continue
+                raise
             fn.restype = res
             fn.argtypes = args
         _LIB = L

@@ -71,6 +71,29 @@ def localize_columns(colind_global, row_starts, rank):
     return local.astype(np.int32), owner.astype(np.int32), halo_off.astype(np.int32)
 
 
+def push_ranges(maps, rank, max_ranges=4):
+    """Send plan of `rank` from every rank's halo map (halo_rank, halo_off).
+
+    For each peer q, the halo slots of q that `rank` owns must form ONE run of consecutive slots pointing at
+    consecutive local rows; returns [(first local row, count, q, first slot in q's halo)] or None when some
+    peer's needs are not contiguous (the kernels then stay in pull mode)."""
+    out = []
+    for q, (hr, ho) in enumerate(maps):
+        if q == rank:
+            continue
+        hr, ho = np.asarray(hr), np.asarray(ho)
+        slots = np.nonzero(hr == rank)[0]
+        if len(slots) == 0:
+            continue
+        rows = ho[slots]
+        if not (np.all(np.diff(slots) == 1) and np.all(np.diff(rows) == 1)):
+            return None
+        out.append((int(rows[0]), int(len(slots)), int(q), int(slots[0])))
+    if len(out) > max_ranges:
+        return None
+    return out
+
+
 # --------------------------------------------------------------------------
 # distributed workspace
 # --------------------------------------------------------------------------
@@ -91,6 +114,18 @@ class DistCgWorkspace:
         if L.krylov_b200_dist_init(self.ws._h, rank, world, len(hr), hr.ctypes.data_as(C.c_void_p),
                                    ho.ctypes.data_as(C.c_void_p)) != 0:
             raise RuntimeError(_lib.last_error())
+        # push mode: if what every peer needs from me is a few contiguous row ranges, producers store those
+        # entries straight into the peers' halo buffers (no fine-grained P2P loads in the SpMV)
+        maps = [None] * world
+        dist.all_gather_object(maps, (hr, ho))
+        ranges = push_ranges(maps, rank)
+        self.push_mode = ranges is not None and os.environ.get("KB200_DIST_PULL", "0") != "1"
+        if self.push_mode:
+            flat = np.ascontiguousarray(np.array(ranges, dtype=np.int32).reshape(-1))
+            nh = np.ascontiguousarray(np.array([len(m[0]) for m in maps], dtype=np.int32))
+            if L.krylov_b200_dist_set_push(self.ws._h, len(ranges), flat.ctypes.data_as(C.c_void_p),
+                                           nh.ctypes.data_as(C.c_void_p)) != 0:
+                raise RuntimeError(_lib.last_error())
         nb = L.krylov_b200_dist_handle_bytes()
         mine = (C.c_ubyte * nb)()
         if L.krylov_b200_dist_export(self.ws._h, mine) != 0:

@@ -120,3 +120,24 @@ def test_handle_exchange_plumbing_gloo_world2(tmp_path):
                          capture_output=True, text=True, timeout=240, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_push_ranges_for_slabs_and_fallback():
+    N, world = 6, 4
+    bounds, rs, blocks = _blocks(N, world)
+    maps = [(b[4], b[5]) for b in blocks]
+    for r in range(world):
+        rg = D.push_ranges(maps, r)
+        assert rg is not None and len(rg) == (r > 0) + (r < world - 1)
+        nloc = rs[r + 1] - rs[r]
+        for start, count, peer, slot in rg:
+            assert count == N * N and abs(peer - r) == 1
+            # the lower neighbour needs my FIRST plane, the upper one my LAST plane
+            assert start == (0 if peer < r else nloc - N * N)
+            # slot: where my plane sits in the peer's halo ([lower halo | upper halo])
+            assert slot == (0 if (peer > r and peer - 1 == r and r == peer - 1 and peer == 0) else slot)
+            hr, ho = maps[peer]
+            assert np.all(hr[slot:slot + count] == r) and np.array_equal(ho[slot:slot + count], np.arange(start, start + count))
+    # a scattered need (every other row) is not a contiguous range -> pull mode
+    bad = [(np.array([1, 1], dtype=np.int32), np.array([0, 2], dtype=np.int32)), (np.zeros(0, np.int32), np.zeros(0, np.int32))]
+    assert D.push_ranges(bad, 1) is None
