@@ -261,7 +261,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
 
   static bool attr_set = false;
   if (A.tma_ok && !attr_set) {
-    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
@@ -273,7 +273,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
     int occ = 0;
     if (dist) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, true, 3>, kTileThreads, A.smem_bytes));
     else if (A.ctas_per_sm >= 4) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, false, 4>, kTileThreads, A.smem_bytes));
-    else KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, false, 3>, kTileThreads, A.smem_bytes));
+    else KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, false, 1>, kTileThreads, A.smem_bytes));
     if (occ < 1) throw std::runtime_error("cg_k1_tma does not fit on an SM with the planned shared-memory ring");
     const int resident = std::min(occ, A.ctas_per_sm) * sm_count();
     k1_grid = std::min(resident, std::max(1, A.ntiles));
@@ -343,7 +343,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
       if (A.tma_ok) {
         if (dist) cg_k1_tma<T, true, 3><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
         else if (A.ctas_per_sm >= 4) cg_k1_tma<T, false, 4><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
-        else cg_k1_tma<T, false, 3><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
+        else cg_k1_tma<T, false, 1><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
       } else {
         if (dist) cg_k1_rows<T, true><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
         else cg_k1_rows<T, false><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);

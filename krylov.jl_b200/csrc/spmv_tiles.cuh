@@ -113,23 +113,21 @@ __device__ __forceinline__ void spmv_tiles_run(const Csr<T>& A, unsigned char* s
 
   if (warp == kConsumerWarps) {
     // ------------------------------ producer ------------------------------
-    // Lane 0 issues the TMA copies.  With a ring of >= 3 stages the whole warp then walks the column indices
-    // of the tile issued ONE iteration earlier (landed, but still queued behind the tile the consumers are
-    // working on) and prefetches the x entries it will gather into L2, so the consumers' first-touch gathers
-    // (the leading-edge diagonal of a stencil) hit L2 instead of paying a DRAM round trip per tile.
-    const uint64_t pol = l2_evict_first_policy();
-    const bool walk = (S >= 3) && A.prefetch_x;
-    int it = 0;
-    int t = blockIdx.x;
-    int k0 = 0, k1 = 0, pk0 = 0, pk1 = 0, wk0_prev = 0, wk1_prev = 0;
-    if (lane == 0 && t < A.ntiles) { k0 = __ldg(&A.rowptr[t * kTileRows]); k1 = __ldg(&A.rowptr[min(t * kTileRows + kTileRows, A.n)]); }
-    for (; t < A.ntiles; t += gridDim.x, it++) {
-      const int s = it % S;
-      if (lane == 0) {
+    // (Tried and removed, profiles/r1_sweep_k1.txt + r1_ab.txt: letting the whole producer warp walk the column
+    //  indices of the queued tile and prefetch its x entries into L2 -- no gain at 3 stages, and the extra live
+    //  state cost the kernel its 3-CTAs/SM register budget: 335 vs 299 us per iteration on the same GPU.)
+    if (lane == 0) {
+      const uint64_t pol = l2_evict_first_policy();
+      int it = 0;
+      int t = blockIdx.x;
+      int k0 = 0, k1 = 0;
+      if (t < A.ntiles) { k0 = __ldg(&A.rowptr[t * kTileRows]); k1 = __ldg(&A.rowptr[min(t * kTileRows + kTileRows, A.n)]); }
+      for (; t < A.ntiles; t += gridDim.x, it++) {
         // start fetching the NEXT tile's nnz range before blocking on the ring slot
         const int tn = t + gridDim.x;
         int nk0 = 0, nk1 = 0;
         if (tn < A.ntiles) { nk0 = __ldg(&A.rowptr[tn * kTileRows]); nk1 = __ldg(&A.rowptr[min(tn * kTileRows + kTileRows, A.n)]); }
+        const int s = it % S;
         mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
         unsigned char* st = ring + (size_t)s * L.stage_bytes();
         const int r0 = t * kTileRows;
@@ -142,22 +140,7 @@ __device__ __forceinline__ void spmv_tiles_run(const Csr<T>& A, unsigned char* s
         tma_load_1d(st, A.rowptr + r0, rp_b, &full[s], pol);
         if (v_b) tma_load_1d(st + L.rp_bytes(), A.val + k0v, v_b, &full[s], pol);
         if (c_b) tma_load_1d(st + L.rp_bytes() + L.val_bytes(), A.colind + k0c, c_b, &full[s], pol);
-        pk0 = k0; pk1 = k1;
         k0 = nk0; k1 = nk1;
-      }
-      if (walk) {
-        // tile of iteration it-1 (slot sp); its [k0,k1) travels from lane 0 by shuffle
-        const int wk0 = __shfl_sync(0xffffffffu, pk0, 0), wk1 = __shfl_sync(0xffffffffu, pk1, 0);
-        // lane 0's pk* now describe iteration `it`; the values for it-1 were shuffled on the previous trip
-        if (it > 0) {
-          const int sp = (it - 1) % S;
-          mbar_wait(&full[sp], ((it - 1) / S) & 1);           // non-consuming wait: the copy has landed
-          const unsigned char* stp = ring + (size_t)sp * L.stage_bytes();
-          const int* csp = reinterpret_cast<const int*>(stp + L.rp_bytes() + L.val_bytes());
-          const int coff = wk0_prev & ~3;
-          for (int k = wk0_prev + lane; k < wk1_prev; k += 32) gather.prefetch(csp[k - coff]);
-        }
-        wk0_prev = wk0; wk1_prev = wk1;
       }
     }
   } else {
