@@ -102,13 +102,17 @@ def build_problem(N, torch, device, k_lo=0, k_hi=None):
     return rp, ci, va
 
 
+_CPU_PROBLEM = {}
+
+
 def cpu_leg(N, iters, threads, budget_s=20.0):
     """Times the CPU restatement of the same loop (oracle/, kind 'port') on a bounded sample of the workload:
     the same matrix, fewer iterations (sized for ~10-30 s)."""
     from krylov_b200.problems import div_grad_csr
     from oracle import oracle as O
-    rp, ci, va = div_grad_csr(N)
-    b = np.ones(N ** 3)
+    if N not in _CPU_PROBLEM:
+        _CPU_PROBLEM[N] = div_grad_csr(N) + (np.ones(N ** 3),)
+    rp, ci, va, b = _CPU_PROBLEM[N]
     t, _, _ = O.cg_timed(rp, ci, va, b, 2, threads)           # calibrate
     per_it = max(t / 2, 1e-6)
     k = int(max(3, min(iters, budget_s / per_it)))

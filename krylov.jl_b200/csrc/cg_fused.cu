@@ -89,12 +89,17 @@ __device__ __forceinline__ bool cg_global_sum(CgState<T>* st, DistComm* dc, T& v
   return true;
 }
 
-template <class T, bool DIST>
-struct PVal {               // p_j = z_j + beta p_j, for local and (DIST) halo columns
+// MODE is a compile-time variant so that the plain path carries no dead branches inside the 8-deep gather batch
+// (a run-time `if (mdiag)` between the loads cost 11 % of K1: profiles/r1_ab.txt):
+//   0 = single GPU, M = I      1 = row-partitioned (halo columns)      2 = single GPU, Diagonal M (Jacobi)
+constexpr int kPlain = 0, kDist = 1, kJacobi = 2;
+
+template <class T, int MODE>
+struct PVal {               // p_j = z_j + beta p_j, for local and (kDist) halo columns
   const T* r; const T* p_old; T beta; const CgPeers<T>* peers;
   const T* mdiag;           // Jacobi / Diagonal M (cg.jl:241 z = M r applied on the fly); nullptr: M = I, z == r
   __device__ __forceinline__ T operator()(int j) const {
-    if (DIST && j >= peers->halo.nloc) {
+    if (MODE == kDist && j >= peers->halo.nloc) {
       const int h = j - peers->halo.nloc;
       if (peers->r_halo)     // push mode: the owners stored these entries into my halo buffers
         return add_rn(__ldg(&peers->r_halo[h]), mul_rn(beta, __ldg(&peers->p_halo_old[h])));
@@ -102,21 +107,21 @@ struct PVal {               // p_j = z_j + beta p_j, for local and (DIST) halo c
       return add_rn(__ldg(&peers->r[rk][off]), mul_rn(beta, __ldg(&peers->p_old[rk][off])));
     }
     T z = __ldg(&r[j]);
-    if (mdiag) z = mul_rn(__ldg(&mdiag[j]), z);
+    if (MODE == kJacobi) z = mul_rn(__ldg(&mdiag[j]), z);
     return add_rn(z, mul_rn(beta, __ldg(&p_old[j])));
   }
   __device__ __forceinline__ void prefetch(int j) const {      // L2 prefetch hook of the tile pipeline
-    if (DIST && j >= peers->halo.nloc) return;
+    if (MODE == kDist && j >= peers->halo.nloc) return;
     prefetch_l2(&r[j]);
     prefetch_l2(&p_old[j]);
-    if (mdiag) prefetch_l2(&mdiag[j]);
+    if (MODE == kJacobi) prefetch_l2(&mdiag[j]);
   }
 };
 
 // ---- K1, TMA-staged -------------------------------------------------------
 // MINB = 4 caps the kernel at 56 registers so four CTAs fit on an SM (a few bytes of spill); MINB = 1 leaves
 // ptxas free (72 registers, three CTAs).  The plan's CTAs-per-SM choice selects the variant.
-template <class T, bool DIST, int MINB>
+template <class T, int MODE, int MINB>
 __global__ void __launch_bounds__(kTileThreads, MINB) cg_k1_tma(Csr<T> A, const T* __restrict__ r, const T* __restrict__ p_old,
                                                           T* __restrict__ p_new, T* __restrict__ Ap, CgState<T>* st,
                                                           T* part, unsigned* ticket, DistComm* dc, CgPeers<T> peers) {
@@ -124,28 +129,29 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_k1_tma(Csr<T> A, const 
   __shared__ T sm[32];
   if (*(volatile int*)&st->done) return;
   T dacc = T(0);
-  const PVal<T, DIST> pval{r, p_old, st->beta, &peers, peers.mdiag};
+  const PVal<T, MODE> pval{r, p_old, st->beta, &peers, peers.mdiag};
   spmv_tiles_run<T>(A, smem, pval, pval, [&](int row, T acc, T pn) {
     p_new[row] = pn;
-    if (DIST) peers.push_p(row, pn);
+    if (MODE == kDist) peers.push_p(row, pn);
     Ap[row] = acc;
     dacc += pn * acc;
   });
+  if (MODE == kDist) __threadfence_system();   // pushed halo entries visible to the peers before the all-reduce
   T mine[1] = {block_sum(dacc, sm)}, tot[1];
   if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) {
-    if (cg_global_sum(st, DIST ? dc : nullptr, tot[0])) cg_k1_finalize(st, tot[0]);
+    if (cg_global_sum(st, MODE == kDist ? dc : nullptr, tot[0])) cg_k1_finalize(st, tot[0]);
   }
 }
 
 // ---- K1, row-per-thread LDG (when the tile plan does not fit) --------------
-template <class T, bool DIST>
+template <class T, int MODE>
 __global__ void __launch_bounds__(kBlock) cg_k1_rows(Csr<T> A, const T* __restrict__ r, const T* __restrict__ p_old,
                                                      T* __restrict__ p_new, T* __restrict__ Ap, CgState<T>* st, T* part,
                                                      unsigned* ticket, DistComm* dc, CgPeers<T> peers) {
   __shared__ T sm[32];
   if (*(volatile int*)&st->done) return;
   T dacc = T(0);
-  const PVal<T, DIST> pval{r, p_old, st->beta, &peers, peers.mdiag};
+  const PVal<T, MODE> pval{r, p_old, st->beta, &peers, peers.mdiag};
   const int stride = gridDim.x * blockDim.x;
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < A.n; row += stride) {
     const int kb = A.rowptr[row], ke = A.rowptr[row + 1];
@@ -153,18 +159,19 @@ __global__ void __launch_bounds__(kBlock) cg_k1_rows(Csr<T> A, const T* __restri
     for (int k = kb; k < ke; k++) acc = add_rn(acc, mul_rn(A.val[k], pval(A.colind[k])));
     const T pn = pval(row);
     p_new[row] = pn;
-    if (DIST) peers.push_p(row, pn);
+    if (MODE == kDist) peers.push_p(row, pn);
     Ap[row] = acc;
     dacc += pn * acc;
   }
+  if (MODE == kDist) __threadfence_system();
   T mine[1] = {block_sum(dacc, sm)}, tot[1];
   if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) {
-    if (cg_global_sum(st, DIST ? dc : nullptr, tot[0])) cg_k1_finalize(st, tot[0]);
+    if (cg_global_sum(st, MODE == kDist ? dc : nullptr, tot[0])) cg_k1_finalize(st, tot[0]);
   }
 }
 
 // ---- K2 -------------------------------------------------------------------
-template <class T>
+template <class T, int MODE>   // kPlain | kDist (push_r may be active) | kJacobi
 __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p,
                                                 const T* __restrict__ Ap, CgState<T>* st, T* part, unsigned* ticket,
                                                 DistComm* dc, const T* __restrict__ mdiag, PushPlan<T> push_r) {
@@ -189,8 +196,8 @@ __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __r
       x[j] = add_rn(xv[u], mul_rn(alpha, pv[u]));
       const T rn = add_rn(rv[u], mul_rn(nalpha, av[u]));
       r[j] = rn;
-      if (push_r.nranges) push_r(j, rn);                            // row-partitioned: neighbours' halo copy of r
-      acc += rn * (mdiag ? mul_rn(__ldg(&mdiag[j]), rn) : rn);      // <r, z>, z = M r (cg.jl:241-242)
+      if (MODE == kDist) push_r(j, rn);                             // row-partitioned: neighbours' halo copy of r
+      acc += rn * (MODE == kJacobi ? mul_rn(__ldg(&mdiag[j]), rn) : rn);   // <r, z>, z = M r (cg.jl:241-242)
     }
   }
   for (; i < n; i += stride) {
@@ -198,9 +205,10 @@ __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __r
     x[j] = add_rn(x[j], mul_rn(alpha, p[j]));
     const T rn = add_rn(r[j], mul_rn(nalpha, Ap[j]));
     r[j] = rn;
-    if (push_r.nranges) push_r(j, rn);
-    acc += rn * (mdiag ? mul_rn(__ldg(&mdiag[j]), rn) : rn);
+    if (MODE == kDist) push_r(j, rn);
+    acc += rn * (MODE == kJacobi ? mul_rn(__ldg(&mdiag[j]), rn) : rn);
   }
+  if (MODE == kDist) __threadfence_system();
   T mine[1] = {block_sum(acc, sm)}, tot[1];
   if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) {
     if (cg_global_sum(st, dc, tot[0])) cg_k2_finalize(st, tot[0]);
@@ -261,19 +269,24 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
 
   static bool attr_set = false;
   if (A.tma_ok && !attr_set) {
-    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, kPlain, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, kPlain, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, kPlain, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, kDist, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, kJacobi, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
+  const bool jac = ws.mdiag_fused != nullptr;
   // The persistent grid must equal what is actually co-resident: a register count that silently drops the
   // occupancy below the plan's CTAs/SM would otherwise run the tiles in 1.5 waves (measured: K1 2.2x slower).
   int k1_grid = A.grid;
   if (A.tma_ok) {
     int occ = 0;
-    if (dist) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, true, 3>, kTileThreads, A.smem_bytes));
-    else if (A.ctas_per_sm >= 4) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, false, 4>, kTileThreads, A.smem_bytes));
-    else KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, false, 1>, kTileThreads, A.smem_bytes));
+    if (dist) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, kDist, 3>, kTileThreads, A.smem_bytes));
+    else if (jac) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, kJacobi, 3>, kTileThreads, A.smem_bytes));
+    else if (A.ctas_per_sm >= 4) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, kPlain, 4>, kTileThreads, A.smem_bytes));
+    else if (A.ctas_per_sm == 3) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, kPlain, 3>, kTileThreads, A.smem_bytes));
+    else KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, kPlain, 1>, kTileThreads, A.smem_bytes));
     if (occ < 1) throw std::runtime_error("cg_k1_tma does not fit on an SM with the planned shared-memory ring");
     const int resident = std::min(occ, A.ctas_per_sm) * sm_count();
     k1_grid = std::min(resident, std::max(1, A.ntiles));
@@ -341,15 +354,20 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
       const bool timed = o.time_kernels && ti >= 0 && ti < kTimedCount;
       if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti], c.stream));
       if (A.tma_ok) {
-        if (dist) cg_k1_tma<T, true, 3><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
-        else if (A.ctas_per_sm >= 4) cg_k1_tma<T, false, 4><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
-        else cg_k1_tma<T, false, 1><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
+        if (dist) cg_k1_tma<T, kDist, 3><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
+        else if (jac) cg_k1_tma<T, kJacobi, 3><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
+        else if (A.ctas_per_sm >= 4) cg_k1_tma<T, kPlain, 4><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
+        else if (A.ctas_per_sm == 3) cg_k1_tma<T, kPlain, 3><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
+        else cg_k1_tma<T, kPlain, 1><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
       } else {
-        if (dist) cg_k1_rows<T, true><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
-        else cg_k1_rows<T, false><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
+        if (dist) cg_k1_rows<T, kDist><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
+        else if (jac) cg_k1_rows<T, kJacobi><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
+        else cg_k1_rows<T, kPlain><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
       }
       if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti + 1], c.stream));
-      cg_k2<T><<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3, dist ? c.dcomm : nullptr, md, push_r);
+      if (dist) cg_k2<T, kDist><<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3, c.dcomm, md, push_r);
+      else if (jac) cg_k2<T, kJacobi><<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3, nullptr, md, push_r);
+      else cg_k2<T, kPlain><<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3, nullptr, md, push_r);
       if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti + 2], c.stream));
       c.launches += 2;
     }

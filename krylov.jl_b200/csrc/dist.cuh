@@ -57,10 +57,7 @@ struct PushPlan {
   __device__ __forceinline__ void operator()(int row, T v) const {
     for (int q = 0; q < nranges; q++) {
       const unsigned d = (unsigned)(row - rg[q].start);
-      if (d < (unsigned)rg[q].count) {
-        dst[q][rg[q].slot + d] = v;
-        __threadfence_system();      // visible to the peer before this CTA's partial can reach the all-reduce
-      }
+      if (d < (unsigned)rg[q].count) dst[q][rg[q].slot + d] = v;   // (the kernel fences once per thread afterwards)
     }
   }
 };

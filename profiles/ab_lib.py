@@ -32,7 +32,7 @@ print(json.dumps(dict(lib=os.path.basename(os.environ.get("KB200_LIB", "current"
                       us_per_iter=round(e0.elapsed_time(e1) * 1e3 / 500, 1))))
 ''' % (ROOT, os.path.join(ROOT, "krylov.jl_b200"))
 old = os.path.join(ROOT, "krylov.jl_b200", "lib_ab", "libkrylov_b200_f96d5dc.so")
-runs = [(old, "2", "3", "0"), (None, "2", "3", "0"), (old, "2", "3", "0"), (None, "2", "3", "0")]
+runs = [(old, "2", "3", "0"), (None, "2", "3", "0"), (None, "3", "2", "0"), (None, "4", "2", "0"), (old, "2", "3", "0"), (None, "2", "3", "0"), (None, "3", "3", "0")]
 for lib, s, c, p in runs:
     env = dict(os.environ, KB200_STAGES=s, KB200_CTAS_PER_SM=c, KB200_PREFETCH=p)
     if lib:
