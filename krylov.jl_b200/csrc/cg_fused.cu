@@ -129,14 +129,15 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_k1_tma(Csr<T> A, const 
   __shared__ T sm[32];
   if (*(volatile int*)&st->done) return;
   T dacc = T(0);
+  bool sent = false;
   const PVal<T, MODE> pval{r, p_old, st->beta, &peers, peers.mdiag};
   spmv_tiles_run<T>(A, smem, pval, pval, [&](int row, T acc, T pn) {
     p_new[row] = pn;
-    if (MODE == kDist) peers.push_p(row, pn);
+    if (MODE == kDist) sent |= peers.push_p(row, pn);
     Ap[row] = acc;
     dacc += pn * acc;
   });
-  if (MODE == kDist) __threadfence_system();   // pushed halo entries visible to the peers before the all-reduce
+  if (MODE == kDist && sent) __threadfence_system();   // pushed halo entries visible to the peers before the all-reduce
   T mine[1] = {block_sum(dacc, sm)}, tot[1];
   if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) {
     if (cg_global_sum(st, MODE == kDist ? dc : nullptr, tot[0])) cg_k1_finalize(st, tot[0]);
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(kBlock) cg_k1_rows(Csr<T> A, const T* __restri
   __shared__ T sm[32];
   if (*(volatile int*)&st->done) return;
   T dacc = T(0);
+  bool sent = false;
   const PVal<T, MODE> pval{r, p_old, st->beta, &peers, peers.mdiag};
   const int stride = gridDim.x * blockDim.x;
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < A.n; row += stride) {
@@ -159,11 +161,11 @@ __global__ void __launch_bounds__(kBlock) cg_k1_rows(Csr<T> A, const T* __restri
     for (int k = kb; k < ke; k++) acc = add_rn(acc, mul_rn(A.val[k], pval(A.colind[k])));
     const T pn = pval(row);
     p_new[row] = pn;
-    if (MODE == kDist) peers.push_p(row, pn);
+    if (MODE == kDist) sent |= peers.push_p(row, pn);
     Ap[row] = acc;
     dacc += pn * acc;
   }
-  if (MODE == kDist) __threadfence_system();
+  if (MODE == kDist && sent) __threadfence_system();
   T mine[1] = {block_sum(dacc, sm)}, tot[1];
   if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) {
     if (cg_global_sum(st, MODE == kDist ? dc : nullptr, tot[0])) cg_k1_finalize(st, tot[0]);
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __r
   if (*(volatile int*)&st->done) return;
   const T alpha = st->alpha, nalpha = -alpha;
   T acc = T(0);
+  bool sent = false;
   // (Measured and rejected, profiles/r1_sweep_k1.txt: walking K2 downwards with evict-first x accesses to reuse
   //  the L2 tails left by K1 made K2 13 % and the following K1 8 % SLOWER -- ascending plain accesses stay.)
   const int stride = gridDim.x * blockDim.x;
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __r
       x[j] = add_rn(xv[u], mul_rn(alpha, pv[u]));
       const T rn = add_rn(rv[u], mul_rn(nalpha, av[u]));
       r[j] = rn;
-      if (MODE == kDist) push_r(j, rn);                             // row-partitioned: neighbours' halo copy of r
+      if (MODE == kDist) sent |= push_r(j, rn);                             // row-partitioned: neighbours' halo copy of r
       acc += rn * (MODE == kJacobi ? mul_rn(__ldg(&mdiag[j]), rn) : rn);   // <r, z>, z = M r (cg.jl:241-242)
     }
   }
@@ -205,10 +208,10 @@ __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __r
     x[j] = add_rn(x[j], mul_rn(alpha, p[j]));
     const T rn = add_rn(r[j], mul_rn(nalpha, Ap[j]));
     r[j] = rn;
-    if (MODE == kDist) push_r(j, rn);
+    if (MODE == kDist) sent |= push_r(j, rn);
     acc += rn * (MODE == kJacobi ? mul_rn(__ldg(&mdiag[j]), rn) : rn);
   }
-  if (MODE == kDist) __threadfence_system();
+  if (MODE == kDist && sent) __threadfence_system();
   T mine[1] = {block_sum(acc, sm)}, tot[1];
   if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) {
     if (cg_global_sum(st, dc, tot[0])) cg_k2_finalize(st, tot[0]);

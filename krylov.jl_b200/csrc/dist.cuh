@@ -54,11 +54,14 @@ struct PushPlan {
   int nranges;                       // 0: pull mode
   PushRange rg[kMaxPushRanges];
   T* dst[kMaxPushRanges];            // peer halo buffer (for the vector being produced) per range
-  __device__ __forceinline__ void operator()(int row, T v) const {
+  // Returns true if `row` was sent somewhere: only those threads need the system-scope fence afterwards.
+  __device__ __forceinline__ bool operator()(int row, T v) const {
+    bool sent = false;
     for (int q = 0; q < nranges; q++) {
       const unsigned d = (unsigned)(row - rg[q].start);
-      if (d < (unsigned)rg[q].count) dst[q][rg[q].slot + d] = v;   // (the kernel fences once per thread afterwards)
+      if (d < (unsigned)rg[q].count) { dst[q][rg[q].slot + d] = v; sent = true; }
     }
+    return sent;
   }
 };
 
