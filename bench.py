@@ -211,8 +211,8 @@ def main():
     # per-kernel breakdown: launches 8..39 of each fused kernel bracketed by CUDA events inside the library
     ws.solve(None, b, time_kernels=True, **solve_kw)
     k1_ms, k2_ms, timed = ws.kernel_times
-    B_k1 = nnz * 12 + (n + 1) * 4 + 4 * n * 8      # matrix + read r,p + write p,Ap
-    B_k2 = 6 * n * 8                               # read x,r,p,Ap + write x,r
+    B_k1 = nnz * 12 + (n + 1) * 4 + 6 * n * 8      # matrix + read r,p,x + write p,Ap,x  (x update rides in K1)
+    B_k2 = 3 * n * 8                               # read r,Ap + write r
     kernels = dict(cg_k1_tma=dict(ms=k1_ms, bytes=B_k1, GBs=B_k1 / (k1_ms * 1e-3) / 1e9 if k1_ms else None),
                    cg_k2=dict(ms=k2_ms, bytes=B_k2, GBs=B_k2 / (k2_ms * 1e-3) / 1e9 if k2_ms else None),
                    timed_iterations=timed, share_k1=k1_ms / (k1_ms + k2_ms) if k1_ms else None)

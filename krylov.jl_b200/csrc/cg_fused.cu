@@ -121,21 +121,42 @@ struct PVal {               // p_j = z_j + beta p_j, for local and (kDist) halo 
 // ---- K1, TMA-staged -------------------------------------------------------
 // MINB = 4 caps the kernel at 56 registers so four CTAs fit on an SM (a few bytes of spill); MINB = 1 leaves
 // ptxas free (72 registers, three CTAs).  The plan's CTAs-per-SM choice selects the variant.
-template <class T, int MODE, int MINB>
+//
+// XUP: K1 of iteration k also applies the PREVIOUS iteration's solution update x += alpha_{k-1} p_{k-1}
+// (cg.jl:239).  K1 holds p_{k-1}[row] in a register anyway (it forms p_k = z + beta p_{k-1}), so moving the update
+// here removes K2's read of p: one vector pass less per iteration (the 9nv of SURVEY's B_cg instead of 10nv).
+// The arithmetic is unchanged (same add/mul on the same operands); the update of the LAST iteration is applied
+// by the host loop at exit.  Not used when a callback must see a current x after every iteration.
+template <class T> struct RowPre { T pn, po, xr; };
+
+template <class T, int MODE, int MINB, bool XUP>
 __global__ void __launch_bounds__(kTileThreads, MINB) cg_k1_tma(Csr<T> A, const T* __restrict__ r, const T* __restrict__ p_old,
                                                           T* __restrict__ p_new, T* __restrict__ Ap, CgState<T>* st,
-                                                          T* part, unsigned* ticket, DistComm* dc, CgPeers<T> peers) {
+                                                          T* part, unsigned* ticket, DistComm* dc, CgPeers<T> peers,
+                                                          T* __restrict__ x) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ T sm[32];
   if (*(volatile int*)&st->done) return;
   T dacc = T(0);
   bool sent = false;
-  const PVal<T, MODE> pval{r, p_old, st->beta, &peers, peers.mdiag};
-  spmv_tiles_run<T>(A, smem, pval, pval, [&](int row, T acc, T pn) {
-    p_new[row] = pn;
-    if (MODE == kDist) sent |= peers.push_p(row, pn);
+  const T beta = st->beta, alpha_prev = st->alpha;
+  const bool xup = XUP && st->iter > 0;            // nothing pending before the first iteration
+  const PVal<T, MODE> pval{r, p_old, beta, &peers, peers.mdiag};
+  auto row_begin = [&](int row) {
+    RowPre<T> q;
+    q.po = __ldg(&p_old[row]);
+    T z = __ldg(&r[row]);
+    if (MODE == kJacobi) z = mul_rn(__ldg(&peers.mdiag[row]), z);
+    q.pn = add_rn(z, mul_rn(beta, q.po));
+    q.xr = xup ? x[row] : T(0);
+    return q;
+  };
+  spmv_tiles_run<T>(A, smem, pval, row_begin, [&](int row, T acc, RowPre<T> q) {
+    p_new[row] = q.pn;
+    if (MODE == kDist) sent |= peers.push_p(row, q.pn);
     Ap[row] = acc;
-    dacc += pn * acc;
+    if (xup) x[row] = add_rn(q.xr, mul_rn(alpha_prev, q.po));
+    dacc += q.pn * acc;
   });
   if (MODE == kDist && sent) __threadfence_system();   // pushed halo entries visible to the peers before the all-reduce
   T mine[1] = {block_sum(dacc, sm)}, tot[1];
@@ -145,14 +166,16 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_k1_tma(Csr<T> A, const 
 }
 
 // ---- K1, row-per-thread LDG (when the tile plan does not fit) --------------
-template <class T, int MODE>
+template <class T, int MODE, bool XUP>
 __global__ void __launch_bounds__(kBlock) cg_k1_rows(Csr<T> A, const T* __restrict__ r, const T* __restrict__ p_old,
                                                      T* __restrict__ p_new, T* __restrict__ Ap, CgState<T>* st, T* part,
-                                                     unsigned* ticket, DistComm* dc, CgPeers<T> peers) {
+                                                     unsigned* ticket, DistComm* dc, CgPeers<T> peers, T* __restrict__ x) {
   __shared__ T sm[32];
   if (*(volatile int*)&st->done) return;
   T dacc = T(0);
   bool sent = false;
+  const T alpha_prev = st->alpha;
+  const bool xup = XUP && st->iter > 0;
   const PVal<T, MODE> pval{r, p_old, st->beta, &peers, peers.mdiag};
   const int stride = gridDim.x * blockDim.x;
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < A.n; row += stride) {
@@ -163,6 +186,7 @@ __global__ void __launch_bounds__(kBlock) cg_k1_rows(Csr<T> A, const T* __restri
     p_new[row] = pn;
     if (MODE == kDist) sent |= peers.push_p(row, pn);
     Ap[row] = acc;
+    if (xup) x[row] = add_rn(x[row], mul_rn(alpha_prev, __ldg(&p_old[row])));
     dacc += pn * acc;
   }
   if (MODE == kDist && sent) __threadfence_system();
@@ -173,7 +197,8 @@ __global__ void __launch_bounds__(kBlock) cg_k1_rows(Csr<T> A, const T* __restri
 }
 
 // ---- K2 -------------------------------------------------------------------
-template <class T, int MODE>   // kPlain | kDist (push_r may be active) | kJacobi
+// XK2 = true: K2 also applies x += alpha p (cg.jl:239) -- used when K1 runs without XUP (callbacks / verbose).
+template <class T, int MODE, bool XK2>   // MODE: kPlain | kDist (push_r may be active) | kJacobi
 __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p,
                                                 const T* __restrict__ Ap, CgState<T>* st, T* part, unsigned* ticket,
                                                 DistComm* dc, const T* __restrict__ mdiag, PushPlan<T> push_r) {
@@ -191,12 +216,13 @@ __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __r
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int j = i + u * stride;
-      xv[u] = x[j]; rv[u] = r[j]; pv[u] = __ldg(&p[j]); av[u] = __ldg(&Ap[j]);
+      rv[u] = r[j]; av[u] = __ldg(&Ap[j]);
+      if (XK2) { xv[u] = x[j]; pv[u] = __ldg(&p[j]); }
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int j = i + u * stride;
-      x[j] = add_rn(xv[u], mul_rn(alpha, pv[u]));
+      if (XK2) x[j] = add_rn(xv[u], mul_rn(alpha, pv[u]));
       const T rn = add_rn(rv[u], mul_rn(nalpha, av[u]));
       r[j] = rn;
       if (MODE == kDist) sent |= push_r(j, rn);                             // row-partitioned: neighbours' halo copy of r
@@ -205,7 +231,7 @@ __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __r
   }
   for (; i < n; i += stride) {
     const int j = i;
-    x[j] = add_rn(x[j], mul_rn(alpha, p[j]));
+    if (XK2) x[j] = add_rn(x[j], mul_rn(alpha, p[j]));
     const T rn = add_rn(r[j], mul_rn(nalpha, Ap[j]));
     r[j] = rn;
     if (MODE == kDist) sent |= push_r(j, rn);
@@ -270,26 +296,38 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   KB_CUDA(cudaMemcpyAsync(dst, &hst[0], sizeof(St), cudaMemcpyHostToDevice, c.stream));
   c.sync();   // hst[0] is reused below as a read-back slot
 
-  static bool attr_set = false;
-  if (A.tma_ok && !attr_set) {
-    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, kPlain, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, kPlain, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, kPlain, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, kDist, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    KB_CUDA(cudaFuncSetAttribute(cg_k1_tma<T, kJacobi, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
-  }
   const bool jac = ws.mdiag_fused != nullptr;
+  const bool single_step = (o.callback != nullptr) || (o.timemax < 1e300) || o.verbose > 0;
+  // x += alpha p moves from K2 into the next K1 (one vector pass less) unless x must be current after every
+  // iteration (callbacks, verbose, time limits) -- KB200_XUP=0 keeps the update in K2 for A/B measurements.
+  const char* exu = getenv("KB200_XUP");
+  const bool xup = !single_step && !(exu && atoi(exu) == 0);
+  // All variants share one signature: pick the kernel once.
+  typedef void (*K1Fn)(Csr<T>, const T*, const T*, T*, T*, CgState<T>*, T*, unsigned*, DistComm*, CgPeers<T>, T*);
+  typedef void (*K2Fn)(int, T*, T*, const T*, const T*, CgState<T>*, T*, unsigned*, DistComm*, const T*, PushPlan<T>);
+  K1Fn k1 = nullptr;
+  K2Fn k2 = nullptr;
+  if (A.tma_ok) {
+    if (dist) k1 = xup ? cg_k1_tma<T, kDist, 3, true> : cg_k1_tma<T, kDist, 3, false>;
+    else if (jac) k1 = xup ? cg_k1_tma<T, kJacobi, 3, true> : cg_k1_tma<T, kJacobi, 3, false>;
+    else if (A.ctas_per_sm >= 4) k1 = xup ? cg_k1_tma<T, kPlain, 4, true> : cg_k1_tma<T, kPlain, 4, false>;
+    else if (A.ctas_per_sm == 3) k1 = xup ? cg_k1_tma<T, kPlain, 3, true> : cg_k1_tma<T, kPlain, 3, false>;
+    else k1 = xup ? cg_k1_tma<T, kPlain, 1, true> : cg_k1_tma<T, kPlain, 1, false>;
+  } else {
+    if (dist) k1 = xup ? cg_k1_rows<T, kDist, true> : cg_k1_rows<T, kDist, false>;
+    else if (jac) k1 = xup ? cg_k1_rows<T, kJacobi, true> : cg_k1_rows<T, kJacobi, false>;
+    else k1 = xup ? cg_k1_rows<T, kPlain, true> : cg_k1_rows<T, kPlain, false>;
+  }
+  if (dist) k2 = xup ? cg_k2<T, kDist, false> : cg_k2<T, kDist, true>;
+  else if (jac) k2 = xup ? cg_k2<T, kJacobi, false> : cg_k2<T, kJacobi, true>;
+  else k2 = xup ? cg_k2<T, kPlain, false> : cg_k2<T, kPlain, true>;
   // The persistent grid must equal what is actually co-resident: a register count that silently drops the
   // occupancy below the plan's CTAs/SM would otherwise run the tiles in 1.5 waves (measured: K1 2.2x slower).
   int k1_grid = A.grid;
   if (A.tma_ok) {
+    KB_CUDA(cudaFuncSetAttribute((const void*)k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     int occ = 0;
-    if (dist) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, kDist, 3>, kTileThreads, A.smem_bytes));
-    else if (jac) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, kJacobi, 3>, kTileThreads, A.smem_bytes));
-    else if (A.ctas_per_sm >= 4) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, kPlain, 4>, kTileThreads, A.smem_bytes));
-    else if (A.ctas_per_sm == 3) KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, kPlain, 3>, kTileThreads, A.smem_bytes));
-    else KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cg_k1_tma<T, kPlain, 1>, kTileThreads, A.smem_bytes));
+    KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1, kTileThreads, A.smem_bytes));
     if (occ < 1) throw std::runtime_error("cg_k1_tma does not fit on an SM with the planned shared-memory ring");
     const int resident = std::min(occ, A.ctas_per_sm) * sm_count();
     k1_grid = std::min(resident, std::max(1, A.ntiles));
@@ -332,7 +370,6 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
     }
   }
 
-  const bool single_step = (o.callback != nullptr) || (o.timemax < 1e300) || o.verbose > 0;
   int batch = o.batch > 0 ? o.batch : 16;
   if (batch > kHist / 2) batch = kHist / 2;
   if (single_step) batch = 1;
@@ -356,21 +393,11 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
       const int ti = enq - kTimedFirst;
       const bool timed = o.time_kernels && ti >= 0 && ti < kTimedCount;
       if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti], c.stream));
-      if (A.tma_ok) {
-        if (dist) cg_k1_tma<T, kDist, 3><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
-        else if (jac) cg_k1_tma<T, kJacobi, 3><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
-        else if (A.ctas_per_sm >= 4) cg_k1_tma<T, kPlain, 4><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
-        else if (A.ctas_per_sm == 3) cg_k1_tma<T, kPlain, 3><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
-        else cg_k1_tma<T, kPlain, 1><<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
-      } else {
-        if (dist) cg_k1_rows<T, kDist><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, c.dcomm, pe);
-        else if (jac) cg_k1_rows<T, kJacobi><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
-        else cg_k1_rows<T, kPlain><<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, nullptr, pe);
-      }
+      DistComm* dcm = dist ? c.dcomm : nullptr;
+      if (A.tma_ok) k1<<<k1_grid, kTileThreads, A.smem_bytes, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, dcm, pe, ws.x);
+      else k1<<<g1r, kBlock, 0, c.stream>>>(A, ws.r, p_old, p_new, ws.Ap, dst, part, c.tickets + 2, dcm, pe, ws.x);
       if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti + 1], c.stream));
-      if (dist) cg_k2<T, kDist><<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3, c.dcomm, md, push_r);
-      else if (jac) cg_k2<T, kJacobi><<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3, nullptr, md, push_r);
-      else cg_k2<T, kPlain><<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3, nullptr, md, push_r);
+      k2<<<g2, kBlock, 0, c.stream>>>(n, ws.x, ws.r, p_new, ws.Ap, dst, part, c.tickets + 3, dcm, md, push_r);
       if (timed) KB_CUDA(cudaEventRecord(tev[3 * ti + 2], c.stream));
       c.launches += 2;
     }
@@ -437,6 +464,9 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   const bool k1_exit = zero_curvature || last.npc;
   T* pcur = k1_exit ? P[(iter + 1) & 1] : P[iter & 1];
   if (pcur != ws.p) { T* tmp = ws.p; ws.p = ws.p2; ws.p2 = tmp; ws.dist.swapped = !ws.dist.swapped; }
+  // XUP: the x update of the last completed iteration has not been applied yet (the K1 that would have done it
+  // saw `done`).  A K1 exit applied its predecessor's update during its own pass, so nothing is pending then.
+  if (xup && !k1_exit && iter > 0) k_axpy<T>(c, n, last.alpha, ws.p, ws.x);
   if (last.npc) {                                   // linesearch branch, cg.jl:203-209
     if (iter == 0) k_copy<T>(c, n, ws.x, ws.p);
     k_copy<T>(c, n, ws.npc_dir, ws.p);

@@ -75,3 +75,26 @@ def test_fused_cg_with_jacobi_preconditioner(kb, O):
         assert st.niter == so["niter"] and np.allclose(st.residuals, so["residuals"], rtol=1e-6)
         assert np.linalg.norm(x - xo) <= 1e-7 * np.linalg.norm(xo)
     assert out[True][2] < out[False][2]
+
+
+def test_cg_x_update_in_k1_is_bit_identical(kb):
+    """Moving x += alpha p from K2 into the next K1 (XUP) changes no arithmetic: x, r and the residual history are
+    bit-identical to the K2 placement, for convergence exits, itmax exits and Float32."""
+    import os
+    from krylov_b200 import problems as P
+    for dt, kw in ((np.float64, dict(atol=0.0, rtol=1e-8)), (np.float64, dict(atol=0.0, rtol=0.0, itmax=7)),
+                   (np.float64, dict(atol=0.0, rtol=0.0, itmax=8)), (np.float32, dict())):
+        rp, ci, va = P.div_grad_csr(20, dtype=dt)
+        n = 20 ** 3
+        b = (np.arange(n) % 7 + 1).astype(dt)
+        outs = []
+        for flag in ("1", "0"):
+            os.environ["KB200_XUP"] = flag
+            ws = kb.CgWorkspace(n, n, dt)
+            ws.solve((rp, ci, va), b, history=True, **kw)
+            outs.append((ws.x, ws.vector("r"), ws.stats))
+            ws.free()
+        os.environ.pop("KB200_XUP", None)
+        (x1, r1, s1), (x0, r0, s0) = outs
+        assert s1.niter == s0.niter and s1.residuals == s0.residuals and s1.status == s0.status
+        assert np.array_equal(x1, x0) and np.array_equal(r1, r0)
