@@ -236,6 +236,14 @@ def main():
     e2e = dict(value=its / e2e_s, unit="it/s", h2d_bytes_per_step=n * 8, d2h_bytes_per_step=n * 8,
                ms_per_step=1e3 * e2e_s / args.steps)
 
+    # DRAM traffic per fused iteration from the committed ncu --set full capture of this same command
+    # (profiles/r1_ncu_cg_final.txt); only meaningful for the workload it was taken on
+    traffic = None
+    try:
+        if args.workload == "poisson215":
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["bytes_per_iteration"]
+    except Exception:
+        pass
     line = dict(metric="CG iterations/s", value=value, unit="it/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
                 data="synthetic",
@@ -243,7 +251,7 @@ def main():
                                      f"atol=rtol=0, itmax={iters} per step", n=n, nnz=nnz, iters_per_step=iters,
                             l2="inputs larger than L2 (matrix 0.87 GB vs 126 MB): no flush needed",
                             matrix_upload_s=round(upload_s, 3), matrix_generate_s=round(gen_s, 3)),
-                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                               peak_source=peak_src, bytes_per_iteration=B,
                               note="unit = one fused CG iteration (cg_k1 + cg_k2); B_cg from SURVEY.md 8(d)",
                               kernels=kernels),

@@ -110,12 +110,6 @@ struct PVal {               // p_j = z_j + beta p_j, for local and (kDist) halo 
     if (MODE == kJacobi) z = mul_rn(__ldg(&mdiag[j]), z);
     return add_rn(z, mul_rn(beta, __ldg(&p_old[j])));
   }
-  __device__ __forceinline__ void prefetch(int j) const {      // L2 prefetch hook of the tile pipeline
-    if (MODE == kDist && j >= peers->halo.nloc) return;
-    prefetch_l2(&r[j]);
-    prefetch_l2(&p_old[j]);
-    if (MODE == kJacobi) prefetch_l2(&mdiag[j]);
-  }
 };
 
 // ---- K1, TMA-staged -------------------------------------------------------

@@ -80,7 +80,6 @@ struct Csr {
   size_t smem_bytes = 0;    // dynamic smem of the staged kernels
   int grid = 0;             // persistent grid (multiple of the SM count)
   int ctas_per_sm = 0;      // resident CTAs per SM the ring was sized for
-  bool prefetch_x = true;   // producer warp prefetches the gathered x entries of queued tiles into L2 (stages >= 3)
 };
 
 template <class T> void csr_upload(Ctx& c, Csr<T>& A, int n, long long nnz, const void* rowptr, const void* colind,

@@ -158,8 +158,6 @@ template <class T> void csr_plan(Ctx& c, Csr<T>& A) {
     int g = sm_count() * per_sm;
     A.grid = g < A.ntiles ? g : (A.ntiles > 0 ? A.ntiles : 1);
     A.ctas_per_sm = per_sm;
-    const char* ep = getenv("KB200_PREFETCH");
-    A.prefetch_x = !(ep && atoi(ep) == 0);
   } else {
     A.stages = 0; A.smem_bytes = 0; A.grid = 0;
   }

@@ -57,14 +57,11 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// Plain x gather (y = A x): read-only path loads + the L2 prefetch hook of the tile pipeline.
+// Plain x gather (y = A x) through the read-only path.
 template <class T>
 struct XGather {
   const T* x;
   __device__ __forceinline__ T operator()(int j) const { return __ldg(&x[j]); }
-  __device__ __forceinline__ void prefetch(int j) const { prefetch_l2(&x[j]); }
 };
 
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
