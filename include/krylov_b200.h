@@ -201,6 +201,11 @@ int krylov_b200_dist_init(void *ws, int rank, int world, int nhalo, const int *h
  * rank's rows each peer needs; nhalo_all[world] = every rank's halo length.  The producing kernels then store
  * those entries directly into the peers' halo buffers and nobody issues fine-grained P2P loads. */
 int krylov_b200_dist_set_push(void *ws, int nranges, const int *ranges4, const int *nhalo_all);
+/* Send list of the general x-halo exchange that precedes every y = A x of a distributed workspace (all four
+ * solvers): entry e sends local row rows[e] to slot slots[e] of rank peers[e]'s halo.  nhalo_all[world] = every
+ * rank's halo length, nglobal = global number of rows.  Call after dist_init and before dist_export/import. */
+int krylov_b200_dist_set_sendlist(void *ws, int nsend, const int *rows, const int *peers, const int *slots,
+                                  const int *nhalo_all, long long nglobal);
 int krylov_b200_dist_export(void *ws, void *handles_out);
 int krylov_b200_dist_import(void *ws, const void *all_handles);
 

@@ -462,17 +462,18 @@ void* krylov_b200_stream(void* ws) {
 // ------------------------------ row-partitioned solves --------------------
 }  // extern "C" (templates below need C++ linkage)
 namespace {
-constexpr int kIpcHandles = 5;   // r, p, p2, mailbox, halo_buf
+constexpr int kIpcHandles = 6;   // r, p, p2, mailbox, halo_buf, xhalo
 constexpr size_t kMailDoubles = 2 * kMaxRanks;
 constexpr size_t kMailBytes = kMailDoubles * sizeof(double) + kMailDoubles * sizeof(unsigned long long);
 
 template <class T> int dist_init_t(Handle* h, int rank, int world, int nhalo, const int* halo_rank, const int* halo_off) {
   Workspace<T>* ws = W<T>(h);
-  if (h->solver != S_CG) throw std::runtime_error("row-partitioned solves are implemented for cg! only");
   if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) throw std::runtime_error("bad rank/world");
   KB_CUDA(cudaSetDevice(ws->ctx.device));
-  if (!ws->p2) ws->p2 = dev_alloc<T>((size_t)ws->n);
-  KB_CUDA(cudaMemset(ws->p2, 0, sizeof(T) * (size_t)ws->n));
+  if (h->solver == S_CG) {
+    if (!ws->p2) ws->p2 = dev_alloc<T>((size_t)ws->n);
+    KB_CUDA(cudaMemset(ws->p2, 0, sizeof(T) * (size_t)ws->n));
+  }
   ws->dist.rank = rank; ws->dist.world = world;
   int *dr = nullptr, *dof = nullptr;
   KB_CUDA(cudaMalloc((void**)&dr, sizeof(int) * (size_t)(nhalo > 0 ? nhalo : 1)));
@@ -488,6 +489,11 @@ template <class T> int dist_init_t(Handle* h, int rank, int world, int nhalo, co
   ws->dist.halo_buf = dev_alloc<T>(3 * (size_t)(nhalo > 0 ? nhalo : 1));
   KB_CUDA(cudaMemset(ws->dist.halo_buf, 0, sizeof(T) * 3 * (size_t)(nhalo > 0 ? nhalo : 1)));
   ws->dist.npush = 0;
+  // general x-halo exchange (all solvers): two sections of nhalo entries
+  ws->dist.xhalo = dev_alloc<T>(2 * (size_t)(nhalo > 0 ? nhalo : 1));
+  KB_CUDA(cudaMemset(ws->dist.xhalo, 0, sizeof(T) * 2 * (size_t)(nhalo > 0 ? nhalo : 1)));
+  ws->dist.nglobal = ws->n;
+  if (h->solver != S_CG) for (int i = 0; i < 3; i++) KB_CUDA(cudaMalloc(&ws->dist.dummy[i], 256));
   return 0;
 }
 
@@ -496,7 +502,11 @@ template <class T> int dist_export_t(Handle* h, void* out) {
   if (!ws->dist.mailbox) throw std::runtime_error("call krylov_b200_dist_init first");
   KB_CUDA(cudaSetDevice(ws->ctx.device));
   cudaIpcMemHandle_t* hs = (cudaIpcMemHandle_t*)out;
-  void* ptrs[kIpcHandles] = {ws->r, ws->p, ws->p2, ws->dist.mailbox, ws->dist.halo_buf};
+  // CG exports r/p/p2 for its in-kernel halo pull; the other solvers export three small placeholder allocations
+  void* vr = ws->kind == S_CG ? (void*)ws->r : ws->dist.dummy[0];
+  void* vp = ws->kind == S_CG ? (void*)ws->p : ws->dist.dummy[1];
+  void* vp2 = ws->kind == S_CG ? (void*)ws->p2 : ws->dist.dummy[2];
+  void* ptrs[kIpcHandles] = {vr, vp, vp2, ws->dist.mailbox, ws->dist.halo_buf, ws->dist.xhalo};
   for (int i = 0; i < kIpcHandles; i++) KB_CUDA(cudaIpcGetMemHandle(&hs[i], ptrs[i]));
   return 0;
 }
@@ -512,7 +522,7 @@ template <class T> int dist_import_t(Handle* h, const void* all) {
   for (int k = 0; k < D.world; k++) {
     void* ptr[kIpcHandles];
     if (k == D.rank) {
-      ptr[0] = ws->r; ptr[1] = ws->p; ptr[2] = ws->p2; ptr[3] = D.mailbox; ptr[4] = D.halo_buf;
+      ptr[0] = ws->r; ptr[1] = ws->p; ptr[2] = ws->p2; ptr[3] = D.mailbox; ptr[4] = D.halo_buf; ptr[5] = D.xhalo;
     } else {
       for (int i = 0; i < kIpcHandles; i++) {
         KB_CUDA(cudaIpcOpenMemHandle(&ptr[i], hs[k * kIpcHandles + i], cudaIpcMemLazyEnablePeerAccess));
@@ -521,10 +531,18 @@ template <class T> int dist_import_t(Handle* h, const void* all) {
     }
     D.r_peer[k] = (T*)ptr[0]; D.bufA_peer[k] = (T*)ptr[1]; D.bufB_peer[k] = (T*)ptr[2];
     D.halo_buf_peer[k] = (T*)ptr[4];
+    D.xhalo_peer[k] = (T*)ptr[5];
     hc.mail_val[k] = (double*)ptr[3];
     hc.mail_seq[k] = (unsigned long long*)((double*)ptr[3] + kMailDoubles);
   }
   D.swapped = false;
+  // plan of the general x-halo exchange (k_halo_exchange)
+  DistExchange* ex = ws->ctx.dex ? ws->ctx.dex : new DistExchange();
+  memset(ex, 0, sizeof(*ex));
+  ex->nsend = D.nsend; ex->send_row = D.send_row; ex->send_peer = D.send_peer; ex->send_slot = D.send_slot;
+  for (int k = 0; k < D.world; k++) { ex->xhalo_peer[k] = D.xhalo_peer[k]; ex->nhalo_peer[k] = D.nhalo_peer[k]; }
+  ex->xhalo = D.xhalo; ex->nhalo = D.halo.nhalo; ex->nloc = ws->n; ex->count = 0;
+  ws->ctx.dex = ex;
   if (!ws->ctx.dcomm) KB_CUDA(cudaMalloc((void**)&ws->ctx.dcomm, sizeof(DistComm)));
   KB_CUDA(cudaMemcpy(ws->ctx.dcomm, &hc, sizeof(DistComm), cudaMemcpyHostToDevice));
   return 0;
@@ -541,6 +559,28 @@ int krylov_b200_dist_init(void* ws, int rank, int world, int nhalo, const int* h
     return h->dtype == KRYLOV_FLOAT64 ? dist_init_t<double>(h, rank, world, nhalo, halo_rank, halo_off)
                                       : dist_init_t<float>(h, rank, world, nhalo, halo_rank, halo_off);
   } catch (const std::exception& e) { return fail("krylov_b200_dist_init", e); }
+}
+int krylov_b200_dist_set_sendlist(void* ws, int nsend, const int* rows, const int* peers, const int* slots,
+                                  const int* nhalo_all, long long nglobal) {
+  try {
+    Handle* h = lookup(ws);
+    if (!h) return fail("krylov_b200_dist_set_sendlist", "unknown workspace handle");
+    auto apply = [&](auto* w) {
+      KB_CUDA(cudaSetDevice(w->ctx.device));
+      auto up = [&](const int* src) {
+        int* d = nullptr;
+        KB_CUDA(cudaMalloc((void**)&d, sizeof(int) * (size_t)(nsend > 0 ? nsend : 1)));
+        if (nsend > 0) KB_CUDA(cudaMemcpy(d, src, sizeof(int) * (size_t)nsend, cudaMemcpyHostToDevice));
+        return d;
+      };
+      w->dist.send_row = up(rows); w->dist.send_peer = up(peers); w->dist.send_slot = up(slots);
+      w->dist.nsend = nsend;
+      for (int k = 0; k < w->dist.world; k++) w->dist.nhalo_peer[k] = nhalo_all[k];
+      w->dist.nglobal = nglobal;
+    };
+    if (h->dtype == KRYLOV_FLOAT64) apply(W<double>(h)); else apply(W<float>(h));
+    return 0;
+  } catch (const std::exception& e) { return fail("krylov_b200_dist_set_sendlist", e); }
 }
 int krylov_b200_dist_set_push(void* ws, int nranges, const int* ranges4, const int* nhalo_all) {
   try {

@@ -65,6 +65,24 @@ struct PushPlan {
   }
 };
 
+// General halo exchange for y = A x on ANY workspace vector (all four solvers, primitive and fused-phase
+// paths): every rank stores the entries of x its peers need into the peers' x-halo buffer (send list built from
+// the halo maps at setup), then the ranks meet in the in-kernel barrier; the SpMV that follows gathers column
+// j >= nloc from the local halo buffer.  Two halo sections alternate by exchange parity, and every solver has at
+// least one global reduction between two products, so a fast rank can never overwrite a section a slow rank is
+// still reading.  (The fused CG keeps its own cheaper scheme: it needs no extra launch.)
+struct DistExchange {
+  int nsend;                   // entries this rank sends per exchange
+  const int* send_row;         // [nsend] local row
+  const int* send_peer;        // [nsend] destination rank
+  const int* send_slot;        // [nsend] slot in the destination's halo
+  void* xhalo_peer[kMaxRanks]; // every rank's x-halo buffer: 2 sections of nhalo_peer[k] elements
+  int nhalo_peer[kMaxRanks];
+  void* xhalo;                 // this rank's x-halo buffer
+  int nhalo, nloc;
+  unsigned long long count;    // exchanges done so far (host-side mirror decides the parity)
+};
+
 __device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }

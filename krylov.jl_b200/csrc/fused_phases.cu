@@ -20,24 +20,28 @@ namespace kb {
 // generic launchers
 // ---------------------------------------------------------------------------
 template <class T, int K, class Epi, class Fin>
-__global__ void __launch_bounds__(kTileThreads) spmv_epi_tma(Csr<T> A, const T* __restrict__ x, Epi epi, Fin fin, T* part,
-                                                             unsigned* ticket) {
+__global__ void __launch_bounds__(kTileThreads) spmv_epi_tma(Csr<T> A, XGather<T> xg, Epi epi, Fin fin, T* part,
+                                                             unsigned* ticket, DistComm* dc) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ T sm[32];
   T d[K];
 #pragma unroll
   for (int k = 0; k < K; k++) d[k] = T(0);
   spmv_tiles_run<T>(
-      A, smem, XGather<T>{x}, NoRowBegin(), [&](int row, T acc, int) { epi(row, acc, d); });
+      A, smem, xg, NoRowBegin(), [&](int row, T acc, int) { epi(row, acc, d); });
   T mine[K], tot[K];
 #pragma unroll
   for (int k = 0; k < K; k++) mine[k] = block_sum(d[k], sm);
-  if (grid_sum_last<T, K>(mine, part, ticket, sm, tot) && threadIdx.x == 0) fin(tot);
+  if (grid_sum_last<T, K>(mine, part, ticket, sm, tot) && threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) tot[k] = dist_reduce(dc, tot[k]);     // row-partitioned: sum over ranks
+    fin(tot);
+  }
 }
 
 template <class T, int K, class Epi, class Fin>
-__global__ void __launch_bounds__(kBlock) spmv_epi_rows(Csr<T> A, const T* __restrict__ x, Epi epi, Fin fin, T* part,
-                                                        unsigned* ticket) {
+__global__ void __launch_bounds__(kBlock) spmv_epi_rows(Csr<T> A, XGather<T> xg, Epi epi, Fin fin, T* part,
+                                                        unsigned* ticket, DistComm* dc) {
   __shared__ T sm[32];
   T d[K];
 #pragma unroll
@@ -46,17 +50,21 @@ __global__ void __launch_bounds__(kBlock) spmv_epi_rows(Csr<T> A, const T* __res
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < A.n; row += stride) {
     const int kb = A.rowptr[row], ke = A.rowptr[row + 1];
     T acc = T(0);
-    for (int k = kb; k < ke; k++) acc = add_rn(acc, mul_rn(A.val[k], __ldg(&x[A.colind[k]])));
+    for (int k = kb; k < ke; k++) acc = add_rn(acc, mul_rn(A.val[k], xg(A.colind[k])));
     epi(row, acc, d);
   }
   T mine[K], tot[K];
 #pragma unroll
   for (int k = 0; k < K; k++) mine[k] = block_sum(d[k], sm);
-  if (grid_sum_last<T, K>(mine, part, ticket, sm, tot) && threadIdx.x == 0) fin(tot);
+  if (grid_sum_last<T, K>(mine, part, ticket, sm, tot) && threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) tot[k] = dist_reduce(dc, tot[k]);
+    fin(tot);
+  }
 }
 
 template <class T, int K, class Body, class Fin>
-__global__ void __launch_bounds__(kBlock) stream_epi(int n, Body body, Fin fin, T* part, unsigned* ticket) {
+__global__ void __launch_bounds__(kBlock) stream_epi(int n, Body body, Fin fin, T* part, unsigned* ticket, DistComm* dc) {
   __shared__ T sm[32];
   T d[K > 0 ? K : 1];
 #pragma unroll
@@ -72,7 +80,11 @@ __global__ void __launch_bounds__(kBlock) stream_epi(int n, Body body, Fin fin, 
     T mine[K > 0 ? K : 1], tot[K > 0 ? K : 1];
 #pragma unroll
     for (int k = 0; k < K; k++) mine[k] = block_sum(d[k], sm);
-    if (grid_sum_last<T, (K > 0 ? K : 1)>(mine, part, ticket, sm, tot) && threadIdx.x == 0) fin(tot);
+    if (grid_sum_last<T, (K > 0 ? K : 1)>(mine, part, ticket, sm, tot) && threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < K; k++) tot[k] = dist_reduce(dc, tot[k]);
+      fin(tot);
+    }
   }
 }
 
@@ -83,6 +95,8 @@ struct NoFin {
 template <class T, int K, class Epi, class Fin>
 static void launch_spmv_epi(Ctx& c, const Csr<T>& A, const T* x, Epi epi, Fin fin, int ticket) {
   if (A.n <= 0) return;
+  k_halo_exchange<T>(c, x);                // row-partitioned operators only
+  const XGather<T> xg = xgather_of<T>(c, x);
   if (A.tma_ok) {
     static bool attr = false;
     if (!attr) { KB_CUDA(cudaFuncSetAttribute(spmv_epi_tma<T, K, Epi, Fin>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
@@ -90,9 +104,9 @@ static void launch_spmv_epi(Ctx& c, const Csr<T>& A, const T* x, Epi epi, Fin fi
     KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_epi_tma<T, K, Epi, Fin>, kTileThreads, A.smem_bytes));
     if (occ < 1) throw std::runtime_error("spmv_epi_tma does not fit on an SM with the planned shared-memory ring");
     const int grid = std::min(std::min(occ, A.ctas_per_sm) * sm_count(), std::max(1, A.ntiles));
-    spmv_epi_tma<T, K, Epi, Fin><<<grid, kTileThreads, A.smem_bytes, c.stream>>>(A, x, epi, fin, (T*)c.partials, c.tickets + ticket);
+    spmv_epi_tma<T, K, Epi, Fin><<<grid, kTileThreads, A.smem_bytes, c.stream>>>(A, xg, epi, fin, (T*)c.partials, c.tickets + ticket, c.dcomm);
   } else {
-    spmv_epi_rows<T, K, Epi, Fin><<<stream_grid(A.n, 1, 8), kBlock, 0, c.stream>>>(A, x, epi, fin, (T*)c.partials, c.tickets + ticket);
+    spmv_epi_rows<T, K, Epi, Fin><<<stream_grid(A.n, 1, 8), kBlock, 0, c.stream>>>(A, xg, epi, fin, (T*)c.partials, c.tickets + ticket, c.dcomm);
   }
   KB_CUDA(cudaGetLastError());
   c.launches++;
@@ -101,7 +115,7 @@ static void launch_spmv_epi(Ctx& c, const Csr<T>& A, const T* x, Epi epi, Fin fi
 template <class T, int K, class Body, class Fin>
 static void launch_stream(Ctx& c, int n, Body body, Fin fin, int ticket) {
   if (n <= 0) return;
-  stream_epi<T, K, Body, Fin><<<stream_grid(n, 2, 8), kBlock, 0, c.stream>>>(n, body, fin, (T*)c.partials, c.tickets + ticket);
+  stream_epi<T, K, Body, Fin><<<stream_grid(n, 2, 8), kBlock, 0, c.stream>>>(n, body, fin, (T*)c.partials, c.tickets + ticket, c.dcomm);
   KB_CUDA(cudaGetLastError());
   c.launches++;
 }

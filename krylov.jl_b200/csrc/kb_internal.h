@@ -32,6 +32,7 @@ struct Ctx {
   void* hscal = nullptr;         // pinned mirror of dscal
   long long launches = 0;        // kernels launched through this context (bench: gpu_launches)
   DistComm* dcomm = nullptr;     // device-resident communicator of a row-partitioned solve (nullptr: single GPU)
+  DistExchange* dex = nullptr;   // host-side plan of the general x-halo exchange (nullptr: single GPU)
 
   void init(int dev);
   void destroy();
@@ -88,6 +89,9 @@ template <class T> void csr_free(Csr<T>& A);
 template <class T> void csr_plan(Ctx& c, Csr<T>& A);
 // y = A x.  variant: 0 auto (TMA-staged when the plan allows), 1 force row-per-thread LDG, 2 force TMA-staged
 template <class T> void k_spmv(Ctx& c, const Csr<T>& A, const T* x, T* y, int variant = 0);
+// Row-partitioned operators: send this rank's boundary entries of x to the peers' halo buffers and meet in the
+// in-kernel barrier (no-op on a single GPU).  Every y = A x on a distributed workspace is preceded by one.
+template <class T> void k_halo_exchange(Ctx& c, const T* x);
 // y = A x and  <x, y>  in one launch (result in dscal[slot])
 template <class T> void k_spmv_dot_dev(Ctx& c, const Csr<T>& A, const T* x, T* y, int slot);
 
@@ -187,6 +191,12 @@ struct Workspace {
     T* halo_buf = nullptr;                      // local halo buffers [r | p(bufA) | p(bufB)], nhalo entries each
     T* halo_buf_peer[kMaxRanks] = {};           // every rank's halo_buf
     int nhalo_peer[kMaxRanks] = {};             // every rank's halo length (section stride inside its halo_buf)
+    void* dummy[3] = {nullptr, nullptr, nullptr};  // placeholder IPC exports of the non-CG solvers
+    T* xhalo = nullptr;                         // general x-halo buffer (2 sections) of k_halo_exchange
+    T* xhalo_peer[kMaxRanks] = {};
+    int nsend = 0;                              // send list of the general exchange (device arrays)
+    int* send_row = nullptr; int* send_peer = nullptr; int* send_slot = nullptr;
+    long long nglobal = 0;                      // global number of rows (default itmax = 2 n)
     int npush = 0;                              // > 0: push mode (contiguous send ranges), else pull mode
     PushRange push[kMaxPushRanges];
   } dist;

@@ -66,6 +66,12 @@ template <class T> void ws_destroy(Workspace<T>* ws) {
   for (void* p : ws->dist.opened) cudaIpcCloseMemHandle(p);
   if (ws->dist.mailbox) cudaFree(ws->dist.mailbox);
   dev_free(ws->dist.halo_buf);
+  dev_free(ws->dist.xhalo);
+  for (void* d : ws->dist.dummy) if (d) cudaFree(d);
+  if (ws->dist.send_row) cudaFree(ws->dist.send_row);
+  if (ws->dist.send_peer) cudaFree(ws->dist.send_peer);
+  if (ws->dist.send_slot) cudaFree(ws->dist.send_slot);
+  delete ws->ctx.dex; ws->ctx.dex = nullptr;
   if (ws->dist.halo.src_rank) cudaFree((void*)ws->dist.halo.src_rank);
   if (ws->dist.halo.src_off) cudaFree((void*)ws->dist.halo.src_off);
   if (ws->ctx.dcomm) cudaFree(ws->ctx.dcomm);
@@ -106,8 +112,7 @@ void cg_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
   if (ws.warm_start && linesearch) throw std::runtime_error("warm_start and linesearch cannot be used together");
   if (o.verbose > 0) printf("CG: system of %d equations in %d variables\n", n, n);
   const bool MisI = M.is_identity();
-  if (ws.dist.world > 1 && (ws.warm_start || !cg_fused_eligible(A, M, o) || !MisI || o.callback))
-    throw std::runtime_error("row-partitioned cg!: only the fused path (CSR operator, M = I, radius = 0, no warm start, no callback) is distributed");
+  const bool dist = ws.dist.world > 1;
   allocate_if(!MisI, ws, ws.z);
   allocate_if(linesearch || radius > 0, ws, ws.npc_dir);
   T *dx = ws.dx, *x = ws.x, *r = ws.r, *Ap = ws.Ap;
@@ -140,7 +145,7 @@ void cg_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
     return;
   }
   int iter = 0;
-  int itmax = o.itmax == 0 ? 2 * n : o.itmax;
+  int itmax = o.itmax == 0 ? 2 * (int)(ws.dist.world > 1 ? ws.dist.nglobal : n) : o.itmax;
   T pAp = 0, pNorm2 = gamma;
   const T eps_tol = tol_of<T>(o.atol) + tol_of<T>(o.rtol) * rNorm;     // cg.jl:181
   if (o.verbose > 0) printf("%5s  %7s  %8s  %8s  %8s  %5s\n", "k", "‖r‖", "pAp", "α", "σ", "timer");
@@ -149,7 +154,9 @@ void cg_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
   bool inconsistent = false, on_boundary = false, zero_curvature = false, user_exit = false, overtimed = false;
   std::string status = "unknown";
 
-  if (cg_fused_eligible(A, M, o) && !(solved || tired)) {
+  // row-partitioned: the fused kernels cover M = I; everything else runs the primitive path, whose SpMV is
+  // preceded by the general halo exchange and whose dots end in the in-kernel all-reduce
+  if (cg_fused_eligible(A, M, o) && !(dist && !MisI) && !(solved || tired)) {
     ws.mdiag_fused = MisI ? nullptr : M.diag;      // Diagonal M is applied inside K1/K2 (z is not materialised)
     cg_fused_loop<T>(ws, *A.csr, o, gamma, eps_tol, itmax, start_time, solved, tired, zero_curvature, inconsistent,
                      user_exit, overtimed, iter);
@@ -292,7 +299,6 @@ void bicgstab_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c_
   const int n = ws.n;
   const bool history = o.history, ldiv = o.ldiv;
   if (o.verbose > 0) printf("BICGSTAB: system of size %d\n", n);
-  if (ws.dist.world > 1) throw std::runtime_error("row-partitioned solves are implemented for cg! only");
   const bool MisI = M.is_identity(), NisI = N.is_identity();
   allocate_if(!MisI, ws, ws.t);
   allocate_if(!NisI, ws, ws.yz);
@@ -324,7 +330,7 @@ void bicgstab_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c_
   };
   if (rNorm == 0) { finish_early(true, "x is a zero-residual solution"); return; }
   int iter = 0;
-  const int itmax = o.itmax == 0 ? 2 * n : o.itmax;
+  const int itmax = o.itmax == 0 ? 2 * (int)(ws.dist.world > 1 ? ws.dist.nglobal : n) : o.itmax;
   const T eps_tol = tol_of<T>(o.atol) + tol_of<T>(o.rtol) * rNorm;
   if (o.verbose > 0) printf("%5s  %7s  %8s  %8s  %5s\n", "k", "‖rₖ‖", "|αₖ|", "|ωₖ|", "timer");
   if (kdisplay(iter, o.verbose)) printf("%5d  %7.1e  %8.1e  %8.1e  %.2fs\n", iter, (double)rNorm, 1.0, 1.0, now_seconds() - start_time);
@@ -409,7 +415,6 @@ void gmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>
   const int n = ws.n;
   const bool history = o.history, ldiv = o.ldiv, restart = o.restart, reorth = o.reorthogonalization;
   if (o.verbose > 0) printf("GMRES: system of size %d\n", n);
-  if (ws.dist.world > 1) throw std::runtime_error("row-partitioned solves are implemented for cg! only");
   const bool MisI = M.is_identity(), NisI = N.is_identity();
   allocate_if(!MisI, ws, ws.q);
   allocate_if(!NisI, ws, ws.pp);
@@ -448,7 +453,7 @@ void gmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>
   }
   const int mem = (int)c.size();                              // gmres.jl:181
   int npass = 0, iter = 0, inner_iter = 0;
-  const int itmax = o.itmax == 0 ? 2 * n : o.itmax;
+  const int itmax = o.itmax == 0 ? 2 * (int)(ws.dist.world > 1 ? ws.dist.nglobal : n) : o.itmax;
   int inner_itmax = itmax;
   if (o.verbose > 0) printf("%5s  %5s  %7s  %7s  %5s\n", "pass", "k", "‖rₖ‖", "hₖ₊₁.ₖ", "timer");
   if (kdisplay(iter, o.verbose)) printf("%5d  %5d  %7.1e  %7s  %.2fs\n", npass, iter, (double)rNorm, "✗ ✗ ✗ ✗", now_seconds() - start_time);
@@ -591,7 +596,6 @@ void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T
   const int n = ws.n;
   const bool history = o.history, ldiv = o.ldiv, linesearch = o.linesearch;
   if (o.verbose > 0) printf("MINRES: system of size %d\n", n);
-  if (ws.dist.world > 1) throw std::runtime_error("row-partitioned solves are implemented for cg! only");
   if (ws.warm_start && linesearch) throw std::runtime_error("warm_start and linesearch cannot be used together");
   const bool MisI = M.is_identity();
   allocate_if(!MisI, ws, ws.vv);
@@ -647,7 +651,7 @@ void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T
   const int window = (int)err_vec.size();
   std::fill(err_vec.begin(), err_vec.end(), T(0));
   int iter = 0;
-  const int itmax = o.itmax == 0 ? 2 * n : o.itmax;
+  const int itmax = o.itmax == 0 ? 2 * (int)(ws.dist.world > 1 ? ws.dist.nglobal : n) : o.itmax;
   if (o.verbose > 0)
     printf("%5s  %7s  %7s  %7s  %8s  %8s  %7s  %7s  %7s  %7s  %5s\n", "k", "‖r‖", "‖Aᴴr‖", "β", "cos", "sin", "‖A‖", "κ(A)", "test1", "test2", "timer");
   const T eps_tol = atol + tol_of<T>(o.rtol) * beta1;        // minres.jl:269

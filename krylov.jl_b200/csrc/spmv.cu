@@ -169,7 +169,7 @@ template <class T> void csr_plan(Ctx& c, Csr<T>& A) {
 // Row-per-thread LDG kernel: always valid (any row length), used when the
 // staging plan does not fit and as an independent check of the staged kernel.
 template <class T, bool DOT>
-__global__ void __launch_bounds__(kBlock) spmv_rows_kernel(Csr<T> A, const T* __restrict__ x, T* __restrict__ y, T* part,
+__global__ void __launch_bounds__(kBlock) spmv_rows_kernel(Csr<T> A, XGather<T> xg, T* __restrict__ y, T* part,
                                                            unsigned* ticket, T* out) {
   __shared__ T sm[32];
   T dacc = T(0);
@@ -177,9 +177,9 @@ __global__ void __launch_bounds__(kBlock) spmv_rows_kernel(Csr<T> A, const T* __
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < A.n; row += stride) {
     const int kb = A.rowptr[row], ke = A.rowptr[row + 1];
     T acc = T(0);
-    for (int k = kb; k < ke; k++) acc = add_rn(acc, mul_rn(A.val[k], __ldg(&x[A.colind[k]])));
+    for (int k = kb; k < ke; k++) acc = add_rn(acc, mul_rn(A.val[k], xg(A.colind[k])));
     y[row] = acc;
-    if (DOT) dacc += __ldg(&x[row]) * acc;
+    if (DOT) dacc += __ldg(&xg.x[row]) * acc;
   }
   if (DOT) {
     T mine[1] = {block_sum(dacc, sm)}, tot[1];
@@ -188,13 +188,13 @@ __global__ void __launch_bounds__(kBlock) spmv_rows_kernel(Csr<T> A, const T* __
 }
 
 template <class T, bool DOT>
-__global__ void __launch_bounds__(kTileThreads) spmv_tma_kernel(Csr<T> A, const T* __restrict__ x, T* __restrict__ y, T* part,
+__global__ void __launch_bounds__(kTileThreads) spmv_tma_kernel(Csr<T> A, XGather<T> xg, T* __restrict__ y, T* part,
                                                                 unsigned* ticket, T* out) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ T sm[32];
   T dacc = T(0);
   spmv_tiles_run<T>(
-      A, smem, XGather<T>{x}, [&](int row) { return DOT ? __ldg(&x[row]) : T(0); },
+      A, smem, xg, [&](int row) { return DOT ? __ldg(&xg.x[row]) : T(0); },
       [&](int row, T acc, T xr) {
         y[row] = acc;
         if (DOT) dacc += xr * acc;
@@ -221,10 +221,10 @@ static void spmv_launch(Ctx& c, const Csr<T>& A, const T* x, T* y, int slot, int
     KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_tma_kernel<T, DOT>, kTileThreads, A.smem_bytes));
     if (occ < 1) throw std::runtime_error("spmv_tma_kernel does not fit on an SM with the planned shared-memory ring");
     const int grid = std::min(std::min(occ, A.ctas_per_sm) * sm_count(), std::max(1, A.ntiles));
-    spmv_tma_kernel<T, DOT><<<grid, kTileThreads, A.smem_bytes, c.stream>>>(A, x, y, (T*)c.partials, c.tickets + 1, out);
+    spmv_tma_kernel<T, DOT><<<grid, kTileThreads, A.smem_bytes, c.stream>>>(A, xgather_of<T>(c, x), y, (T*)c.partials, c.tickets + 1, out);
   } else {
     const int grid = stream_grid(A.n, 1, 8);
-    spmv_rows_kernel<T, DOT><<<grid, kBlock, 0, c.stream>>>(A, x, y, (T*)c.partials, c.tickets + 1, out);
+    spmv_rows_kernel<T, DOT><<<grid, kBlock, 0, c.stream>>>(A, xgather_of<T>(c, x), y, (T*)c.partials, c.tickets + 1, out);
   }
   KB_CUDA(cudaGetLastError());
   c.launches++;
@@ -234,11 +234,57 @@ template <class T> void k_spmv(Ctx& c, const Csr<T>& A, const T* x, T* y, int va
 template <class T> void k_spmv_dot_dev(Ctx& c, const Csr<T>& A, const T* x, T* y, int slot) { spmv_launch<T, true>(c, A, x, y, slot, 0); }
 
 // ---------------------------------------------------------------------------
+// General x-halo exchange of row-partitioned operators (dist.cuh: DistExchange)
+// ---------------------------------------------------------------------------
+template <class T> struct ExchangeDst { T* p[kMaxRanks]; };
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) halo_exchange_kernel(const T* __restrict__ x, int nsend, const int* __restrict__ row,
+                                                               const int* __restrict__ peer, const int* __restrict__ slot,
+                                                               ExchangeDst<T> dst, unsigned* ticket, DistComm* dc) {
+  __shared__ bool is_last;
+  const int stride = gridDim.x * blockDim.x;
+  bool sent = false;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nsend; e += stride) {
+    dst.p[peer[e]][slot[e]] = x[row[e]];
+    sent = true;
+  }
+  if (sent) __threadfence_system();        // my stores are visible to the peers before the barrier below
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+    if (is_last) *ticket = 0u;
+  }
+  __syncthreads();
+  // the last CTA of this rank enters the cross-GPU barrier: when it returns, every rank has finished pushing
+  if (is_last && threadIdx.x == 0) dist_allreduce_sum(dc, 0.0);
+}
+
+template <class T> void k_halo_exchange(Ctx& c, const T* x) {
+  if (!c.dex) return;
+  DistExchange& d = *c.dex;
+  ExchangeDst<T> dst;
+  const size_t par = (size_t)(d.count & 1);
+  for (int k = 0; k < kMaxRanks; k++)
+    dst.p[k] = d.xhalo_peer[k] ? reinterpret_cast<T*>(d.xhalo_peer[k]) + par * (size_t)d.nhalo_peer[k] : nullptr;
+  const int grid = d.nsend > 0 ? std::min(sm_count(), (d.nsend + kBlock - 1) / kBlock) : 1;
+  halo_exchange_kernel<T><<<grid, kBlock, 0, c.stream>>>(x, d.nsend, d.send_row, d.send_peer, d.send_slot, dst, c.tickets + 6, c.dcomm);
+  KB_CUDA(cudaGetLastError());
+  c.launches++;
+  d.count++;
+}
+
+// ---------------------------------------------------------------------------
 // Operator application (A, M, N as the solvers see them)
 // ---------------------------------------------------------------------------
 template <class T> void op_apply(Ctx& c, const LinOp<T>& op, const T* x, T* y, bool ldiv) {
   switch (op.kind) {
-    case LinOp<T>::CSR: k_spmv<T>(c, *op.csr, x, y, 0); break;
+    case LinOp<T>::CSR:
+      k_halo_exchange<T>(c, x);            // row-partitioned operators only; no-op on a single GPU
+      k_spmv<T>(c, *op.csr, x, y, 0);
+      break;
     case LinOp<T>::DIAG: k_diagmul<T>(c, op.n, y, op.diag, x, ldiv); break;
     case LinOp<T>::DEV_CB:
       c.sync();                       // the callback may use its own stream
@@ -263,6 +309,7 @@ template <class T> void op_apply(Ctx& c, const LinOp<T>& op, const T* x, T* y, b
   template void csr_plan<T>(Ctx&, Csr<T>&);                                                                      \
   template void k_spmv<T>(Ctx&, const Csr<T>&, const T*, T*, int);                                               \
   template void k_spmv_dot_dev<T>(Ctx&, const Csr<T>&, const T*, T*, int);                                       \
+  template void k_halo_exchange<T>(Ctx&, const T*);                                                              \
   template void op_apply<T>(Ctx&, const LinOp<T>&, const T*, T*, bool);
 INST(double)
 INST(float)

@@ -57,12 +57,28 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
-// Plain x gather (y = A x) through the read-only path.
+// x gather (y = A x) through the read-only path.  Row-partitioned operators: column j >= nloc is halo entry
+// j - nloc of the local halo buffer (filled by k_halo_exchange); the source is chosen by a pointer select, not a
+// branch, so the batch of gathers stays a straight line of loads.  Single GPU: nloc = INT_MAX.
 template <class T>
 struct XGather {
   const T* x;
-  __device__ __forceinline__ T operator()(int j) const { return __ldg(&x[j]); }
+  const T* xh_minus_nloc;   // halo buffer base shifted by -nloc (only dereferenced for j >= nloc)
+  int nloc;
+  __device__ __forceinline__ T operator()(int j) const {
+    const T* base = j < nloc ? x : xh_minus_nloc;
+    return __ldg(&base[j]);
+  }
 };
+
+// The gather for vector x under context c (host side).
+template <class T>
+inline XGather<T> xgather_of(const Ctx& c, const T* x) {
+  if (!c.dex) return XGather<T>{x, x, 2147483647};
+  const DistExchange& d = *c.dex;
+  const T* section = reinterpret_cast<const T*>(d.xhalo) + (size_t)((d.count + 1) & 1) * (size_t)d.nhalo;   // parity of the LAST exchange
+  return XGather<T>{x, section - d.nloc, d.nloc};
+}
 
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
   uint64_t pol;

@@ -88,6 +88,7 @@ SIGNATURES = {
     "krylov_b200_dist_handle_bytes": (_I, []),
     "krylov_b200_dist_init": (_I, [_P, _I, _I, _I, _P, _P]),
     "krylov_b200_dist_set_push": (_I, [_P, _I, _P, _P]),
+    "krylov_b200_dist_set_sendlist": (_I, [_P, _I, _P, _P, _P, _P, _LL]),
     "krylov_b200_dist_export": (_I, [_P, _P]),
     "krylov_b200_dist_import": (_I, [_P, _P]),
     "kb200_ctx_create": (_P, [_I]),

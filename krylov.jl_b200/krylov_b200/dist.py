@@ -94,19 +94,36 @@ def push_ranges(maps, rank, max_ranges=4):
     return out
 
 
+def send_list(maps, rank):
+    """General send list of `rank` from every rank's halo map: for each peer q and each halo slot h of q owned by
+    `rank`, one entry (local row = halo_off_q[h], peer = q, slot = h).  Returns three int32 arrays."""
+    rows, peers, slots = [], [], []
+    for q, (hr, ho) in enumerate(maps):
+        if q == rank:
+            continue
+        hr, ho = np.asarray(hr), np.asarray(ho)
+        idx = np.nonzero(hr == rank)[0]
+        rows.append(ho[idx]); peers.append(np.full(len(idx), q)); slots.append(idx)
+    cat = lambda a: np.ascontiguousarray(np.concatenate(a) if a else np.zeros(0), dtype=np.int32)
+    return cat(rows), cat(peers), cat(slots)
+
+
 # --------------------------------------------------------------------------
 # distributed workspace
 # --------------------------------------------------------------------------
-class DistCgWorkspace:
-    """CgWorkspace for one row block.  `csr_local` = (rowptr, colind_local, values) with the
-    [local | halo] column numbering of localize_columns()."""
+class DistWorkspace:
+    """Workspace of any of the four solvers for one row block.  `csr_local` = (rowptr, colind_local, values) with
+    the [local | halo] column numbering of localize_columns().  CG runs its fused two-kernel iteration with the
+    in-kernel halo pull; every other product (all solvers, primitive and fused-phase paths) is preceded by the
+    general halo exchange kernel; every dot product ends in the in-kernel all-reduce."""
 
-    def __init__(self, csr_local, halo_rank, halo_off, rank, world, dtype=np.float64, device="cuda"):
+    def __init__(self, solver, csr_local, halo_rank, halo_off, rank, world, dtype=np.float64, device="cuda",
+                 memory=0, window=0):
         import torch.distributed as dist
-        from . import CgWorkspace
+        from . import krylov_workspace
         self.rank, self.world = rank, world
         nloc = int(csr_local[0].shape[0]) - 1
-        self.ws = CgWorkspace(nloc, nloc, dtype, device=device)
+        self.ws = krylov_workspace(solver, nloc, nloc, dtype, device=device, memory=memory, window=window)
         self.ws.set_operator(csr_local)
         L = _lib.lib()
         hr = np.ascontiguousarray(halo_rank, dtype=np.int32)
@@ -118,13 +135,20 @@ class DistCgWorkspace:
         # entries straight into the peers' halo buffers (no fine-grained P2P loads in the SpMV)
         maps = [None] * world
         dist.all_gather_object(maps, (hr, ho))
-        ranges = push_ranges(maps, rank)
+        nh = np.ascontiguousarray(np.array([len(m[0]) for m in maps], dtype=np.int32))
+        nloc_all = [None] * world
+        dist.all_gather_object(nloc_all, nloc)
+        rows, peers, slots = send_list(maps, rank)
+        if L.krylov_b200_dist_set_sendlist(self.ws._h, len(rows), rows.ctypes.data_as(C.c_void_p),
+                                           peers.ctypes.data_as(C.c_void_p), slots.ctypes.data_as(C.c_void_p),
+                                           nh.ctypes.data_as(C.c_void_p), int(sum(nloc_all))) != 0:
+            raise RuntimeError(_lib.last_error())
+        ranges = push_ranges(maps, rank) if solver == "cg" else None
         # measured at 2 GPUs (profiles/r1_scale_2gpu_push_vs_pull.txt): pull 4833 / 567.5 it/s vs push 4685 / 563.1
         # (n = 1e7 / 1e8) -- pull stays the default, push is opt-in
         self.push_mode = ranges is not None and os.environ.get("KB200_DIST_PUSH", "0") == "1"
         if self.push_mode:
             flat = np.ascontiguousarray(np.array(ranges, dtype=np.int32).reshape(-1))
-            nh = np.ascontiguousarray(np.array([len(m[0]) for m in maps], dtype=np.int32))
             if L.krylov_b200_dist_set_push(self.ws._h, len(ranges), flat.ctypes.data_as(C.c_void_p),
                                            nh.ctypes.data_as(C.c_void_p)) != 0:
                 raise RuntimeError(_lib.last_error())
@@ -143,6 +167,9 @@ class DistCgWorkspace:
     def solve(self, b_local, **kw):
         return self.ws.solve(None, b_local, **kw)
 
+    def warm_start(self, x0_local):
+        return self.ws.warm_start(x0_local)
+
     @property
     def x(self):
         return self.ws.x
@@ -153,6 +180,21 @@ class DistCgWorkspace:
 
     def free(self):
         self.ws.free()
+
+
+class DistCgWorkspace(DistWorkspace):
+    def __init__(self, csr_local, halo_rank, halo_off, rank, world, dtype=np.float64, device="cuda"):
+        super().__init__("cg", csr_local, halo_rank, halo_off, rank, world, dtype=dtype, device=device)
+
+
+def make_stencil_rank(gen, N, rank, world, torch, device, dtype=np.float64):
+    """This rank's z-slab of a 7-point stencil matrix `gen` (problems.div_grad_csr / kron_unsymmetric_csr)."""
+    bounds = slab_bounds(N, world)
+    k_lo, k_hi = bounds[rank]
+    rp, ci, va = gen(N, dtype=dtype, k_lo=k_lo, k_hi=k_hi, xp=torch, device=device)
+    row_starts = np.array([b[0] * N * N for b in bounds] + [N ** 3], dtype=np.int64)
+    ci_loc, hr, ho = localize_columns(ci, row_starts, rank)
+    return (rp, ci_loc, va), hr, ho, (k_hi - k_lo) * N * N
 
 
 def make_poisson_rank(N, rank, world, torch, device, dtype=np.float64):

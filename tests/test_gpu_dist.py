@@ -55,3 +55,69 @@ def test_distributed_cg_matches_single_gpu_and_oracle(tmp_path, O, world):
     assert res["niter"] == so["niter"] and res["status"] == so["status"]
     assert np.allclose(res["residuals"], so["residuals"], rtol=1e-6)
     assert np.linalg.norm(np.array(res["x"]) - xo) <= 1e-6 * np.linalg.norm(xo)
+
+
+def test_distributed_other_solvers_match_oracle(tmp_path, O):
+    """gmres! / bicgstab! / minres! (fused phases and primitive path) and the primitive-path cg! (Jacobi M, warm
+    start) on 2 GPUs: general halo exchange before every product + in-kernel all-reduce of every dot."""
+    world = 2
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    N = 14
+    script = tmp_path / "w2.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys, json
+        sys.path[:0] = [{ROOT!r}, {os.path.join(ROOT, 'krylov.jl_b200')!r}]
+        import numpy as np, torch, torch.distributed as dist
+        from krylov_b200 import dist as D, _lib, problems as P
+        rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(local); dev = torch.device("cuda", local)
+        _lib.lib().krylov_b200_set_device(local)
+        dist.init_process_group("nccl", device_id=dev)
+        N = {N}
+        out = {{}}
+        def gather(x):
+            xs = [None] * world
+            dist.all_gather_object(xs, x.cpu().numpy())
+            return np.concatenate(xs).tolist()
+        def bvec(csr, nloc, kind):
+            if kind == "ones":
+                return torch.ones(nloc, dtype=torch.float64, device=dev)
+            # b = A * ones computed from the local rows (halo columns included)
+            rp, ci, va = csr
+            rows = torch.repeat_interleave(torch.arange(nloc, device=dev), (rp[1:] - rp[:-1]).long())
+            b = torch.zeros(nloc, dtype=torch.float64, device=dev); b.index_add_(0, rows, va); return b
+        cases = [("gmres_kron", "gmres", P.kron_unsymmetric_csr, "Aones", dict(memory=30), dict(restart=True), True),
+                 ("gmres_kron_prim", "gmres", P.kron_unsymmetric_csr, "Aones", dict(memory=30), dict(restart=True), False),
+                 ("bicgstab_kron", "bicgstab", P.kron_unsymmetric_csr, "Aones", dict(), dict(), True),
+                 ("bicgstab_kron_prim", "bicgstab", P.kron_unsymmetric_csr, "Aones", dict(), dict(), False),
+                 ("minres_lap", "minres", P.div_grad_csr, "ones", dict(), dict(), True),
+                 ("minres_lap_prim", "minres", P.div_grad_csr, "ones", dict(), dict(), False),
+                 ("cg_prim", "cg", P.div_grad_csr, "ones", dict(), dict(), False)]
+        for name, solver, gen, bk, wkw, skw, fused in cases:
+            csr, hr, ho, nloc = D.make_stencil_rank(gen, N, rank, world, torch, dev)
+            ws = D.DistWorkspace(solver, csr, hr, ho, rank, world, **wkw)
+            b = bvec(csr, nloc, bk)
+            ws.solve(b, history=True, fused=fused, **skw)
+            st = ws.stats
+            out[name] = dict(niter=st.niter, residuals=st.residuals, status=st.status, x=gather(ws.x))
+            ws.free()
+        if rank == 0:
+            json.dump(out, open({str(tmp_path / 'out2.json')!r}, "w"))
+        dist.destroy_process_group()
+    """))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29543", str(script)],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    out = json.load(open(tmp_path / "out2.json"))
+    Ak, bk = O.kron_unsymmetric(N)
+    Al, bl = O.sparse_laplacian(N)
+    ref = {"gmres_kron": O.gmres(Ak, bk, memory=30, restart=True), "bicgstab_kron": O.bicgstab(Ak, bk),
+           "minres_lap": O.minres(Al, bl), "cg_prim": O.cg(Al, bl)}
+    for name, r in out.items():
+        xo, so = ref[name.replace("_prim", "")]
+        assert r["niter"] == so["niter"] and r["status"] == so["status"], (name, r["niter"], so["niter"])
+        tol = 1e-5 if name.startswith("bicgstab") else 1e-6
+        assert np.allclose(r["residuals"], so["residuals"], rtol=tol, atol=1e-9 * so["residuals"][0]), name
+        assert np.linalg.norm(np.array(r["x"]) - xo) <= 1e-6 * np.linalg.norm(xo), name
