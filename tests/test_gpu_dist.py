@@ -114,7 +114,7 @@ def test_distributed_other_solvers_match_oracle(tmp_path, O):
     Ak, bk = O.kron_unsymmetric(N)
     Al, bl = O.sparse_laplacian(N)
     ref = {"gmres_kron": O.gmres(Ak, bk, memory=30, restart=True), "bicgstab_kron": O.bicgstab(Ak, bk),
-           "minres_lap": O.minres(Al, bl), "cg_prim": O.cg(Al, bl)}
+           "minres_lap": O.minres(Al, bl), "cg": O.cg(Al, bl)}
     for name, r in out.items():
         xo, so = ref[name.replace("_prim", "")]
         assert r["niter"] == so["niter"] and r["status"] == so["status"], (name, r["niter"], so["niter"])
