@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -117,7 +117,7 @@ def cpu_leg(N, iters, threads, budget_s=20.0):
     per_it = max(t / 2, 1e-6)
     k = int(max(3, min(iters, budget_s / per_it)))
     t, _, rn = O.cg_timed(rp, ci, va, b, k, threads)
-    return dict(value=k / t, unit="CG iterations/s", cores=threads, kind="port",
+    return dict(value=k / t, unit="it/s", cores=threads, kind="port",
                 sample=f"{k} iterations of cg.jl:195-268 on get_div_grad({N},{N},{N}), b=ones, {threads} thread(s), "
                        f"{t:.2f} s wall"), k, t
 

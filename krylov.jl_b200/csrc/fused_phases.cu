@@ -19,8 +19,8 @@ namespace kb {
 // ---------------------------------------------------------------------------
 // generic launchers
 // ---------------------------------------------------------------------------
-template <class T, int K, class Epi, class Fin>
-__global__ void __launch_bounds__(kTileThreads) spmv_epi_tma(Csr<T> A, XGather<T> xg, Epi epi, Fin fin, T* part,
+template <class T, int K, class Epi, class Fin, class G>
+__global__ void __launch_bounds__(kTileThreads) spmv_epi_tma(Csr<T> A, G xg, Epi epi, Fin fin, T* part,
                                                              unsigned* ticket, DistComm* dc) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ T sm[32];
@@ -39,8 +39,8 @@ __global__ void __launch_bounds__(kTileThreads) spmv_epi_tma(Csr<T> A, XGather<T
   }
 }
 
-template <class T, int K, class Epi, class Fin>
-__global__ void __launch_bounds__(kBlock) spmv_epi_rows(Csr<T> A, XGather<T> xg, Epi epi, Fin fin, T* part,
+template <class T, int K, class Epi, class Fin, class G>
+__global__ void __launch_bounds__(kBlock) spmv_epi_rows(Csr<T> A, G xg, Epi epi, Fin fin, T* part,
                                                         unsigned* ticket, DistComm* dc) {
   __shared__ T sm[32];
   T d[K];
@@ -92,24 +92,32 @@ struct NoFin {
   template <class T> __device__ void operator()(const T*) const {}
 };
 
-template <class T, int K, class Epi, class Fin>
-static void launch_spmv_epi(Ctx& c, const Csr<T>& A, const T* x, Epi epi, Fin fin, int ticket) {
-  if (A.n <= 0) return;
-  k_halo_exchange<T>(c, x);                // row-partitioned operators only
-  const XGather<T> xg = xgather_of<T>(c, x);
+template <class T, int K, class Epi, class Fin, class G>
+static void launch_spmv_epi_g(Ctx& c, const Csr<T>& A, G xg, Epi epi, Fin fin, int ticket) {
   if (A.tma_ok) {
     static bool attr = false;
-    if (!attr) { KB_CUDA(cudaFuncSetAttribute(spmv_epi_tma<T, K, Epi, Fin>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+    if (!attr) { KB_CUDA(cudaFuncSetAttribute(spmv_epi_tma<T, K, Epi, Fin, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
     int occ = 0;          // persistent grid = what is really co-resident (never more than one wave)
-    KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_epi_tma<T, K, Epi, Fin>, kTileThreads, A.smem_bytes));
+    KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_epi_tma<T, K, Epi, Fin, G>, kTileThreads, A.smem_bytes));
     if (occ < 1) throw std::runtime_error("spmv_epi_tma does not fit on an SM with the planned shared-memory ring");
     const int grid = std::min(std::min(occ, A.ctas_per_sm) * sm_count(), std::max(1, A.ntiles));
-    spmv_epi_tma<T, K, Epi, Fin><<<grid, kTileThreads, A.smem_bytes, c.stream>>>(A, xg, epi, fin, (T*)c.partials, c.tickets + ticket, c.dcomm);
+    spmv_epi_tma<T, K, Epi, Fin, G><<<grid, kTileThreads, A.smem_bytes, c.stream>>>(A, xg, epi, fin, (T*)c.partials, c.tickets + ticket, c.dcomm);
   } else {
-    spmv_epi_rows<T, K, Epi, Fin><<<stream_grid(A.n, 1, 8), kBlock, 0, c.stream>>>(A, xg, epi, fin, (T*)c.partials, c.tickets + ticket, c.dcomm);
+    spmv_epi_rows<T, K, Epi, Fin, G><<<stream_grid(A.n, 1, 8), kBlock, 0, c.stream>>>(A, xg, epi, fin, (T*)c.partials, c.tickets + ticket, c.dcomm);
   }
   KB_CUDA(cudaGetLastError());
   c.launches++;
+}
+
+template <class T, int K, class Epi, class Fin>
+static void launch_spmv_epi(Ctx& c, const Csr<T>& A, const T* x, Epi epi, Fin fin, int ticket) {
+  if (A.n <= 0) return;
+  if (c.dex) {                               // row-partitioned operator: exchange the halo of x, gather [local | halo]
+    k_halo_exchange<T>(c, x);
+    launch_spmv_epi_g<T, K, Epi, Fin, XGather<T>>(c, A, xgather_of<T>(c, x), epi, fin, ticket);
+  } else {
+    launch_spmv_epi_g<T, K, Epi, Fin, XPlain<T>>(c, A, XPlain<T>{x}, epi, fin, ticket);
+  }
 }
 
 template <class T, int K, class Body, class Fin>
@@ -131,13 +139,16 @@ template <class S> static S* state_buf(void*& dev, void*& host) {
 }
 
 // ===========================================================================
-// BiCGSTAB  (src/bicgstab.jl:215-256, M = N = I)
+// BiCGSTAB  (src/bicgstab.jl:215-256, N = I, M = I or a diagonal applied by multiplication)
 // ===========================================================================
 template <class T> struct BicgState { T rho, alpha, omega, beta, next_rho, rNorm, cv, ts, tt, cr, rr; };
 
-template <class T> struct BicgK1Epi {   // v = A p ; <c, v>
-  T* v; const T* c;
-  __device__ __forceinline__ void operator()(int row, T acc, T* d) const { v[row] = acc; d[0] += __ldg(&c[row]) * acc; }
+template <class T> struct BicgK1Epi {   // v = M (A p) ; <c, v>          (bicgstab.jl:221-223; m: diagonal of M or null)
+  T* v; const T* c; const T* m;
+  __device__ __forceinline__ void operator()(int row, T acc, T* d) const {
+    if (m) acc = mul_rn(__ldg(&m[row]), acc);
+    v[row] = acc; d[0] += __ldg(&c[row]) * acc;
+  }
 };
 template <class T> struct BicgK1Fin {   // alpha = rho / <c, v>          (bicgstab.jl:223)
   BicgState<T>* s;
@@ -147,9 +158,10 @@ template <class T> struct BicgK2Body {  // s = r - alpha v               (bicgst
   const T* r; const T* v; T* sv; const BicgState<T>* s;
   __device__ __forceinline__ void operator()(int i, T*) const { sv[i] = add_rn(r[i], mul_rn(-s->alpha, v[i])); }
 };
-template <class T> struct BicgK3Epi {   // t = A s ; <t,s>, <t,t>
-  T* t; const T* sv;
+template <class T> struct BicgK3Epi {   // t = M (A s) ; <t,s>, <t,t>     (bicgstab.jl:228-230)
+  T* t; const T* sv; const T* m;
   __device__ __forceinline__ void operator()(int row, T acc, T* d) const {
+    if (m) acc = mul_rn(__ldg(&m[row]), acc);
     t[row] = acc; d[0] += acc * __ldg(&sv[row]); d[1] += acc * acc;
   }
 };
@@ -200,10 +212,11 @@ void bicgstab_fused_iteration(Workspace<T>& ws, const Csr<T>& A, const T* cvec, 
     H->rho = rho_in;
     KB_CUDA(cudaMemcpyAsync(S, H, sizeof(St), cudaMemcpyHostToDevice, c.stream));
   }
-  T* t = ws.qd;    // t == d == qd when M = I  (bicgstab.jl:153-154)
-  launch_spmv_epi<T, 1>(c, A, ws.p, BicgK1Epi<T>{ws.v, cvec}, BicgK1Fin<T>{S}, 4);
+  const T* m = ws.mdiag_fused;          // left diagonal preconditioner fused into the two SpMV epilogues
+  T* t = m ? ws.t : ws.qd;              // t == d == qd when M = I  (bicgstab.jl:153-154)
+  launch_spmv_epi<T, 1>(c, A, ws.p, BicgK1Epi<T>{ws.v, cvec, m}, BicgK1Fin<T>{S}, 4);
   launch_stream<T, 0>(c, n, BicgK2Body<T>{ws.r, ws.v, ws.s, S}, NoFin(), 5);
-  launch_spmv_epi<T, 2>(c, A, ws.s, BicgK3Epi<T>{t, ws.s}, BicgK3Fin<T>{S}, 4);
+  launch_spmv_epi<T, 2>(c, A, ws.s, BicgK3Epi<T>{t, ws.s, m}, BicgK3Fin<T>{S}, 4);
   launch_stream<T, 2>(c, n, BicgK4Body<T>{ws.x, ws.p, ws.s, t, cvec, ws.r, S}, BicgK4Fin<T>{S}, 5);
   KB_CUDA(cudaMemcpyAsync(H + 1, S, sizeof(St), cudaMemcpyDeviceToHost, c.stream));   // scalars of this iteration
   launch_stream<T, 0>(c, n, BicgK5Body<T>{ws.p, ws.r, ws.v, S}, NoFin(), 5);
@@ -212,12 +225,12 @@ void bicgstab_fused_iteration(Workspace<T>& ws, const Csr<T>& A, const T* cvec, 
 }
 
 // ===========================================================================
-// MINRES  (src/minres.jl:285-333,389-409, M = I)
+// MINRES  (src/minres.jl:285-333,389-409, M = I or a diagonal applied by multiplication)
 // ===========================================================================
 template <class T> struct MinresState { T vy, alpha, beta2, xx; };
 
 template <class T> struct MinresK1Epi {  // y = (A v [+ lambda v]) / beta [- (beta/oldbeta) r1] ; <v, y>   (:289-294)
-  T* y; const T* v; const T* r1; T lambda, inv_beta, c1; int iter;
+  T* y; const T* v; const T* r1; T lambda, inv_beta, c1; int iter;     // v == r2 when M = I, else v = M r2
   __device__ __forceinline__ void operator()(int row, T acc, T* d) const {
     const T vr = __ldg(&v[row]);
     T t = acc;
@@ -232,15 +245,23 @@ template <class T> struct MinresK1Fin {  // alpha = <v,y> / beta
   MinresState<T>* s; T beta;
   __device__ void operator()(const T* tot) const { s->vy = tot[0]; s->alpha = div_rn(tot[0], beta); }
 };
-template <class T> struct MinresK2Body { // y -= (alpha/beta) r2 ; w update (:295-307) ; <y,y> (:313, v == r2 <- y)
+template <class T> struct MinresK2Body { // y -= (alpha/beta) r2 ; w update (:295-307) ; v = M y ; <y,v> (:311-313, r2 <- y)
   T* y; const T* r2; T* w; const T* w2; const MinresState<T>* s;
   T beta, inv_beta, cs, sn, deltabar, eps; int iter;
+  T* v; const T* m;                                         // M = I: v == nullptr (v aliases r2)
   __device__ __forceinline__ void operator()(int i, T* d) const {
     const T alpha = s->alpha;
-    const T vi = r2[i];                                     // v == r2 (M = I), value BEFORE r2 <- y
-    const T yn = add_rn(y[i], mul_rn(div_rn(-alpha, beta), vi));
+    const T r2i = r2[i];
+    const T vi = m ? v[i] : r2i;                            // v_k, value BEFORE v <- M y
+    const T yn = add_rn(y[i], mul_rn(div_rn(-alpha, beta), r2i));
     y[i] = yn;
-    d[0] += yn * yn;
+    if (m) {
+      const T vn = mul_rn(m[i], yn);                        // v_{k+1} = M r2_{k+1}
+      v[i] = vn;
+      d[0] += yn * vn;
+    } else {
+      d[0] += yn * yn;
+    }
     if (iter == 1) {
       w[i] = div_rn(vi, beta);                              // kdivcopy!(n, w, v, beta), w == w2
     } else {
@@ -284,8 +305,11 @@ void minres_fused_lanczos(Workspace<T>& ws, const Csr<T>& A, int iter, T lambda,
   St* H = (St*)ws.fused_host;
   const T inv_beta = T(1) / beta;
   const T c1 = iter >= 2 ? -beta / oldbeta : T(0);
-  launch_spmv_epi<T, 1>(c, A, ws.r2, MinresK1Epi<T>{ws.y, ws.r2, ws.r1, lambda, inv_beta, c1, iter}, MinresK1Fin<T>{S, beta}, 4);
-  launch_stream<T, 1>(c, n, MinresK2Body<T>{ws.y, ws.r2, w, ws.w2, S, beta, inv_beta, cs, sn, deltabar, eps_rot, iter},
+  const T* m = ws.mdiag_fused;
+  T* v = m ? ws.vv : ws.r2;                                 // minres.jl:193
+  launch_spmv_epi<T, 1>(c, A, v, MinresK1Epi<T>{ws.y, v, ws.r1, lambda, inv_beta, c1, iter}, MinresK1Fin<T>{S, beta}, 4);
+  launch_stream<T, 1>(c, n, MinresK2Body<T>{ws.y, ws.r2, w, ws.w2, S, beta, inv_beta, cs, sn, deltabar, eps_rot, iter,
+                                            m ? ws.vv : nullptr, m},
                       MinresK2Fin<T>{S}, 5);
   KB_CUDA(cudaMemcpyAsync(H, S, sizeof(St), cudaMemcpyDeviceToHost, c.stream));
   c.sync();
@@ -308,14 +332,17 @@ T minres_fused_update(Workspace<T>& ws, T* w, T gamma, T phi) {
 }
 
 // ===========================================================================
-// GMRES  (src/gmres.jl:255-262,274, M = N = I, no reorthogonalization)
+// GMRES  (src/gmres.jl:255-262,274, N = I, M = I or a diagonal applied by multiplication, no reorthogonalization)
 // ===========================================================================
 constexpr int kGmresMaxFused = 120;    // h[] slots in the state block
 template <class T> struct GmresState { T hbis2; T h[kGmresMaxFused]; };
 
-template <class T> struct GmresSpmvEpi {  // w = A v_k ; h_1 = <v_1, w>
-  T* w; const T* v1;
-  __device__ __forceinline__ void operator()(int row, T acc, T* d) const { w[row] = acc; d[0] += __ldg(&v1[row]) * acc; }
+template <class T> struct GmresSpmvEpi {  // q = M (A v_k) ; h_1 = <v_1, q>   (gmres.jl:256-260; m: diagonal of M or null)
+  T* w; const T* v1; const T* m;
+  __device__ __forceinline__ void operator()(int row, T acc, T* d) const {
+    if (m) acc = mul_rn(__ldg(&m[row]), acc);
+    w[row] = acc; d[0] += __ldg(&v1[row]) * acc;
+  }
 };
 template <class T> struct GmresHFin {
   GmresState<T>* s; int slot;            // slot < 0: ||q||^2
@@ -338,8 +365,9 @@ void gmres_fused_arnoldi(Workspace<T>& ws, const Csr<T>& A, int k, T* h_out, T* 
   typedef GmresState<T> St;
   St* S = state_buf<St>(ws.fused_state, ws.fused_host);
   St* H = (St*)ws.fused_host;
-  T* q = ws.w;                                              // q == w when M = I (gmres.jl:150)
-  launch_spmv_epi<T, 1>(c, A, ws.V[k - 1], GmresSpmvEpi<T>{q, ws.V[0]}, GmresHFin<T>{S, 0}, 4);
+  const T* m = ws.mdiag_fused;
+  T* q = m ? ws.q : ws.w;                                   // q == w when M = I (gmres.jl:150)
+  launch_spmv_epi<T, 1>(c, A, ws.V[k - 1], GmresSpmvEpi<T>{q, ws.V[0], m}, GmresHFin<T>{S, 0}, 4);
   for (int i = 0; i < k; i++) {
     const T* vnext = (i + 1 < k) ? ws.V[i + 1] : nullptr;
     launch_stream<T, 1>(c, n, GmresMgsBody<T>{q, ws.V[i], vnext, S, i}, GmresHFin<T>{S, (i + 1 < k) ? i + 1 : -1}, 5);

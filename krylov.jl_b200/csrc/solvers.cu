@@ -338,7 +338,8 @@ void bicgstab_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c_
   if (next_rho == 0) { finish_early(false, "Breakdown bᴴc = 0"); return; }
   bool solved = rNorm <= eps_tol, tired = iter >= itmax, breakdown = false, user_exit = false, overtimed = false;
   std::string status = "unknown";
-  const bool fusedB = o.fused && A.kind == LinOp<T>::CSR && MisI && NisI;
+  const bool fusedB = o.fused && A.kind == LinOp<T>::CSR && NisI && (MisI || (M.kind == LinOp<T>::DIAG && !ldiv));
+  ws.mdiag_fused = (fusedB && !MisI) ? M.diag : nullptr;     // Jacobi M rides in the SpMV epilogues
 
   while (!(solved || tired || breakdown || user_exit || overtimed)) {
     iter = iter + 1;
@@ -458,7 +459,8 @@ void gmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>
   if (o.verbose > 0) printf("%5s  %5s  %7s  %7s  %5s\n", "pass", "k", "‖rₖ‖", "hₖ₊₁.ₖ", "timer");
   if (kdisplay(iter, o.verbose)) printf("%5d  %5d  %7.1e  %7s  %.2fs\n", npass, iter, (double)rNorm, "✗ ✗ ✗ ✗", now_seconds() - start_time);
   const T btol = std::pow(eps_of<T>(), T(0.75));              // gmres.jl:195
-  const bool fusedG = o.fused && A.kind == LinOp<T>::CSR && MisI && NisI && !reorth;
+  const bool fusedG = o.fused && A.kind == LinOp<T>::CSR && NisI && !reorth && (MisI || (M.kind == LinOp<T>::DIAG && !ldiv));
+  ws.mdiag_fused = (fusedG && !MisI) ? M.diag : nullptr;
   bool breakdown = false, inconsistent = false, solved = rNorm <= eps_tol, tired = iter >= itmax;
   bool inner_tired = inner_iter >= inner_itmax, user_exit = false, overtimed = false;
   std::string status = "unknown";
@@ -662,7 +664,8 @@ void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T
   stats.indefinite = false;
   T delta_w = 0, beta_w = 0, zeta_k = 0, zeta_km1 = 0;
   std::string status = "unknown";
-  const bool fusedM = o.fused && A.kind == LinOp<T>::CSR && MisI && !linesearch;
+  const bool fusedM = o.fused && A.kind == LinOp<T>::CSR && !linesearch && (MisI || (M.kind == LinOp<T>::DIAG && !ldiv));
+  ws.mdiag_fused = (fusedM && !MisI) ? M.diag : nullptr;
 
   while (!(solved || tired || ill_cond || user_exit || overtimed)) {
     iter = iter + 1;
@@ -674,7 +677,7 @@ void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T
       w = (iter == 1) ? ws.w2 : ws.w1;
       T beta2;
       minres_fused_lanczos<T>(ws, *A.csr, iter, lambda, beta, oldbeta, cs, sn, deltabar, eps_rot, w, &alpha, &beta2);
-      r1 = ws.r1; r2 = ws.r2; y = ws.y; v = r2;
+      r1 = ws.r1; r2 = ws.r2; y = ws.y; v = MisI ? r2 : ws.vv;
       delta = cs * deltabar + sn * alpha;
       oldbeta = beta;
       beta = beta2;

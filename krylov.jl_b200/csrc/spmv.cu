@@ -168,8 +168,8 @@ template <class T> void csr_plan(Ctx& c, Csr<T>& A) {
 // ---------------------------------------------------------------------------
 // Row-per-thread LDG kernel: always valid (any row length), used when the
 // staging plan does not fit and as an independent check of the staged kernel.
-template <class T, bool DOT>
-__global__ void __launch_bounds__(kBlock) spmv_rows_kernel(Csr<T> A, XGather<T> xg, T* __restrict__ y, T* part,
+template <class T, bool DOT, class G>
+__global__ void __launch_bounds__(kBlock) spmv_rows_kernel(Csr<T> A, G xg, T* __restrict__ y, T* part,
                                                            unsigned* ticket, T* out) {
   __shared__ T sm[32];
   T dacc = T(0);
@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(kBlock) spmv_rows_kernel(Csr<T> A, XGather<T> 
   }
 }
 
-template <class T, bool DOT>
-__global__ void __launch_bounds__(kTileThreads) spmv_tma_kernel(Csr<T> A, XGather<T> xg, T* __restrict__ y, T* part,
+template <class T, bool DOT, class G>
+__global__ void __launch_bounds__(kTileThreads) spmv_tma_kernel(Csr<T> A, G xg, T* __restrict__ y, T* part,
                                                                 unsigned* ticket, T* out) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ T sm[32];
@@ -205,29 +205,35 @@ __global__ void __launch_bounds__(kTileThreads) spmv_tma_kernel(Csr<T> A, XGathe
   }
 }
 
-template <class T, bool DOT>
-static void spmv_launch(Ctx& c, const Csr<T>& A, const T* x, T* y, int slot, int variant) {
-  if (A.n <= 0) return;
+template <class T, bool DOT, class G>
+static void spmv_launch_g(Ctx& c, const Csr<T>& A, G xg, T* y, int slot, int variant) {
   T* out = reinterpret_cast<T*>(reinterpret_cast<double*>(c.dscal) + slot);
   const bool staged = variant == 2 || (variant == 0 && A.tma_ok);
   if (staged) {
     if (!A.tma_ok) throw std::runtime_error("TMA-staged SpMV requested but the tile plan does not fit shared memory");
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[DOT]) {
-      KB_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<T, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr_set[DOT] = true;
+    static bool attr_set = false;                // one flag per <T, DOT, G> instantiation
+    if (!attr_set) {
+      KB_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<T, DOT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr_set = true;
     }
     int occ = 0;   // persistent grid = what is really co-resident (never more than one wave)
-    KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_tma_kernel<T, DOT>, kTileThreads, A.smem_bytes));
+    KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_tma_kernel<T, DOT, G>, kTileThreads, A.smem_bytes));
     if (occ < 1) throw std::runtime_error("spmv_tma_kernel does not fit on an SM with the planned shared-memory ring");
     const int grid = std::min(std::min(occ, A.ctas_per_sm) * sm_count(), std::max(1, A.ntiles));
-    spmv_tma_kernel<T, DOT><<<grid, kTileThreads, A.smem_bytes, c.stream>>>(A, xgather_of<T>(c, x), y, (T*)c.partials, c.tickets + 1, out);
+    spmv_tma_kernel<T, DOT, G><<<grid, kTileThreads, A.smem_bytes, c.stream>>>(A, xg, y, (T*)c.partials, c.tickets + 1, out);
   } else {
     const int grid = stream_grid(A.n, 1, 8);
-    spmv_rows_kernel<T, DOT><<<grid, kBlock, 0, c.stream>>>(A, xgather_of<T>(c, x), y, (T*)c.partials, c.tickets + 1, out);
+    spmv_rows_kernel<T, DOT, G><<<grid, kBlock, 0, c.stream>>>(A, xg, y, (T*)c.partials, c.tickets + 1, out);
   }
   KB_CUDA(cudaGetLastError());
   c.launches++;
+}
+
+template <class T, bool DOT>
+static void spmv_launch(Ctx& c, const Csr<T>& A, const T* x, T* y, int slot, int variant) {
+  if (A.n <= 0) return;
+  if (c.dex) spmv_launch_g<T, DOT, XGather<T>>(c, A, xgather_of<T>(c, x), y, slot, variant);   // row-partitioned: [local | halo]
+  else spmv_launch_g<T, DOT, XPlain<T>>(c, A, XPlain<T>{x}, y, slot, variant);
 }
 
 template <class T> void k_spmv(Ctx& c, const Csr<T>& A, const T* x, T* y, int variant) { spmv_launch<T, false>(c, A, x, y, 1, variant); }

@@ -57,9 +57,18 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
-// x gather (y = A x) through the read-only path.  Row-partitioned operators: column j >= nloc is halo entry
-// j - nloc of the local halo buffer (filled by k_halo_exchange); the source is chosen by a pointer select, not a
-// branch, so the batch of gathers stays a straight line of loads.  Single GPU: nloc = INT_MAX.
+// x gather (y = A x) through the read-only path, single GPU.  The kernels are compiled once per gather type:
+// the pointer select of the row-partitioned variant below costs the single-GPU fused phases 6-17 % when it is
+// only disabled at run time (profiles/README.md), so it is a compile-time choice like the CG kernels' MODE.
+template <class T>
+struct XPlain {
+  const T* __restrict__ x;
+  __device__ __forceinline__ T operator()(int j) const { return __ldg(&x[j]); }
+};
+
+// Row-partitioned operators: column j >= nloc is halo entry j - nloc of the local halo buffer (filled by
+// k_halo_exchange); the source is chosen by a pointer select, not a branch, so the batch of gathers stays a
+// straight line of loads.
 template <class T>
 struct XGather {
   const T* x;

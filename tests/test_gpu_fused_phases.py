@@ -98,3 +98,47 @@ def test_cg_x_update_in_k1_is_bit_identical(kb):
         (x1, r1, s1), (x0, r0, s0) = outs
         assert s1.niter == s0.niter and s1.residuals == s0.residuals and s1.status == s0.status
         assert np.array_equal(x1, x0) and np.array_equal(r1, r0)
+
+
+def _jacobi_problem(O, kind):
+    import scipy.sparse as sp
+    if kind == "sym":
+        A, b = O.sparse_laplacian(12)
+        A = sp.csr_matrix(A + sp.diags(np.linspace(0.0, 5.0, A.shape[0])))
+    else:
+        A, b = O.kron_unsymmetric(9)
+        A = sp.csr_matrix(A + sp.diags(np.linspace(0.0, 3.0, A.shape[0])))
+    return A, b, 1.0 / A.diagonal()
+
+
+@pytest.mark.parametrize("solver", ["bicgstab", "gmres", "gmres_restart", "minres"])
+def test_fused_phases_with_jacobi_preconditioner(kb, O, solver):
+    """Left diagonal M folded into the SpMV epilogues / the Lanczos stream pass: the fused phases,
+    the primitive path (M as its own kernel) and the oracle agree; the fused path launches fewer kernels."""
+    name = solver.split("_")[0]
+    A, b, d = _jacobi_problem(O, "sym" if name == "minres" else "unsym")
+    kw = dict(M=d)
+    okw = dict(M=d)
+    mem = 0
+    if name == "gmres":
+        mem = 20
+        kw["restart"] = okw["restart"] = solver.endswith("restart")
+        okw["memory"] = mem
+    out = {}
+    for fused in (True, False):
+        ws = kb.krylov_workspace(name, A.shape[0], A.shape[1], np.float64, memory=mem)
+        ws.solve(A, b, history=True, fused=fused, **kw)
+        out[fused] = (ws.x, ws.stats, ws.launches)
+        ws.free()
+    xo, so = getattr(O, name)(A, b, **okw)
+    tol = 1e-5 if name == "bicgstab" else 1e-6
+    for fused in (True, False):
+        x, st, _ = out[fused]
+        assert st.status == so["status"], (fused, st.status, so["status"])
+        assert st.niter == so["niter"], (fused, st.niter, so["niter"])
+        assert np.allclose(st.residuals, so["residuals"], rtol=tol, atol=1e-9 * so["residuals"][0]), fused
+        assert np.linalg.norm(x - xo) <= 1e-6 * np.linalg.norm(xo), fused
+    assert out[True][2] < out[False][2], (out[True][2], out[False][2])
+    if name == "minres":
+        assert np.allclose(out[True][1].Aresiduals, so["Aresiduals"], rtol=1e-5, atol=1e-12)
+        assert np.allclose(out[True][1].Acond, so["Acond"], rtol=1e-6)
