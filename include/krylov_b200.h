@@ -42,7 +42,8 @@ typedef enum { KRYLOV_FLOAT32 = 0, KRYLOV_FLOAT64 = 1, KRYLOV_COMPLEX32 = 2, KRY
 /* krylov.h:44-46 has KRYLOV_CPU only; KRYLOV_CUDA is this library's addition */
 typedef enum { KRYLOV_CPU = 0, KRYLOV_CUDA = 1 } KrylovDeviceType;
 
-/* positional, frozen (krylov.h:48-83).  Implemented here: CG, MINRES, GMRES, BICGSTAB. */
+/* positional, frozen (krylov.h:48-83).  Implemented here: CG, MINRES, GMRES, BICGSTAB (the hot path) and the
+ * siblings FOM, FGMRES, CGS that run on the same kernels; every other value returns -2. */
 typedef enum {
   KRYLOV_CG = 0, KRYLOV_CR = 1, KRYLOV_SYMMLQ = 2, KRYLOV_MINRES = 3, KRYLOV_MINRES_QLP = 4, KRYLOV_DIOM = 5,
   KRYLOV_DQGMRES = 6, KRYLOV_FOM = 7, KRYLOV_GMRES = 8, KRYLOV_FGMRES = 9, KRYLOV_BICGSTAB = 10, KRYLOV_CGS = 11,
@@ -139,6 +140,10 @@ int krylov_b200_attach_csr(void *ws, void *csr);
  * the operator the solver applies (P^-1 with the default ldiv=false). NULL detaches. */
 int krylov_b200_set_preconditioner_diag(void *ws, int which, const void *d, int location);
 
+/* cg_lanczos! (src/cg_lanczos.jl) has no slot in the reference's KrylovSolverType; this value selects it in
+ * krylov_workspace_create.  Options: M, check_curvature (KrylovB200Options), the common tolerances. */
+#define KRYLOV_B200_CG_LANCZOS 100
+
 /* Extra solve-time switches not present in KrylovOptions. */
 typedef struct {
   int history;        /* 1: record residual history (kwarg `history`)              */
@@ -150,6 +155,7 @@ typedef struct {
   int (*callback)(void *ws, void *user); /* kwarg `callback`; nonzero return = stop */
   void *callback_user;
   int time_kernels;   /* fused CG: event-time launches 8..39 of each kernel (see krylov_b200_get_kernel_times) */
+  int check_curvature; /* CG-Lanczos: kwarg `check_curvature` (src/cg_lanczos.jl:94)                            */
 } KrylovB200Options;
 KrylovB200Options krylov_b200_default_options(void);
 int krylov_b200_set_options(void *ws, const KrylovB200Options *opts);
@@ -167,6 +173,7 @@ typedef struct {
   double allocation_timer;
   double timer;
   char status[96];
+  double Anorm;       /* LanczosStats.Anorm (cg_lanczos!); NaN for the other solvers */
 } KrylovB200Stats;
 int krylov_b200_get_stats(void *ws, KrylovB200Stats *out);
 /* which: 0 residuals, 1 Aresiduals, 2 Acond.  Returns the number copied (<= cap) or -1. */

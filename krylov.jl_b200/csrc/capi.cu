@@ -61,7 +61,10 @@ int fail(const char* where, const char* msg) {
   return -1;
 }
 
-bool supported_solver(int s) { return s == S_CG || s == S_MINRES || s == S_GMRES || s == S_BICGSTAB; }
+bool supported_solver(int s) {
+  return s == S_CG || s == S_MINRES || s == S_GMRES || s == S_BICGSTAB || s == S_FOM || s == S_FGMRES || s == S_CGS ||
+         s == S_CG_LANCZOS;
+}
 
 int pick_device() {
   int cnt = 0;
@@ -135,7 +138,11 @@ SolveOpts map_opts(const Handle* h, const KrylovOptions* o) {
   s.timemax = std::isnan(o->timemax) ? INFINITY : o->timemax;
   if (h->solver == S_CG) { s.radius = o->radius; s.linesearch = o->linesearch != 0; }
   if (h->solver == S_MINRES) { s.lambda = o->lambda; s.linesearch = o->linesearch != 0; }
-  if (h->solver == S_GMRES) { s.restart = o->restart != 0; s.reorthogonalization = o->reorthogonalization != 0; }
+  // _typed_solve_gmres! serves GMRES, FGMRES and FOM (c_stores.jl:376-398)
+  if (h->solver == S_GMRES || h->solver == S_FGMRES || h->solver == S_FOM) {
+    s.restart = o->restart != 0; s.reorthogonalization = o->reorthogonalization != 0;
+  }
+  s.check_curvature = h->ext.check_curvature != 0;
   s.history = h->ext.history != 0;
   s.ldiv = h->ext.ldiv != 0;
   s.etol = std::isnan(h->ext.etol) ? -1 : h->ext.etol;
@@ -168,6 +175,14 @@ int do_solve(Handle* h, KrylovMatvec fA, KrylovMatvec fM, KrylovMatvec fN, const
     case S_CG: cg_solve<T>(*ws, A, bd, M, so); break;
     case S_MINRES: minres_solve<T>(*ws, A, bd, M, so); break;
     case S_GMRES: gmres_solve<T>(*ws, A, bd, M, N, so); break;
+    case S_FOM: fom_solve<T>(*ws, A, bd, M, N, so); break;
+    case S_FGMRES: fgmres_solve<T>(*ws, A, bd, M, N, so); break;
+    case S_CG_LANCZOS: cg_lanczos_solve<T>(*ws, A, bd, M, so); break;
+    case S_CGS: {
+      const T* cd = stage_in<T>(h, ws, c, ws->cbuf);
+      cgs_solve<T>(*ws, A, bd, cd, M, N, so);
+      break;
+    }
     case S_BICGSTAB: {
       // the reference's C layer never forwards `c` for BiCGSTAB (c = b); we accept it when given
       const T* cd = stage_in<T>(h, ws, c, ws->cbuf);
@@ -208,8 +223,10 @@ template <class T> void* vec_by_name(Workspace<T>* ws, const char* nm) {
   struct { const char* n; T* p; } tab[] = {
       {"x", ws->x}, {"dx", ws->dx}, {"r", ws->r}, {"p", ws->p}, {"Ap", ws->Ap}, {"z", ws->z}, {"npc_dir", ws->npc_dir},
       {"v", ws->kind == S_MINRES ? (ws->vv ? ws->vv : ws->r2) : ws->v}, {"s", ws->s}, {"qd", ws->qd}, {"t", ws->t}, {"yz", ws->yz},
-      {"r1", ws->r1}, {"r2", ws->r2}, {"w1", ws->w1}, {"w2", ws->w2}, {"y", ws->y}, {"w", ws->w}, {"q", ws->q}};
+      {"r1", ws->r1}, {"r2", ws->r2}, {"w1", ws->w1}, {"w2", ws->w2}, {"y", ws->y}, {"w", ws->w}, {"q", ws->q},
+      {"u", ws->u}, {"ts", ws->ts}, {"vw", ws->vw}, {"Mv", ws->Mv}, {"Mv_prev", ws->Mv_prev}, {"Mv_next", ws->Mv_next}};
   for (auto& e : tab) if (!strcmp(e.n, nm)) return e.p;
+  if (nm[0] == 'Z') { int i = atoi(nm + 1); if (i >= 1 && i <= (int)ws->Z.size()) return ws->Z[i - 1]; return nullptr; }
   if (nm[0] == 'V') { int i = atoi(nm + 1); if (i >= 1 && i <= (int)ws->V.size()) return ws->V[i - 1]; }
   return nullptr;
 }
@@ -418,6 +435,7 @@ int krylov_b200_get_stats(void* ws, KrylovB200Stats* out) {
   out->npcCount = s.npcCount; out->nresiduals = (int)s.residuals.size(); out->nAresiduals = (int)s.Aresiduals.size();
   out->nAcond = (int)s.Acond.size(); out->allocation_timer = s.allocation_timer; out->timer = s.timer;
   strncpy(out->status, s.status.c_str(), sizeof(out->status) - 1);
+  out->Anorm = s.Anorm;
   return 0;
 }
 

@@ -359,7 +359,7 @@ template <class T> struct GmresMgsBody {  // q -= h_i v_i ; then <v_{i+1}, q> or
 
 // Arnoldi step k (1-based inner_iter): w = A V[k]; MGS against V[1..k]; returns h[0..k-1] and Hbis.
 template <class T>
-void gmres_fused_arnoldi(Workspace<T>& ws, const Csr<T>& A, int k, T* h_out, T* Hbis) {
+void gmres_fused_arnoldi(Workspace<T>& ws, const Csr<T>& A, int k, T* h_out, T* Hbis, const T* xin) {
   Ctx& c = ws.ctx;
   const int n = ws.n;
   typedef GmresState<T> St;
@@ -367,7 +367,7 @@ void gmres_fused_arnoldi(Workspace<T>& ws, const Csr<T>& A, int k, T* h_out, T* 
   St* H = (St*)ws.fused_host;
   const T* m = ws.mdiag_fused;
   T* q = m ? ws.q : ws.w;                                   // q == w when M = I (gmres.jl:150)
-  launch_spmv_epi<T, 1>(c, A, ws.V[k - 1], GmresSpmvEpi<T>{q, ws.V[0], m}, GmresHFin<T>{S, 0}, 4);
+  launch_spmv_epi<T, 1>(c, A, xin ? xin : ws.V[k - 1], GmresSpmvEpi<T>{q, ws.V[0], m}, GmresHFin<T>{S, 0}, 4);
   for (int i = 0; i < k; i++) {
     const T* vnext = (i + 1 < k) ? ws.V[i + 1] : nullptr;
     launch_stream<T, 1>(c, n, GmresMgsBody<T>{q, ws.V[i], vnext, S, i}, GmresHFin<T>{S, (i + 1 < k) ? i + 1 : -1}, 5);
@@ -389,15 +389,17 @@ template <class T, int NV> struct MultiAxpyBody {
   }
 };
 template <class T>
-void gmres_fused_update_x(Workspace<T>& ws, T* xr, int k, const T* y) {
+void fused_multi_axpy(Workspace<T>& ws, T* xr, int k, const T* y, T* const* vecs) {
   constexpr int NV = 8;
   for (int base = 0; base < k; base += NV) {
     MultiAxpyBody<T, NV> body;
     body.xr = xr; body.cnt = std::min(NV, k - base);
-    for (int i = 0; i < NV; i++) { body.v[i] = ws.V[std::min(base + i, k - 1)]; body.y[i] = (base + i < k) ? y[base + i] : T(0); }
+    for (int i = 0; i < NV; i++) { body.v[i] = vecs[std::min(base + i, k - 1)]; body.y[i] = (base + i < k) ? y[base + i] : T(0); }
     launch_stream<T, 0>(ws.ctx, ws.n, body, NoFin(), 5);
   }
 }
+template <class T>
+void gmres_fused_update_x(Workspace<T>& ws, T* xr, int k, const T* y) { fused_multi_axpy<T>(ws, xr, k, y, ws.V.data()); }
 
 int gmres_fused_max() { return kGmresMaxFused; }
 
@@ -405,7 +407,8 @@ int gmres_fused_max() { return kGmresMaxFused; }
   template void bicgstab_fused_iteration<T>(Workspace<T>&, const Csr<T>&, const T*, bool, T, T*, T*, T*, T*);         \
   template void minres_fused_lanczos<T>(Workspace<T>&, const Csr<T>&, int, T, T, T, T, T, T, T, T*, T*, T*);          \
   template T minres_fused_update<T>(Workspace<T>&, T*, T, T);                                                        \
-  template void gmres_fused_arnoldi<T>(Workspace<T>&, const Csr<T>&, int, T*, T*);                                   \
+  template void gmres_fused_arnoldi<T>(Workspace<T>&, const Csr<T>&, int, T*, T*, const T*);                         \
+  template void fused_multi_axpy<T>(Workspace<T>&, T*, int, const T*, T* const*);                                    \
   template void gmres_fused_update_x<T>(Workspace<T>&, T*, int, const T*);
 INST(double)
 INST(float)

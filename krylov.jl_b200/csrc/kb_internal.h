@@ -128,8 +128,9 @@ struct SolveOpts {
   bool linesearch = false;          // CG, MINRES
   double lambda = 0;                // MINRES
   double etol = -1, conlim = -1;    // MINRES (<0 => defaults)
-  bool restart = false;             // GMRES
-  bool reorthogonalization = false; // GMRES
+  bool restart = false;             // GMRES, FOM, FGMRES
+  bool reorthogonalization = false; // GMRES, FOM, FGMRES
+  bool check_curvature = false;     // CG-Lanczos
   bool ldiv = false;
   int (*callback)(void* ws, void* user) = nullptr;   // returns nonzero => user-requested exit
   void* callback_user = nullptr;
@@ -144,11 +145,13 @@ struct Stats {
   int npcCount = 0;
   std::vector<double> residuals, Aresiduals, Acond;
   double allocation_timer = 0, timer = 0;
+  double Anorm = NAN;                  // LanczosStats (cg_lanczos!)
   std::string status = "unknown";
   void reset() { residuals.clear(); Aresiduals.clear(); Acond.clear(); indefinite = false; npcCount = 0; }
 };
 
-enum SolverKind { S_CG = 0, S_MINRES = 3, S_GMRES = 8, S_BICGSTAB = 10 };
+// values of KrylovSolverType (interfaces/include/krylov.h:48-83); cg_lanczos has no slot in the reference's C enum
+enum SolverKind { S_CG = 0, S_MINRES = 3, S_FOM = 7, S_GMRES = 8, S_FGMRES = 9, S_BICGSTAB = 10, S_CGS = 11, S_CG_LANCZOS = 100 };
 
 // One workspace per (solver, dtype): owns every device vector of the solver
 // (src/krylov_workspaces.jl; SURVEY.md appendix B for fields and aliasing).
@@ -165,8 +168,11 @@ struct Workspace {
   T *p2 = nullptr;                                                                   // CG fused: second p buffer
   T *v = nullptr, *s = nullptr, *qd = nullptr, *t = nullptr, *yz = nullptr;           // BiCGSTAB (+ r, p)
   T *r1 = nullptr, *r2 = nullptr, *w1 = nullptr, *w2 = nullptr, *y = nullptr, *vv = nullptr;  // MINRES
-  T *w = nullptr, *q = nullptr, *pp = nullptr;                                        // GMRES (+ V)
+  T *w = nullptr, *q = nullptr, *pp = nullptr;                                        // GMRES / FOM / FGMRES (+ V)
+  T *u = nullptr, *ts = nullptr, *vw = nullptr;                                       // CGS (+ r, p, q, yz)
+  T *Mv = nullptr, *Mv_prev = nullptr, *Mv_next = nullptr;                            // CG-Lanczos (+ p, vv)
   std::vector<T*> V;
+  std::vector<T*> Z;                   // FGMRES: Z[k] = N_k V[k]
   std::vector<T> c, sgiv, zg, R;       // GMRES host-side Givens data
   std::vector<T> err_vec;              // MINRES window
   int memory = 20, window = 5;
@@ -212,6 +218,11 @@ template <class T> void cg_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b
 template <class T> void gmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const LinOp<T>& N, const SolveOpts& o);
 template <class T> void bicgstab_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c, const LinOp<T>& M, const LinOp<T>& N, const SolveOpts& o);
 template <class T> void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const SolveOpts& o);
+// Sibling solvers on the same kernels (siblings.cu)
+template <class T> void cgs_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c, const LinOp<T>& M, const LinOp<T>& N, const SolveOpts& o);
+template <class T> void cg_lanczos_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const SolveOpts& o);
+template <class T> void fom_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const LinOp<T>& N, const SolveOpts& o);
+template <class T> void fgmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const LinOp<T>& N, const SolveOpts& o);
 
 // Fused CG (cg_fused.cu).  Returns false if the configuration is not eligible
 // (caller falls back to the generic primitive path, still on the GPU).
@@ -228,7 +239,9 @@ template <class T> void bicgstab_fused_iteration(Workspace<T>& ws, const Csr<T>&
 template <class T> void minres_fused_lanczos(Workspace<T>& ws, const Csr<T>& A, int iter, T lambda, T beta, T oldbeta, T cs, T sn,
                                              T deltabar, T eps_rot, T* w, T* alpha, T* beta2);
 template <class T> T minres_fused_update(Workspace<T>& ws, T* w, T gamma, T phi);
-template <class T> void gmres_fused_arnoldi(Workspace<T>& ws, const Csr<T>& A, int k, T* h_out, T* Hbis);
+// xin: vector the operator is applied to (default V[k]; FGMRES passes Z[k])
+template <class T> void gmres_fused_arnoldi(Workspace<T>& ws, const Csr<T>& A, int k, T* h_out, T* Hbis, const T* xin = nullptr);
+template <class T> void fused_multi_axpy(Workspace<T>& ws, T* xr, int k, const T* y, T* const* vecs);
 template <class T> void gmres_fused_update_x(Workspace<T>& ws, T* xr, int k, const T* y);
 int gmres_fused_max();
 

@@ -1,0 +1,41 @@
+// solver_common.h -- small host helpers shared by the solver drivers (solvers.cu, siblings.cu).
+#pragma once
+#include <cmath>
+#include <limits>
+
+#include "kb_internal.h"
+
+namespace kb {
+
+template <class T> static inline T eps_of() { return std::numeric_limits<T>::epsilon(); }
+template <class T> static inline T tol_of(double t) { return t < 0 ? std::sqrt(eps_of<T>()) : (T)t; }
+
+// allocate_if (src/krylov_utils.jl:281-288)
+template <class T> static inline void allocate_if(bool cond, Workspace<T>& ws, T*& v) {
+  const double t0 = now_seconds();
+  if (cond && !v) v = dev_alloc<T>((size_t)ws.n);
+  ws.stats.allocation_timer += now_seconds() - t0;
+}
+
+static inline bool kdisplay(int iter, int verbose) { return verbose > 0 && iter % verbose == 0; }
+
+// default itmax = 2n of the GLOBAL system (row-partitioned workspaces hold a slice)
+template <class T> static inline int default_itmax(const Workspace<T>& ws, int itmax) {
+  return itmax == 0 ? 2 * (int)(ws.dist.world > 1 ? ws.dist.nglobal : ws.n) : itmax;
+}
+
+// sym_givens, real case (src/krylov_utils.jl:21-51)
+template <class T> static inline void sym_givens(T a, T b, T* c, T* s, T* rho) {
+  const T sa = (T)((a > 0) - (a < 0)), sb = (T)((b > 0) - (b < 0));
+  if (b == T(0)) { *c = sa + (T)(a == T(0)); *s = T(0); *rho = std::fabs(a); }
+  else if (a == T(0)) { *c = T(0); *s = sb; *rho = std::fabs(b); }
+  else if (std::fabs(b) > std::fabs(a)) {
+    const T t = a / b;
+    *s = sb / std::sqrt(T(1) + t * t); *c = *s * t; *rho = b / *s;
+  } else {
+    const T t = b / a;
+    *c = sa / std::sqrt(T(1) + t * t); *s = *c * t; *rho = a / *c;
+  }
+}
+
+}  // namespace kb

@@ -7,12 +7,9 @@
 #include <cstring>
 #include <limits>
 
-#include "kb_internal.h"
+#include "solver_common.h"
 
 namespace kb {
-
-template <class T> static inline T eps_of() { return std::numeric_limits<T>::epsilon(); }
-template <class T> static inline T tol_of(double t) { return t < 0 ? std::sqrt(eps_of<T>()) : (T)t; }
 
 // ---------------------------------------------------------------------------
 // Workspaces  (src/krylov_workspaces.jl: CgWorkspace :236-291, MinresWorkspace
@@ -35,16 +32,21 @@ template <class T> Workspace<T>* ws_create(SolverKind kind, int m, int n, int me
         ws->window = window > 0 ? window : 5;
         ws->err_vec.assign(ws->window, T(0));
         break;
-      case S_GMRES: {
+      case S_GMRES: case S_FGMRES: case S_FOM: {     // FgmresWorkspace :2983-3003, FomWorkspace :3065-3084
         ws->w = A();
         int mem = memory > 0 ? memory : 20;
         if (mem > m) mem = m;                       // krylov_workspaces.jl:2900
         ws->memory = mem;
         for (int i = 0; i < mem; i++) ws->V.push_back(A());
+        if (kind == S_FGMRES) for (int i = 0; i < mem; i++) ws->Z.push_back(A());
+        // host-side small arrays: GMRES/FGMRES c, s, z, R; FOM l (sgiv), z (zg), U (R)
         ws->c.assign(mem, T(0)); ws->sgiv.assign(mem, T(0)); ws->zg.assign(mem, T(0));
         ws->R.assign((size_t)mem * (mem + 1) / 2, T(0));
         break;
       }
+      case S_CGS: ws->r = A(); ws->u = A(); ws->p = A(); ws->q = A(); ws->ts = A(); break;          // CgsWorkspace :1527-1545
+      case S_CG_LANCZOS: ws->Mv = A(); ws->Mv_prev = A(); ws->p = A(); ws->Mv_next = A(); break;    // CgLanczosWorkspace :575-591
+      default: throw std::runtime_error("unsupported solver");
     }
   } catch (...) {
     ws_destroy(ws);
@@ -58,9 +60,11 @@ template <class T> void ws_destroy(Workspace<T>* ws) {
   if (!ws) return;
   if (ws->ctx.stream) cudaStreamSynchronize(ws->ctx.stream);
   T* vecs[] = {ws->x, ws->dx, ws->r, ws->p, ws->Ap, ws->z, ws->npc_dir, ws->p2, ws->v, ws->s, ws->qd, ws->t, ws->yz,
-               ws->r1, ws->r2, ws->w1, ws->w2, ws->y, ws->vv, ws->w, ws->q, ws->pp, ws->bbuf, ws->cbuf};
+               ws->r1, ws->r2, ws->w1, ws->w2, ws->y, ws->vv, ws->w, ws->q, ws->pp, ws->bbuf, ws->cbuf,
+               ws->u, ws->ts, ws->vw, ws->Mv, ws->Mv_prev, ws->Mv_next};
   for (T* p : vecs) dev_free(p);
   for (T* p : ws->V) dev_free(p);
+  for (T* p : ws->Z) dev_free(p);
   if (ws->fused_state) cudaFree(ws->fused_state);
   if (ws->fused_host) cudaFreeHost(ws->fused_host);
   for (void* p : ws->dist.opened) cudaIpcCloseMemHandle(p);
@@ -79,21 +83,12 @@ template <class T> void ws_destroy(Workspace<T>* ws) {
   delete ws;
 }
 
-// allocate_if (src/krylov_utils.jl:281-288)
-template <class T> static void allocate_if(bool cond, Workspace<T>& ws, T*& v) {
-  const double t0 = now_seconds();
-  if (cond && !v) v = dev_alloc<T>((size_t)ws.n);
-  ws.stats.allocation_timer += now_seconds() - t0;
-}
-
 // warm_start! (src/workspace_accessors.jl:193-200)
 template <class T> void ws_warm_start(Workspace<T>* ws, const T* x0_dev) {
   allocate_if(true, *ws, ws->dx);
   k_copy<T>(ws->ctx, ws->n, ws->dx, x0_dev);
   ws->warm_start = true;
 }
-
-static bool kdisplay(int iter, int verbose) { return verbose > 0 && iter % verbose == 0; }
 
 // ===========================================================================
 // cg!  (src/cg.jl:120-291)
@@ -390,20 +385,6 @@ void bicgstab_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c_
   stats.niter = iter; stats.solved = solved; stats.inconsistent = false;
   stats.timer = now_seconds() - start_time;
   stats.status = status;
-}
-
-// sym_givens, real case (src/krylov_utils.jl:21-51)
-template <class T> static void sym_givens(T a, T b, T* c, T* s, T* rho) {
-  const T sa = (T)((a > 0) - (a < 0)), sb = (T)((b > 0) - (b < 0));
-  if (b == T(0)) { *c = sa + (T)(a == T(0)); *s = T(0); *rho = std::fabs(a); }
-  else if (a == T(0)) { *c = T(0); *s = sb; *rho = std::fabs(b); }
-  else if (std::fabs(b) > std::fabs(a)) {
-    const T t = a / b;
-    *s = sb / std::sqrt(T(1) + t * t); *c = *s * t; *rho = b / *s;
-  } else {
-    const T t = b / a;
-    *c = sa / std::sqrt(T(1) + t * t); *s = *c * t; *rho = a / *c;
-  }
 }
 
 // ===========================================================================

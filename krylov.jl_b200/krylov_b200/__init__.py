@@ -32,7 +32,9 @@ from ._lib import (KRYLOV_CPU, KRYLOV_CUDA, KRYLOV_FLOAT32, KRYLOV_FLOAT64, SOLV
 __all__ = ["CgWorkspace", "GmresWorkspace", "BicgstabWorkspace", "MinresWorkspace", "KrylovWorkspace", "SimpleStats",
            "cg", "cg_", "gmres", "gmres_", "bicgstab", "bicgstab_", "minres", "minres_", "krylov_workspace",
            "krylov_solve", "krylov_solve_", "solution", "statistics", "results", "issolved", "iteration_count",
-           "elapsed_time", "Aprod_count", "warm_start_", "device_count", "B200Error"]
+           "elapsed_time", "Aprod_count", "warm_start_", "device_count", "B200Error",
+           "FomWorkspace", "FgmresWorkspace", "CgsWorkspace", "CgLanczosWorkspace", "fom", "fom_", "fgmres", "fgmres_",
+           "cgs", "cgs_", "cg_lanczos", "cg_lanczos_"]
 
 
 class B200Error(RuntimeError):
@@ -53,6 +55,7 @@ class SimpleStats:
     allocation_timer: float = 0.0
     timer: float = 0.0
     status: str = "unknown"
+    Anorm: float = math.nan          # LanczosStats (src/krylov_stats.jl), cg_lanczos! only
 
 
 def device_count() -> int:
@@ -200,7 +203,8 @@ class KrylovWorkspace:
 
     def solve(self, A, b, *, c=None, M=None, N=None, atol=None, rtol=None, itmax=0, timemax=math.inf, verbose=0,
               history=False, callback=None, radius=0.0, linesearch=False, lambda_=0.0, etol=None, conlim=None,
-              restart=False, reorthogonalization=False, ldiv=False, fused=True, batch=0, time_kernels=False):
+              restart=False, reorthogonalization=False, ldiv=False, fused=True, batch=0, time_kernels=False,
+              check_curvature=False):
         """solver!(ws, A, b; kwargs...)  -- kwargs as in cg.jl:100-111, gmres.jl:96-108,
         bicgstab.jl:105-116, minres.jl:138-151.  M / N: None (identity), a 1-D array
         (Diagonal preconditioner) or a host callable."""
@@ -216,6 +220,7 @@ class KrylovWorkspace:
         e = lib().krylov_b200_default_options()
         e.history, e.ldiv, e.fused, e.batch = int(history), int(ldiv), int(fused), int(batch)
         e.time_kernels = int(time_kernels)
+        e.check_curvature = int(check_curvature)
         if etol is not None:
             e.etol = float(etol)
         if conlim is not None:
@@ -320,9 +325,11 @@ class KrylovWorkspace:
             buf = (C.c_double * max(cnt, 1))()
             k = lib().krylov_b200_get_history(self._h, which, buf, cnt)
             return list(buf[:max(k, 0)])
-        return SimpleStats(s.niter, bool(s.solved), bool(s.inconsistent), bool(s.indefinite), s.npcCount,
-                           hist(0, s.nresiduals), hist(1, s.nAresiduals), hist(2, s.nAcond), s.allocation_timer, s.timer,
-                           s.status.decode("utf-8"))
+        out = SimpleStats(s.niter, bool(s.solved), bool(s.inconsistent), bool(s.indefinite), s.npcCount,
+                          hist(0, s.nresiduals), hist(1, s.nAresiduals), hist(2, s.nAcond), s.allocation_timer, s.timer,
+                          s.status.decode("utf-8"))
+        out.Anorm = s.Anorm          # LanczosStats.Anorm (cg_lanczos!), NaN otherwise
+        return out
 
     @property
     def launches(self) -> int:
@@ -357,13 +364,32 @@ class BicgstabWorkspace(KrylovWorkspace):
     nA = 2
 
 
-_WS = {"cg": CgWorkspace, "minres": MinresWorkspace, "gmres": GmresWorkspace, "bicgstab": BicgstabWorkspace}
+# sibling solvers on the same kernels
+class FomWorkspace(KrylovWorkspace):
+    solver = "fom"
+
+
+class FgmresWorkspace(KrylovWorkspace):
+    solver = "fgmres"
+
+
+class CgsWorkspace(KrylovWorkspace):
+    solver = "cgs"
+    nA = 2
+
+
+class CgLanczosWorkspace(KrylovWorkspace):
+    solver = "cg_lanczos"
+
+
+_WS = {"cg": CgWorkspace, "minres": MinresWorkspace, "gmres": GmresWorkspace, "bicgstab": BicgstabWorkspace,
+       "fom": FomWorkspace, "fgmres": FgmresWorkspace, "cgs": CgsWorkspace, "cg_lanczos": CgLanczosWorkspace}
 
 
 def krylov_workspace(method: str, *args, **kw) -> KrylovWorkspace:
     """krylov_workspace(Val(method), ...)  (src/interface.jl:248-348)"""
     if method not in _WS:
-        raise B200Error(f"method {method!r} is outside the B200 path (cg, gmres, bicgstab, minres)")
+        raise B200Error(f"method {method!r} is outside the B200 path ({', '.join(sorted(_WS))})")
     return _WS[method](*args, **kw)
 
 
@@ -403,10 +429,13 @@ def _make_outofplace(name):
 
 cg_, gmres_, bicgstab_, minres_ = (_make_inplace(s) for s in ("cg", "gmres", "bicgstab", "minres"))
 cg, gmres, bicgstab, minres = (_make_outofplace(s) for s in ("cg", "gmres", "bicgstab", "minres"))
+fom_, fgmres_, cgs_, cg_lanczos_ = (_make_inplace(s) for s in ("fom", "fgmres", "cgs", "cg_lanczos"))
+fom, fgmres, cgs, cg_lanczos = (_make_outofplace(s) for s in ("fom", "fgmres", "cgs", "cg_lanczos"))
 
 
 def krylov_solve(method: str, A, b, x0=None, **kw):
-    return {"cg": cg, "gmres": gmres, "bicgstab": bicgstab, "minres": minres}[method](A, b, x0, **kw)
+    return {"cg": cg, "gmres": gmres, "bicgstab": bicgstab, "minres": minres, "fom": fom, "fgmres": fgmres, "cgs": cgs,
+            "cg_lanczos": cg_lanczos}[method](A, b, x0, **kw)
 
 
 # workspace_accessors.jl:140-152

@@ -17,7 +17,9 @@ SO_PATH = os.environ.get("KB200_LIB") or os.path.join(ROOT, "lib", "libkrylov_b2
 KRYLOV_FLOAT32, KRYLOV_FLOAT64 = 0, 1
 KRYLOV_CPU, KRYLOV_CUDA = 0, 1
 KRYLOV_CG, KRYLOV_MINRES, KRYLOV_GMRES, KRYLOV_BICGSTAB = 0, 3, 8, 10
-SOLVER_IDS = {"cg": KRYLOV_CG, "minres": KRYLOV_MINRES, "gmres": KRYLOV_GMRES, "bicgstab": KRYLOV_BICGSTAB}
+KRYLOV_FOM, KRYLOV_FGMRES, KRYLOV_CGS, KRYLOV_B200_CG_LANCZOS = 7, 9, 11, 100
+SOLVER_IDS = {"cg": KRYLOV_CG, "minres": KRYLOV_MINRES, "gmres": KRYLOV_GMRES, "bicgstab": KRYLOV_BICGSTAB,
+              "fom": KRYLOV_FOM, "fgmres": KRYLOV_FGMRES, "cgs": KRYLOV_CGS, "cg_lanczos": KRYLOV_B200_CG_LANCZOS}
 
 MATVEC = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p)
 CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
@@ -37,13 +39,14 @@ class KrylovOptions(C.Structure):
 class KrylovB200Options(C.Structure):
     _fields_ = [("history", C.c_int), ("ldiv", C.c_int), ("etol", C.c_double), ("conlim", C.c_double),
                 ("fused", C.c_int), ("batch", C.c_int), ("callback", CALLBACK), ("callback_user", C.c_void_p),
-                ("time_kernels", C.c_int)]
+                ("time_kernels", C.c_int), ("check_curvature", C.c_int)]
 
 
 class KrylovB200Stats(C.Structure):
     _fields_ = [("niter", C.c_int), ("solved", C.c_int), ("inconsistent", C.c_int), ("indefinite", C.c_int),
                 ("npcCount", C.c_int), ("nresiduals", C.c_int), ("nAresiduals", C.c_int), ("nAcond", C.c_int),
-                ("allocation_timer", C.c_double), ("timer", C.c_double), ("status", C.c_char * 96)]
+                ("allocation_timer", C.c_double), ("timer", C.c_double), ("status", C.c_char * 96),
+                ("Anorm", C.c_double)]
 
 
 # every symbol include/krylov_b200.h declares: name -> (restype, argtypes)

@@ -19,6 +19,7 @@
 #define POW pow
 #define EPS DBL_EPSILON
 #include "krylov_oracle_impl.h"
+#include "krylov_oracle_siblings.h"
 #undef REAL
 #undef SUF
 #undef SQRT
@@ -36,6 +37,7 @@
 #define POW powf
 #define EPS FLT_EPSILON
 #include "krylov_oracle_impl.h"
+#include "krylov_oracle_siblings.h"
 
 
 /* ---------------------------------------------------------------------------
@@ -87,4 +89,4 @@ double oracle_cg_timed_f64(int n, const int *rowptr, const int *colind, const do
   return t1 - t0;
 }
 
-int oracle_abi_version(void) { return 2; }
+int oracle_abi_version(void) { return 3; }

@@ -15,6 +15,7 @@
  * tests/test_oracle_kat.py; no Julia runtime exists here to compare iterates,
  * so iterate-level parity is "unpinned" exactly as for the four main solvers.
  */
+#define PUSH(arr, cnt, v) do { if ((arr) && (cnt) < o->hist_cap) (arr)[(cnt)] = (v); (cnt)++; } while (0)
 
 /* ============================ cgs!  (src/cgs.jl:125-282) ============================ */
 int SUF(oracle_cgs)(int n, const int *rowptr, const int *colind, const REAL *val,
@@ -492,3 +493,5 @@ done:
   free(V); free(Z); free(cc); free(ss); free(zz); free(R); free(w); free(qbuf); free(dx);
   return 0;
 }
+
+#undef PUSH

@@ -41,7 +41,7 @@ class Opts(C.Structure):
 def build(force: bool = False) -> str:
     """Compile oracle/libkrylov_oracle.so with the committed Makefile."""
     so = os.path.join(_HERE, "libkrylov_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("krylov_oracle.c", "krylov_oracle_impl.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("krylov_oracle.c", "krylov_oracle_impl.h", "krylov_oracle_siblings.h", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -169,6 +169,58 @@ def minres(A, b, x0=None, M=None, dtype=np.float64, **kw):
                                             _p(x), _p(res), _p(ares), _p(acond), _p(npc), C.byref(st))
     k = min(st.nAres, o.hist_cap)
     return _result(st, x, res, dict(Aresiduals=ares[:k].copy(), Acond=acond[:k].copy(), npc_dir=npc))
+
+
+def cgs(A, b, c=None, x0=None, M=None, N=None, dtype=np.float64, **kw):
+    """cgs! (src/cgs.jl:125-282)."""
+    suf, _ = _suf(dtype)
+    n, rp, ci, va = _csr(A, dtype)
+    b, c, x0, M, N = (_vec(v, dtype) for v in (b, c, x0, M, N))
+    o = _opts(n, kw, 1 << 22)
+    x = np.zeros(n, dtype)
+    res = np.zeros(o.hist_cap, dtype)
+    st = Stats()
+    getattr(lib(), f"oracle_cgs_{suf}")(n, _p(rp), _p(ci), _p(va), _p(b), _p(c), _p(x0), _p(M), _p(N),
+                                         C.byref(o), _p(x), _p(res), C.byref(st))
+    return _result(st, x, res)
+
+
+def cg_lanczos(A, b, x0=None, M=None, check_curvature=False, dtype=np.float64, **kw):
+    """cg_lanczos! (src/cg_lanczos.jl:110-264).  Extra stats key: Anorm (LanczosStats)."""
+    suf, ct = _suf(dtype)
+    n, rp, ci, va = _csr(A, dtype)
+    b, x0, M = _vec(b, dtype), _vec(x0, dtype), _vec(M, dtype)
+    o = _opts(n, kw, 1 << 22)
+    x = np.zeros(n, dtype)
+    res = np.zeros(o.hist_cap, dtype)
+    anorm = ct(0)
+    st = Stats()
+    getattr(lib(), f"oracle_cg_lanczos_{suf}")(n, _p(rp), _p(ci), _p(va), _p(b), _p(x0), _p(M), int(check_curvature),
+                                                C.byref(o), _p(x), _p(res), C.byref(anorm), C.byref(st))
+    return _result(st, x, res, dict(Anorm=float(anorm.value)))
+
+
+def _arnoldi_family(name, A, b, x0, M, N, dtype, kw):
+    suf, _ = _suf(dtype)
+    n, rp, ci, va = _csr(A, dtype)
+    b, x0, M, N = (_vec(v, dtype) for v in (b, x0, M, N))
+    o = _opts(n, kw, 1 << 22)
+    x = np.zeros(n, dtype)
+    res = np.zeros(o.hist_cap, dtype)
+    st = Stats()
+    getattr(lib(), f"oracle_{name}_{suf}")(n, _p(rp), _p(ci), _p(va), _p(b), _p(x0), _p(M), _p(N),
+                                            C.byref(o), _p(x), _p(res), C.byref(st))
+    return _result(st, x, res)
+
+
+def fom(A, b, x0=None, M=None, N=None, dtype=np.float64, **kw):
+    """fom! (src/fom.jl:121-368)."""
+    return _arnoldi_family("fom", A, b, x0, M, N, dtype, kw)
+
+
+def fgmres(A, b, x0=None, M=None, N=None, dtype=np.float64, **kw):
+    """fgmres! (src/fgmres.jl:128-388); N: None or the diagonal of a fixed right preconditioner."""
+    return _arnoldi_family("fgmres", A, b, x0, M, N, dtype, kw)
 
 
 def cg_timed(rowptr, colind, val, b, iters, threads=1):

@@ -42,13 +42,23 @@ def build(name):
         n = 40
         A = sp.csr_matrix(sp.diags([np.ones(n - 1), np.ones(n), np.ones(n - 1)], [-1, 0, 1]))
         return "minres", A, A @ np.arange(1.0, n + 1), {}, f64
+    # sibling solvers
+    if name == "cgs_kron10":
+        A = _mat(P.kron_unsymmetric_csr(10)); return "cgs", A, A @ np.ones(A.shape[0]), {}, f64
+    if name == "fom_kron10_mem30_restart":
+        A = _mat(P.kron_unsymmetric_csr(10)); return "fom", A, A @ np.ones(A.shape[0]), dict(memory=30, restart=True), f64
+    if name == "fgmres_kron10_mem30_restart":
+        A = _mat(P.kron_unsymmetric_csr(10)); return "fgmres", A, A @ np.ones(A.shape[0]), dict(memory=30, restart=True), f64
+    if name == "cg_lanczos_divgrad16":
+        A = _mat(P.div_grad_csr(16)); return "cg_lanczos", A, np.ones(A.shape[0]), {}, f64
     raise KeyError(name)
 
 
 NAMES = ["cg_divgrad16_default", "cg_divgrad32_bench", "cg_divgrad12_f32", "cg_ragged_7x5x3",
          "gmres_kron10_restart30", "gmres_divgrad16_mem10_restart", "gmres_divgrad16_mem10_norestart",
          "gmres_kron8_reorth", "bicgstab_kron10", "bicgstab_random3000_f32", "minres_divgrad16", "minres_shift",
-         "minres_indefinite"]
+         "minres_indefinite", "cgs_kron10", "fom_kron10_mem30_restart", "fgmres_kron10_mem30_restart",
+         "cg_lanczos_divgrad16"]
 
 
 def run_oracle(O, name):

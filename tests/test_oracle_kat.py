@@ -223,3 +223,102 @@ def test_float32_instantiation(O):
     assert resid(A, x.astype(np.float64), b) <= 1e-3
     x, st = O.bicgstab(A, b, dtype=np.float32)
     assert st["solved"]
+
+
+# ---- SURVEY.md 8(f)-3 sibling solvers (oracle/krylov_oracle_siblings.h) ---------------------------------------
+# test/test_cgs.jl
+def test_cgs_reference_cases(O):
+    tol = 1e-6
+    for gen in (O.symmetric_definite, O.symmetric_indefinite, O.sparse_laplacian):
+        A, b = gen()
+        x, st = O.cgs(A, b)
+        assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.kron_unsymmetric(8)
+    x, st = O.cgs(A, b)
+    assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.zero_rhs()
+    x, st = O.cgs(A, b)
+    assert np.linalg.norm(x) == 0 and st["status"] == "x is a zero-residual solution"
+    A, b, M = O.square_preconditioned()
+    x, st = O.cgs(A, b, M=M)
+    assert resid(A, x, b) <= tol and st["solved"]
+    x, st = O.cgs(A, b, N=M)
+    assert resid(A, x, b) <= tol and st["solved"]
+    A = sp.csr_matrix(np.array([[1.0, 2.0], [3.0, 4.0]]))             # bc_breakdown, test_cgs.jl
+    x, st = O.cgs(A, np.array([0.0, 1.0]), c=np.array([1.0, 0.0]))
+    assert st["status"] == "Breakdown bᴴc = 0" and not st["solved"] and st["niter"] == 0
+
+
+# test/test_cg_lanczos.jl
+def test_cg_lanczos_reference_cases(O):
+    tol = 1e-6
+    n = 10
+    A, b = O.symmetric_definite(n)
+    x, st = O.cg_lanczos(A, b, itmax=n)
+    assert resid(A, x, b) <= tol and st["solved"] and st["Anorm"] > 0
+    A = sp.lil_matrix(A)
+    A[n - 2, n - 2] = -4.0                                             # test_cg_lanczos.jl: negative curvature detection
+    x, st = O.cg_lanczos(sp.csr_matrix(A), b, check_curvature=True)
+    assert st["status"] == "negative curvature" and st["indefinite"]
+    A, b = O.zero_rhs()
+    x, st = O.cg_lanczos(A, b)
+    assert np.linalg.norm(x) == 0 and st["status"] == "x is a zero-residual solution"
+    A, b, M = O.square_preconditioned()
+    x, st = O.cg_lanczos(A, b, M=M)
+    assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.sparse_laplacian()                                        # same Krylov iterates as cg! (Frommer & Maass)
+    x, st = O.cg_lanczos(A, b)
+    xc, sc = O.cg(A, b)
+    assert st["niter"] == sc["niter"] and np.allclose(st["residuals"], sc["residuals"], rtol=1e-8)
+
+
+# test/test_fom.jl, test/test_fgmres.jl
+@pytest.mark.parametrize("name", ["fom", "fgmres"])
+def test_fom_fgmres_reference_cases(O, name):
+    f = getattr(O, name)
+    tol = 1e-6
+    for gen in (O.symmetric_definite, O.symmetric_indefinite):
+        A, b = gen()
+        x, st = f(A, b)
+        assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.kron_unsymmetric(8)
+    x, st = f(A, b)
+    assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.almost_singular()
+    x, st = f(A, b)
+    assert resid(A, x, b) <= 100 * tol and st["solved"]
+    A, b = O.square_inconsistent()
+    x, st = f(A, b)
+    assert st["inconsistent"]
+    A, b = O.zero_rhs()
+    x, st = f(A, b)
+    assert np.linalg.norm(x) == 0 and st["status"] == "x is a zero-residual solution"
+    A, b, M = O.square_preconditioned()
+    x, st = f(A, b, M=M)
+    assert np.linalg.norm(M * (b - A @ x)) / np.linalg.norm(M * b) <= tol and st["solved"]
+    x, st = f(A, b, N=M)
+    assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.sparse_laplacian()
+    d = 1.0 / A.diagonal()
+    for restart in (False, True):                                      # restart block of both test files
+        memory = 10
+        x, st = f(A, b, restart=restart, memory=memory)
+        assert resid(A, x, b) <= tol and st["niter"] > memory and st["solved"]
+        x, st = f(A, b, M=d, restart=restart, memory=memory)
+        assert np.linalg.norm(d * (b - A @ x)) / np.linalg.norm(d * b) <= tol and st["niter"] > memory and st["solved"]
+        x, st = f(A, b, N=d, restart=restart, memory=memory)
+        assert resid(A, x, b) <= tol and st["niter"] > memory and st["solved"]
+        x, st = f(A, b, M=d, N=1.0 / np.sqrt(A.diagonal()), restart=restart, memory=memory)
+        assert np.linalg.norm(d * (b - A @ x)) / np.linalg.norm(d * b) <= tol and st["niter"] > memory and st["solved"]
+    A, b = O.cartesian_poisson(12, 12)
+    x, st = f(A, b, reorthogonalization=True)
+    assert resid(A, x, b) <= tol and st["solved"]
+
+
+def test_fgmres_with_identity_N_is_gmres(O):
+    """fgmres! with N = I runs gmres!'s arithmetic exactly (Z[k] is a copy of V[k])."""
+    A, b = O.kron_unsymmetric(8)
+    for kw in (dict(memory=20), dict(memory=10, restart=True)):
+        xg, sg = O.gmres(A, b, **kw)
+        xf, sf = O.fgmres(A, b, **kw)
+        assert sg["niter"] == sf["niter"] and np.array_equal(sg["residuals"], sf["residuals"]) and np.array_equal(xg, xf)
