@@ -14,6 +14,7 @@
 
 #include "../../include/krylov_b200.h"
 #include "kb_internal.h"
+#include "block.h"
 
 using namespace kb;
 
@@ -32,6 +33,8 @@ struct CsrAny {
 
 struct Handle {
   int solver = 0, dtype = 1, device_kind = 0;
+  bool block = false;                  // ws is a BlockWorkspace (krylov_block_* entry points)
+  int p = 0;
   void* ws = nullptr;
   std::shared_ptr<CsrAny> csr;
   void* Mdiag = nullptr;
@@ -44,11 +47,14 @@ struct Handle {
 std::mutex g_mu;
 std::unordered_map<void*, Handle*> g_handles;
 
-Handle* lookup(void* p) {
+Handle* lookup_any(void* p) {
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_handles.find(p);
   return it == g_handles.end() ? nullptr : it->second;
 }
+// single-RHS entry points only accept single-RHS handles, block entry points only block handles
+Handle* lookup(void* p) { Handle* h = lookup_any(p); return (h && !h->block) ? h : nullptr; }
+Handle* lookup_block(void* p) { Handle* h = lookup_any(p); return (h && h->block) ? h : nullptr; }
 
 int fail(const char* where, const std::exception& e) {
   g_last_error = std::string(where) + ": " + e.what();
@@ -82,6 +88,16 @@ int pick_device() {
 }
 
 template <class T> Workspace<T>* W(Handle* h) { return reinterpret_cast<Workspace<T>*>(h->ws); }
+template <class T> BlockWorkspace<T>* BW(Handle* h) { return reinterpret_cast<BlockWorkspace<T>*>(h->ws); }
+// what the entry points shared by both handle kinds need
+Ctx& ctx_of(Handle* h) {
+  if (h->block) return h->dtype == KRYLOV_FLOAT64 ? BW<double>(h)->ctx : BW<float>(h)->ctx;
+  return h->dtype == KRYLOV_FLOAT64 ? W<double>(h)->ctx : W<float>(h)->ctx;
+}
+int n_of(Handle* h) {
+  if (h->block) return h->dtype == KRYLOV_FLOAT64 ? BW<double>(h)->n : BW<float>(h)->n;
+  return h->dtype == KRYLOV_FLOAT64 ? W<double>(h)->n : W<float>(h)->n;
+}
 template <class T> Csr<T>& csr_of(CsrAny& a);
 template <> Csr<double>& csr_of<double>(CsrAny& a) { return a.d; }
 template <> Csr<float>& csr_of<float>(CsrAny& a) { return a.f; }
@@ -217,7 +233,10 @@ template <class T> int do_warm_start(Handle* h, const void* x0, int n) {
 }
 
 template <class T> Stats& stats_of(Handle* h) { return W<T>(h)->stats; }
-Stats& stats_any(Handle* h) { return h->dtype == KRYLOV_FLOAT64 ? stats_of<double>(h) : stats_of<float>(h); }
+Stats& stats_any(Handle* h) {
+  if (h->block) return h->dtype == KRYLOV_FLOAT64 ? BW<double>(h)->stats : BW<float>(h)->stats;
+  return h->dtype == KRYLOV_FLOAT64 ? stats_of<double>(h) : stats_of<float>(h);
+}
 
 template <class T> void* vec_by_name(Workspace<T>* ws, const char* nm) {
   struct { const char* n; T* p; } tab[] = {
@@ -337,15 +356,134 @@ int krylov_workspace_free(void* ws) {
 }
 
 // Block solvers: outside the path.
-int krylov_block_workspace_create(KrylovBlockSolverType, int, int, int, KrylovDataType, KrylovDeviceType,
-                                  const KrylovWorkspaceOptions*, void**) { return -2; }
-int krylov_block_solve(void*, KrylovBlockMatvec, KrylovBlockMatvec, KrylovBlockMatvec, const void*, void*, const KrylovOptions*) { return -1; }
-int krylov_block_get_X(void*, void*, int, int) { return -1; }
-int krylov_block_is_solved(void*) { return -1; }
-int krylov_block_niter(void*) { return -1; }
-double krylov_block_elapsed_time(void*) { return -1.0; }
-int krylov_block_warm_start(void*, const void*, int, int) { return -2; }
-int krylov_block_workspace_free(void*) { return 1; }
+// Block solvers (interfaces/src/LibKrylov.jl block entry points; krylov.h:246-285).  block_gmres only:
+// KRYLOV_BLOCK_MINRES answers -2.  B, X, X0 are the reference's column-major n x p blocks.
+int krylov_block_workspace_create(KrylovBlockSolverType solver, int m, int n, int p, KrylovDataType dtype, KrylovDeviceType device,
+                                  const KrylovWorkspaceOptions* wopts, void** ws_out) {
+  try {
+    if (solver != KRYLOV_BLOCK_GMRES || (dtype != KRYLOV_FLOAT32 && dtype != KRYLOV_FLOAT64)) return -2;
+    if (device != KRYLOV_CPU && device != KRYLOV_CUDA) return fail("krylov_block_workspace_create", "unknown device");
+    if (!ws_out) return fail("krylov_block_workspace_create", "ws_out is NULL");
+    if (m < 0 || n < 0 || p < 1) return fail("krylov_block_workspace_create", "bad dimensions");
+    const int dev = pick_device();
+    const int memory = wopts ? wopts->memory : 0;
+    Handle* h = new Handle();
+    h->block = true; h->p = p; h->solver = (int)solver; h->dtype = (int)dtype; h->device_kind = (int)device;
+    h->ext = krylov_b200_default_options();
+    try {
+      if (dtype == KRYLOV_FLOAT64) h->ws = block_ws_create<double>(m, n, p, memory, dev);
+      else h->ws = block_ws_create<float>(m, n, p, memory, dev);
+    } catch (...) { delete h; throw; }
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      g_handles[h] = h;
+    }
+    *ws_out = h;
+    return 0;
+  } catch (const std::exception& e) { return fail("krylov_block_workspace_create", e); }
+}
+
+}  // extern "C" (templates below need C++ linkage)
+namespace {
+template <class T> BlockOp<T> make_block_cb(Handle* h, KrylovBlockMatvec fn, void* ud) {
+  BlockOp<T> op;
+  if (!fn) return op;
+  op.fn = fn; op.userdata = ud;
+  op.kind = h->device_kind == KRYLOV_CUDA ? BlockOp<T>::DEV_CB : BlockOp<T>::HOST_CB;
+  return op;
+}
+// caller block (host or device, column-major) -> device column-major staging in ws.tmp2
+template <class T> const T* stage_block(Handle* h, BlockWorkspace<T>* ws, const void* src) {
+  if (h->device_kind == KRYLOV_CUDA) return (const T*)src;
+  const size_t np = (size_t)ws->n * ws->p;
+  if (!ws->tmp2) ws->tmp2 = dev_alloc<T>(np);
+  KB_CUDA(cudaMemcpyAsync(ws->tmp2, src, sizeof(T) * np, cudaMemcpyHostToDevice, ws->ctx.stream));
+  return ws->tmp2;
+}
+template <class T> int do_block_solve(Handle* h, KrylovBlockMatvec fA, KrylovBlockMatvec fM, KrylovBlockMatvec fN, const void* B,
+                                      void* ud, const KrylovOptions* opts) {
+  BlockWorkspace<T>* ws = BW<T>(h);
+  KB_CUDA(cudaSetDevice(ws->ctx.device));
+  SolveOpts so = map_opts(h, opts);
+  KrylovOptions d = krylov_default_options();
+  const KrylovOptions* o = opts ? opts : &d;
+  so.restart = o->restart != 0; so.reorthogonalization = o->reorthogonalization != 0;
+  BlockOp<T> A = make_block_cb<T>(h, fA, ud);
+  if (!fA) {
+    if (!h->csr) throw std::runtime_error("no operator: pass matvec_A or attach one with krylov_b200_set_operator_csr");
+    A.kind = BlockOp<T>::CSR; A.csr = &csr_of<T>(*h->csr);
+    if (A.csr->n != ws->n) throw std::runtime_error("(workspace.m, workspace.n) is inconsistent with size(A)");
+  }
+  BlockOp<T> M = make_block_cb<T>(h, fM, ud), N = make_block_cb<T>(h, fN, ud);
+  if (!fM && h->Mdiag) { M.kind = BlockOp<T>::DIAG; M.diag = (const T*)h->Mdiag; }
+  if (!fN && h->Ndiag) { N.kind = BlockOp<T>::DIAG; N.diag = (const T*)h->Ndiag; }
+  if (!B) throw std::runtime_error("B is NULL");
+  const T* Bd = stage_block<T>(h, ws, B);
+  block_gmres_solve<T>(*ws, A, Bd, M, N, so);
+  return 0;
+}
+template <class T> int do_block_get_X(Handle* h, void* X, int n, int p) {
+  BlockWorkspace<T>* ws = BW<T>(h);
+  if (n != ws->n || p != ws->p) throw std::runtime_error("X should have size n x p");
+  KB_CUDA(cudaSetDevice(ws->ctx.device));
+  const size_t np = (size_t)n * p;
+  if (h->device_kind == KRYLOV_CUDA) { block_get_X<T>(*ws, (T*)X); return 0; }
+  block_get_X<T>(*ws, ws->tmp);
+  KB_CUDA(cudaMemcpyAsync(X, ws->tmp, sizeof(T) * np, cudaMemcpyDeviceToHost, ws->ctx.stream));
+  ws->ctx.sync();
+  return 0;
+}
+template <class T> int do_block_warm_start(Handle* h, const void* X0, int n, int p) {
+  BlockWorkspace<T>* ws = BW<T>(h);
+  if (n != ws->n || p != ws->p) throw std::runtime_error("X0 should have size n x p");
+  KB_CUDA(cudaSetDevice(ws->ctx.device));
+  block_warm_start<T>(*ws, stage_block<T>(h, ws, X0));
+  return 0;
+}
+}  // namespace
+extern "C" {
+
+int krylov_block_solve(void* ws, KrylovBlockMatvec matvec_A, KrylovBlockMatvec matvec_M, KrylovBlockMatvec matvec_N, const void* B,
+                       void* userdata, const KrylovOptions* opts) {
+  try {
+    Handle* h = lookup_block(ws);
+    if (!h) return fail("krylov_block_solve", "unknown block workspace handle");
+    return h->dtype == KRYLOV_FLOAT64 ? do_block_solve<double>(h, matvec_A, matvec_M, matvec_N, B, userdata, opts)
+                                      : do_block_solve<float>(h, matvec_A, matvec_M, matvec_N, B, userdata, opts);
+  } catch (const std::exception& e) { return fail("krylov_block_solve", e); }
+}
+int krylov_block_get_X(void* ws, void* X, int n, int p) {
+  try {
+    Handle* h = lookup_block(ws);
+    if (!h || !X) return fail("krylov_block_get_X", "bad arguments");
+    return h->dtype == KRYLOV_FLOAT64 ? do_block_get_X<double>(h, X, n, p) : do_block_get_X<float>(h, X, n, p);
+  } catch (const std::exception& e) { return fail("krylov_block_get_X", e); }
+}
+int krylov_block_is_solved(void* ws) { Handle* h = lookup_block(ws); return h ? (stats_any(h).solved ? 1 : 0) : -1; }
+int krylov_block_niter(void* ws) { Handle* h = lookup_block(ws); return h ? stats_any(h).niter : -1; }
+double krylov_block_elapsed_time(void* ws) { Handle* h = lookup_block(ws); return h ? stats_any(h).timer : -1.0; }
+int krylov_block_warm_start(void* ws, const void* x0, int n, int p) {
+  try {
+    Handle* h = lookup_block(ws);
+    if (!h || !x0) return fail("krylov_block_warm_start", "bad arguments");
+    return h->dtype == KRYLOV_FLOAT64 ? do_block_warm_start<double>(h, x0, n, p) : do_block_warm_start<float>(h, x0, n, p);
+  } catch (const std::exception& e) { return fail("krylov_block_warm_start", e); }
+}
+int krylov_block_workspace_free(void* ws) {
+  try {
+    Handle* h = lookup_block(ws);
+    if (!h) return 1;
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      g_handles.erase(ws);
+    }
+    h->csr.reset();
+    dev_free(h->Mdiag); dev_free(h->Ndiag);
+    if (h->dtype == KRYLOV_FLOAT64) block_ws_destroy<double>(BW<double>(h)); else block_ws_destroy<float>(BW<float>(h));
+    delete h;
+    return 0;
+  } catch (const std::exception& e) { return fail("krylov_block_workspace_free", e); }
+}
 
 // ------------------------------- part 2 -----------------------------------
 int krylov_b200_device_count(void) {
@@ -359,28 +497,24 @@ const char* krylov_b200_last_error(void) { return g_last_error.c_str(); }
 int krylov_b200_set_operator_csr(void* ws, int n, long long nnz, const void* rowptr, const void* colind, const void* values,
                                  int index_base, int index_bytes, int location) {
   try {
-    Handle* h = lookup(ws);
+    Handle* h = lookup_any(ws);
     if (!h) return fail("krylov_b200_set_operator_csr", "unknown workspace handle");
     auto a = std::make_shared<CsrAny>();
     a->dtype = h->dtype;
-    if (h->dtype == KRYLOV_FLOAT64) {
-      Workspace<double>* w = W<double>(h);
-      KB_CUDA(cudaSetDevice(w->ctx.device));
-      if (n != w->n) throw std::runtime_error("(workspace.m, workspace.n) is inconsistent with size(A)");
-      csr_upload<double>(w->ctx, a->d, n, nnz, rowptr, colind, (const double*)values, index_base, index_bytes, location != 0);
-    } else {
-      Workspace<float>* w = W<float>(h);
-      KB_CUDA(cudaSetDevice(w->ctx.device));
-      if (n != w->n) throw std::runtime_error("(workspace.m, workspace.n) is inconsistent with size(A)");
-      csr_upload<float>(w->ctx, a->f, n, nnz, rowptr, colind, (const float*)values, index_base, index_bytes, location != 0);
-    }
+    Ctx& cx = ctx_of(h);
+    KB_CUDA(cudaSetDevice(cx.device));
+    if (n != n_of(h)) throw std::runtime_error("(workspace.m, workspace.n) is inconsistent with size(A)");
+    if (h->dtype == KRYLOV_FLOAT64)
+      csr_upload<double>(cx, a->d, n, nnz, rowptr, colind, (const double*)values, index_base, index_bytes, location != 0);
+    else
+      csr_upload<float>(cx, a->f, n, nnz, rowptr, colind, (const float*)values, index_base, index_bytes, location != 0);
     h->csr = a;
     return 0;
   } catch (const std::exception& e) { return fail("krylov_b200_set_operator_csr", e); }
 }
 
 int krylov_b200_share_operator(void* ws, void* src) {
-  Handle* h = lookup(ws); Handle* s = lookup(src);
+  Handle* h = lookup_any(ws); Handle* s = lookup_any(src);
   if (!h || !s) return fail("krylov_b200_share_operator", "unknown workspace handle");
   if (!s->csr || s->dtype != h->dtype) return fail("krylov_b200_share_operator", "source has no CSR operator of this dtype");
   h->csr = s->csr;
@@ -388,7 +522,7 @@ int krylov_b200_share_operator(void* ws, void* src) {
 }
 
 int krylov_b200_attach_csr(void* ws, void* csr) {
-  Handle* h = lookup(ws);
+  Handle* h = lookup_any(ws);
   if (!h || !csr) return fail("krylov_b200_attach_csr", "bad arguments");
   CsrAny* a = (CsrAny*)csr;
   if (a->dtype != h->dtype) return fail("krylov_b200_attach_csr", "dtype mismatch");
@@ -398,14 +532,13 @@ int krylov_b200_attach_csr(void* ws, void* csr) {
 
 int krylov_b200_set_preconditioner_diag(void* ws, int which, const void* d, int location) {
   try {
-    Handle* h = lookup(ws);
+    Handle* h = lookup_any(ws);
     if (!h) return fail("krylov_b200_set_preconditioner_diag", "unknown workspace handle");
     void*& slot = which == 0 ? h->Mdiag : h->Ndiag;
     if (!d) { dev_free(slot); slot = nullptr; return 0; }
     const size_t esz = h->dtype == KRYLOV_FLOAT64 ? 8 : 4;
-    const int n = h->dtype == KRYLOV_FLOAT64 ? W<double>(h)->n : W<float>(h)->n;
-    const int dev = h->dtype == KRYLOV_FLOAT64 ? W<double>(h)->ctx.device : W<float>(h)->ctx.device;
-    KB_CUDA(cudaSetDevice(dev));
+    const int n = n_of(h);
+    KB_CUDA(cudaSetDevice(ctx_of(h).device));
     if (!slot) slot = dev_alloc<char>(esz * (size_t)n);
     KB_CUDA(cudaMemcpy(slot, d, esz * (size_t)n, location ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
     return 0;
@@ -420,14 +553,14 @@ KrylovB200Options krylov_b200_default_options(void) {
 }
 
 int krylov_b200_set_options(void* ws, const KrylovB200Options* opts) {
-  Handle* h = lookup(ws);
+  Handle* h = lookup_any(ws);
   if (!h) return fail("krylov_b200_set_options", "unknown workspace handle");
   h->ext = opts ? *opts : krylov_b200_default_options();
   return 0;
 }
 
 int krylov_b200_get_stats(void* ws, KrylovB200Stats* out) {
-  Handle* h = lookup(ws);
+  Handle* h = lookup_any(ws);
   if (!h || !out) return fail("krylov_b200_get_stats", "unknown workspace handle");
   const Stats& s = stats_any(h);
   memset(out, 0, sizeof(*out));
@@ -440,7 +573,7 @@ int krylov_b200_get_stats(void* ws, KrylovB200Stats* out) {
 }
 
 int krylov_b200_get_history(void* ws, int which, double* out, int cap) {
-  Handle* h = lookup(ws);
+  Handle* h = lookup_any(ws);
   if (!h) return fail("krylov_b200_get_history", "unknown workspace handle");
   const Stats& s = stats_any(h);
   const std::vector<double>& v = which == 0 ? s.residuals : which == 1 ? s.Aresiduals : s.Acond;
@@ -466,15 +599,15 @@ int krylov_b200_get_kernel_times(void* ws, double* out) {
 }
 
 long long krylov_b200_launch_count(void* ws) {
-  Handle* h = lookup(ws);
+  Handle* h = lookup_any(ws);
   if (!h) return -1;
-  return h->dtype == KRYLOV_FLOAT64 ? W<double>(h)->ctx.launches : W<float>(h)->ctx.launches;
+  return ctx_of(h).launches;
 }
 
 void* krylov_b200_stream(void* ws) {
-  Handle* h = lookup(ws);
+  Handle* h = lookup_any(ws);
   if (!h) return nullptr;
-  return h->dtype == KRYLOV_FLOAT64 ? (void*)W<double>(h)->ctx.stream : (void*)W<float>(h)->ctx.stream;
+  return (void*)ctx_of(h).stream;
 }
 
 // ------------------------------ row-partitioned solves --------------------

@@ -34,7 +34,7 @@ __all__ = ["CgWorkspace", "GmresWorkspace", "BicgstabWorkspace", "MinresWorkspac
            "krylov_solve", "krylov_solve_", "solution", "statistics", "results", "issolved", "iteration_count",
            "elapsed_time", "Aprod_count", "warm_start_", "device_count", "B200Error",
            "FomWorkspace", "FgmresWorkspace", "CgsWorkspace", "CgLanczosWorkspace", "fom", "fom_", "fgmres", "fgmres_",
-           "cgs", "cgs_", "cg_lanczos", "cg_lanczos_"]
+           "cgs", "cgs_", "cg_lanczos", "cg_lanczos_", "BlockGmresWorkspace", "block_gmres", "block_gmres_"]
 
 
 class B200Error(RuntimeError):
@@ -380,6 +380,163 @@ class CgsWorkspace(KrylovWorkspace):
 
 class CgLanczosWorkspace(KrylovWorkspace):
     solver = "cg_lanczos"
+
+
+class BlockGmresWorkspace(KrylovWorkspace):
+    """BlockGmresWorkspace(m, n, p, dtype; memory=5) (src/block_krylov_workspaces.jl:108-171): block_gmres! on
+    n x p blocks of right-hand sides.  B, X0 and X are n x p arrays (any layout on the Python
+    side; the C ABI exchanges the reference's column-major blocks)."""
+
+    solver = "block_gmres"
+
+    def __init__(self, m, n, p, dtype=np.float64, *, memory: int = 0, device: str = "host"):
+        self.m, self.n, self.p = int(m), int(n), int(p)
+        self.dtype = np.dtype(dtype)
+        self.device = device
+        self._keep = []
+        self._cb = None
+        self._h = C.c_void_p()
+        w = KrylovWorkspaceOptions(memory, 0)
+        rc = lib().krylov_block_workspace_create(0, self.m, self.n, self.p, _dtype_id(self.dtype),
+                                                 KRYLOV_CUDA if device == "cuda" else KRYLOV_CPU, C.byref(w), C.byref(self._h))
+        if rc != 0:
+            raise B200Error(f"krylov_block_workspace_create -> {rc}: {_lib.last_error()}")
+        self._ext = lib().krylov_b200_default_options()
+        self._op_id = None
+
+    def free(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().krylov_block_workspace_free(self._h)
+            self._h = C.c_void_p()
+
+    def _block_cb(self, f):
+        if f is None:
+            return _lib.BLOCK_MATVEC(), None
+        n, p, dt = self.n, self.p, self.dtype
+        if self.device == "cuda":
+            raise B200Error("Python callables are host operators; create the workspace with device='host'")
+
+        def tramp(xp, yp, pcols, _ud):
+            X = np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_byte)), shape=(n * pcols * dt.itemsize,)).view(dt)
+            Y = np.ctypeslib.as_array(C.cast(yp, C.POINTER(C.c_byte)), shape=(n * pcols * dt.itemsize,)).view(dt)
+            Y.reshape((pcols, n)).T[:] = f(X.reshape((pcols, n)).T)       # column-major n x p views
+        cb = _lib.BLOCK_MATVEC(tramp)
+        return cb, cb
+
+    def _colmajor(self, B):
+        if _is_torch(B):
+            return B.t().contiguous()                                     # p x n row-major == n x p column-major
+        return np.asfortranarray(B, dtype=self.dtype)
+
+    def solve(self, A, B, *, M=None, N=None, atol=None, rtol=None, itmax=0, timemax=math.inf, verbose=0, history=False,
+              callback=None, restart=False, reorthogonalization=False, ldiv=False):
+        """block_gmres!(ws, A, B; kwargs...)  (src/block_gmres.jl:85-98)."""
+        o = lib().krylov_default_options()
+        if atol is not None:
+            o.atol = float(atol)
+        if rtol is not None:
+            o.rtol = float(rtol)
+        o.itmax, o.verbose = int(itmax), int(verbose)
+        o.timemax = math.nan if math.isinf(timemax) else float(timemax)
+        o.restart, o.reorthogonalization = int(restart), int(reorthogonalization)
+        e = lib().krylov_b200_default_options()
+        e.history, e.ldiv = int(history), int(ldiv)
+        keep = []
+        if callback is not None:
+            wsref = self
+
+            def cb_tramp(_ws, _user):
+                r = callback(wsref)
+                if not isinstance(r, (bool, np.bool_)):
+                    wsref._cb_error = TypeError(f"callback must return Bool, got {type(r).__name__}")
+                    return 1
+                return int(r)
+            e.callback = _lib.CALLBACK(cb_tramp)
+            keep.append(e.callback)
+        self._cb_error = None
+        lib().krylov_b200_set_options(self._h, C.byref(e))
+        fA = None
+        if callable(A) and not hasattr(A, "shape"):
+            fA, k = self._block_cb(A)
+            keep.append(k)
+        elif A is not None:
+            self.set_operator(A)
+        fM = fN = None
+        for which, P in ((0, M), (1, N)):
+            if P is None:
+                self._set_diag(which, None)
+            elif callable(P) and not hasattr(P, "shape"):
+                f, k = self._block_cb(P)
+                keep.append(k)
+                if which == 0:
+                    fM = f
+                else:
+                    fN = f
+                self._set_diag(which, None)
+            else:
+                self._set_diag(which, P)
+        if tuple(B.shape) != (self.n, self.p):
+            raise B200Error("Inconsistent problem size")
+        if _is_torch(B) != (self.device == "cuda"):
+            raise B200Error("ktypeof(B) must match the workspace storage (host array / device tensor)")
+        Bc = self._colmajor(B)
+        pb, kb_ = _ptr(Bc)
+        null = _lib.BLOCK_MATVEC()
+        rc = lib().krylov_block_solve(self._h, fA or null, fM or null, fN or null, pb, None, C.byref(o))
+        del keep
+        if self._cb_error is not None:
+            raise self._cb_error
+        if rc != 0:
+            raise B200Error(_lib.last_error())
+        return self
+
+    def warm_start(self, X0):
+        if tuple(X0.shape) != (self.n, self.p):
+            raise B200Error(f"X0 should have size {self.n} x {self.p}")
+        Xc = self._colmajor(X0)
+        p, k = _ptr(Xc)
+        if lib().krylov_block_warm_start(self._h, p, self.n, self.p) != 0:
+            raise B200Error(_lib.last_error())
+        return self
+
+    @property
+    def x(self):
+        """solution(ws): n x p (host array, or a torch CUDA tensor for device workspaces)."""
+        if self.device == "cuda":
+            import torch
+            out = torch.empty((self.p, self.n), dtype=torch.float64 if self.dtype == np.float64 else torch.float32, device="cuda")
+            if lib().krylov_block_get_X(self._h, C.c_void_p(out.data_ptr()), self.n, self.p) != 0:
+                raise B200Error(_lib.last_error())
+            return out.t()
+        out = np.empty((self.n, self.p), dtype=self.dtype, order="F")
+        if lib().krylov_block_get_X(self._h, out.ctypes.data_as(C.c_void_p), self.n, self.p) != 0:
+            raise B200Error(_lib.last_error())
+        return out
+
+    X = x
+
+
+def block_gmres(A, B, X0=None, *, memory=0, **kw):
+    """(X, stats) = block_gmres(A, B[, X0]; memory=5, kwargs...)  (src/block_gmres.jl:1-60)"""
+    n, p = B.shape
+    dt = B.cpu().numpy().dtype if _is_torch(B) else np.asarray(B).dtype
+    if dt not in (np.float32, np.float64):
+        dt = np.float64
+    ws = BlockGmresWorkspace(n, n, p, dt, memory=memory, device="cuda" if _is_torch(B) else "host")
+    try:
+        if X0 is not None:
+            ws.warm_start(X0)
+        ws.solve(A, B if _is_torch(B) else np.asarray(B, dtype=dt), **kw)
+        return ws.x, ws.stats
+    finally:
+        ws.free()
+
+
+def block_gmres_(ws: BlockGmresWorkspace, A, B, X0=None, **kw):
+    """block_gmres!(workspace, A, B[, X0]; kwargs...)"""
+    if X0 is not None:
+        ws.warm_start(X0)
+    return ws.solve(A, B, **kw)
 
 
 _WS = {"cg": CgWorkspace, "minres": MinresWorkspace, "gmres": GmresWorkspace, "bicgstab": BicgstabWorkspace,

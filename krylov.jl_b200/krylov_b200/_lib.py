@@ -22,6 +22,7 @@ SOLVER_IDS = {"cg": KRYLOV_CG, "minres": KRYLOV_MINRES, "gmres": KRYLOV_GMRES, "
               "fom": KRYLOV_FOM, "fgmres": KRYLOV_FGMRES, "cgs": KRYLOV_CGS, "cg_lanczos": KRYLOV_B200_CG_LANCZOS}
 
 MATVEC = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p)
+BLOCK_MATVEC = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
 CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
 
 
@@ -65,8 +66,8 @@ SIGNATURES = {
     "krylov_warm_start": (_I, [_P, _P, _I]),
     "krylov_warm_start2": (_I, [_P, _P, _P, _I, _I]),
     "krylov_workspace_free": (_I, [_P]),
-    "krylov_block_workspace_create": (_I, [_I, _I, _I, _I, _I, _I, _P, C.POINTER(_P)]),
-    "krylov_block_solve": (_I, [_P, _P, _P, _P, _P, _P, _P]),
+    "krylov_block_workspace_create": (_I, [_I, _I, _I, _I, _I, _I, C.POINTER(KrylovWorkspaceOptions), C.POINTER(_P)]),
+    "krylov_block_solve": (_I, [_P, BLOCK_MATVEC, BLOCK_MATVEC, BLOCK_MATVEC, _P, _P, C.POINTER(KrylovOptions)]),
     "krylov_block_get_X": (_I, [_P, _P, _I, _I]),
     "krylov_block_is_solved": (_I, [_P]),
     "krylov_block_niter": (_I, [_P]),

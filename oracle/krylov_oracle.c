@@ -20,6 +20,7 @@
 #define EPS DBL_EPSILON
 #include "krylov_oracle_impl.h"
 #include "krylov_oracle_siblings.h"
+#include "krylov_oracle_block.h"
 #undef REAL
 #undef SUF
 #undef SQRT
@@ -38,6 +39,7 @@
 #define EPS FLT_EPSILON
 #include "krylov_oracle_impl.h"
 #include "krylov_oracle_siblings.h"
+#include "krylov_oracle_block.h"
 
 
 /* ---------------------------------------------------------------------------

@@ -41,7 +41,7 @@ class Opts(C.Structure):
 def build(force: bool = False) -> str:
     """Compile oracle/libkrylov_oracle.so with the committed Makefile."""
     so = os.path.join(_HERE, "libkrylov_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("krylov_oracle.c", "krylov_oracle_impl.h", "krylov_oracle_siblings.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("krylov_oracle.c", "krylov_oracle_impl.h", "krylov_oracle_siblings.h", "krylov_oracle_block.h", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -221,6 +221,34 @@ def fom(A, b, x0=None, M=None, N=None, dtype=np.float64, **kw):
 def fgmres(A, b, x0=None, M=None, N=None, dtype=np.float64, **kw):
     """fgmres! (src/fgmres.jl:128-388); N: None or the diagonal of a fixed right preconditioner."""
     return _arnoldi_family("fgmres", A, b, x0, M, N, dtype, kw)
+
+
+def block_gmres(A, B, X0=None, M=None, N=None, dtype=np.float64, **kw):
+    """block_gmres! (src/block_gmres.jl:110-359).  B, X0, X: n x p (any layout; converted to column-major)."""
+    suf, _ = _suf(dtype)
+    n, rp, ci, va = _csr(A, dtype)
+    B = np.asfortranarray(B, dtype=dtype)
+    p = B.shape[1]
+    X0f = None if X0 is None else np.asfortranarray(X0, dtype=dtype)
+    M, N = _vec(M, dtype), _vec(N, dtype)
+    o = _opts(n, kw, 1 << 22)
+    X = np.zeros((n, p), dtype, order="F")
+    res = np.zeros(o.hist_cap, dtype)
+    st = Stats()
+    getattr(lib(), f"oracle_block_gmres_{suf}")(n, p, _p(rp), _p(ci), _p(va), _p(B), _p(X0f), _p(M), _p(N),
+                                                 C.byref(o), _p(X), _p(res), C.byref(st))
+    return _result(st, X, res)
+
+
+def householder(Q, compact=False, dtype=np.float64):
+    """householder!(Q, R, tau; compact) (src/block_krylov_utils.jl:201-208) -> (Q or reflectors, R, tau)."""
+    suf, _ = _suf(dtype)
+    Q = np.array(Q, dtype=dtype, order="F")
+    m, k = Q.shape
+    R = np.zeros((k, k), dtype, order="F")
+    tau = np.zeros(k, dtype)
+    getattr(lib(), f"oracle_householder_{suf}")(m, k, _p(Q), _p(R), _p(tau), int(compact))
+    return Q, R, tau
 
 
 def cg_timed(rowptr, colind, val, b, iters, threads=1):

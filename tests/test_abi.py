@@ -64,7 +64,9 @@ def test_unknown_solver_and_bad_handles():         # test_api.c:131-139, 175-182
     bogus = C.c_void_p(0x1234)
     assert L.krylov_workspace_free(bogus) == 1
     assert L.krylov_is_solved(bogus) == -1 and L.krylov_niter(bogus) == -1 and L.krylov_elapsed_time(bogus) == -1.0
-    assert L.krylov_block_workspace_create(0, 4, 4, 2, 1, 0, None, C.byref(ws)) == -2
+    assert L.krylov_block_workspace_create(1, 4, 4, 2, 1, 0, None, C.byref(ws)) == -2          # block_minres: outside the path
+    assert L.krylov_block_workspace_create(0, 4, 4, 2, 2, 0, None, C.byref(ws)) == -2          # complex block_gmres
+    assert L.krylov_block_workspace_free(bogus) == 1 and L.krylov_block_is_solved(bogus) == -1
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -322,3 +322,53 @@ def test_fgmres_with_identity_N_is_gmres(O):
         xg, sg = O.gmres(A, b, **kw)
         xf, sf = O.fgmres(A, b, **kw)
         assert sg["niter"] == sf["niter"] and np.array_equal(sg["residuals"], sf["residuals"]) and np.array_equal(xg, xf)
+
+
+# ---- SURVEY.md 8(f)-2 block_gmres (oracle/krylov_oracle_block.h) -----------------------------------------------
+def _test_block_problem(n=20, p=3):
+    """interfaces/test/C/test_block.c:36-87: A = tridiag(-1, 8, -1), X_true columns 1, t, t^2, B = A X_true."""
+    A = sp.diags([-np.ones(n - 1), 8.0 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1], format="csr")
+    t = np.arange(1, n + 1) / n
+    Xt = np.stack([np.ones(n), t, t * t][:p], axis=1)
+    return A, Xt, A @ Xt
+
+
+def test_householder_matches_lapack(O):
+    """householder! (src/block_krylov_utils.jl:201-208) calls LAPACK geqrf/orgqr; numpy.linalg.qr is the same LAPACK
+    pair, so the restated dgeqr2/dorg2r must agree to rounding, signs included."""
+    rng = np.random.default_rng(0)
+    for m, k in ((50, 6), (7, 7), (40, 1), (64, 16)):
+        Am = rng.standard_normal((m, k))
+        Q, R, tau = O.householder(Am)
+        Qn, Rn = np.linalg.qr(Am)
+        assert np.abs(Q - Qn).max() <= 1e-13 and np.abs(R - Rn).max() <= 1e-13
+        assert np.abs(Q.T @ Q - np.eye(k)).max() <= 1e-14
+
+
+def test_block_gmres_reference_c_cases(O):
+    """interfaces/test/C/test_block.c: solver, preconditioner (left / right Jacobi), warm start, memory=4."""
+    A, Xt, B = _test_block_problem()
+    kw = dict(atol=1e-10, rtol=1e-10, itmax=200)
+    X, st = O.block_gmres(A, B, **kw)
+    assert st["solved"] and st["niter"] > 0 and np.abs(X - Xt).max() < 1e-6
+    niter_cold = st["niter"]
+    d = 1.0 / A.diagonal()
+    for pre in (dict(M=d), dict(N=d)):
+        X, st = O.block_gmres(A, B, **pre, **kw)
+        assert st["solved"] and np.abs(X - Xt).max() < 1e-6
+    X, st = O.block_gmres(A, B, X0=Xt, **kw)
+    assert st["solved"] and st["niter"] < niter_cold
+    X, st = O.block_gmres(A, B, memory=4, **kw)
+    assert st["solved"] and np.abs(X - Xt).max() < 1e-6
+
+
+def test_block_gmres_with_one_column_is_gmres(O):
+    """p = 1: the block method is GMRES (Householder QR of one column is a normalisation up to sign)."""
+    A, b = O.kron_unsymmetric(6)
+    X, st = O.block_gmres(A, b[:, None], memory=20)
+    x, sg = O.gmres(A, b, memory=20)
+    assert st["niter"] == sg["niter"] and np.allclose(st["residuals"], sg["residuals"], rtol=1e-9)
+    assert np.allclose(X[:, 0], x, rtol=1e-9, atol=1e-12)
+    for kw in (dict(restart=True, memory=5), dict(reorthogonalization=True)):
+        X, st = O.block_gmres(A, np.stack([b, b[::-1].copy(), np.cos(np.arange(len(b)))], axis=1), **kw)
+        assert st["solved"]
