@@ -21,25 +21,33 @@
 
 #include "solver_common.h"
 #include "block.h"
+#include "spmv_tiles.cuh"
 
 namespace kb {
 
 constexpr int kMaxBlockP = 32;
-constexpr int kPanelTile = 64;      // rows of a panel staged per tile
+constexpr int kPanelTileElems = 2048;   // capacity of one staged panel tile (16 KB of doubles)
 
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-template <class T>
-__global__ void __launch_bounds__(kBlock) transpose_kernel(int rows, int cols, const T* __restrict__ in, T* __restrict__ out) {
-  // in: rows x cols row-major  ->  out: cols x rows row-major (i.e. `in` read as column-major cols x rows)
-  const long long total = (long long)rows * cols;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i / cols), c = (int)(i % cols);
-    out[(size_t)c * rows + r] = in[i];
+template <class T> struct Vec2 { T x, y; };
+template <class T> __device__ __forceinline__ Vec2<T> ld2(const T* p) {
+  return *reinterpret_cast<const Vec2<T>*>(p);   // p is 2-element aligned (P even, 256-byte aligned panels)
+}
+// Layout conversion between the ABI's column-major n x p blocks and the row-major panels: one thread per panel row,
+// so the column-major side is accessed coalesced across threads and the panel side as contiguous p-vectors.
+template <class T, bool TO_PANEL>
+__global__ void __launch_bounds__(kBlock) relayout_kernel(int n, int p, const T* __restrict__ in, T* __restrict__ out) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    for (int c = 0; c < p; c++) {
+      if (TO_PANEL) out[(size_t)r * p + c] = in[(size_t)c * n + r];
+      else out[(size_t)c * n + r] = in[(size_t)r * p + c];
+    }
   }
 }
 
+// W = A P, generic: p threads per row (any p, any row length)
 template <class T>
 __global__ void __launch_bounds__(kBlock) spmm_rows_kernel(Csr<T> A, int p, const T* __restrict__ X, T* __restrict__ Y) {
   const long long total = (long long)A.n * p;
@@ -52,6 +60,71 @@ __global__ void __launch_bounds__(kBlock) spmm_rows_kernel(Csr<T> A, int p, cons
   }
 }
 
+// W = A P on the TMA-staged tile pipeline of the SpMV (spmv_tiles.cuh: same producer, same shared-memory ring):
+// P lanes share a row (see the consumer loop).  Row sums accumulate in ascending column order, non-contracted, like
+// the SpMV.
+template <class T, int P>
+__global__ void __launch_bounds__(kTileThreads) spmm_tma_kernel(Csr<T> A, const T* __restrict__ X, T* __restrict__ Y) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const TileLayout<T> L{A.tile_cap};
+  const int S = A.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + S;
+  unsigned char* ring = smem + 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int VA = 16 / sizeof(T);
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == kConsumerWarps) {
+    if (lane == 0) tile_producer<T>(A, L, S, ring, full, empty);
+    return;
+  }
+  int it = 0;
+  for (int t = blockIdx.x; t < A.ntiles; t += gridDim.x, it++) {
+    const int s = it % S;
+    mbar_wait(&full[s], (it / S) & 1);
+    const unsigned char* st = ring + (size_t)s * L.stage_bytes();
+    const int* rp = reinterpret_cast<const int*>(st);
+    const T* vs = reinterpret_cast<const T*>(st + L.rp_bytes());
+    const int* cs = reinterpret_cast<const int*>(st + L.rp_bytes() + L.val_bytes());
+    {
+      // P lanes per row: the P lanes of a row read the same staged (value, column) pair (broadcast) and one contiguous
+      // P-vector of the panel (coalesced); a warp covers 32 / P rows per step and its 32 tile rows in P steps.
+      const int k0 = rp[0];
+      const T* vrow = vs - (k0 & ~(VA - 1));
+      const int* crow = cs - (k0 & ~3);
+      constexpr int RPW = 32 / P;
+      const int rsub = lane / P, c = lane % P;
+#pragma unroll 1
+      for (int step = 0; step < P; step++) {
+        const int lr = warp * 32 + step * RPW + rsub;          // row inside the tile
+        const int grow = t * kTileRows + lr;
+        if (grow < A.n) {
+          const int kb = rp[lr], ke = rp[lr + 1];
+          T acc = T(0);
+          for (int k = kb; k < ke; k += kGatherDepth) {
+            T xv[kGatherDepth], av[kGatherDepth];
+#pragma unroll
+            for (int u = 0; u < kGatherDepth; u++) {
+              if (k + u < ke) { av[u] = vrow[k + u]; xv[u] = __ldg(&X[(size_t)crow[k + u] * P + c]); }
+            }
+#pragma unroll
+            for (int u = 0; u < kGatherDepth; u++) {
+              if (k + u < ke) acc = add_rn(acc, mul_rn(av[u], xv[u]));
+            }
+          }
+          Y[(size_t)grow * P + c] = acc;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+}
+
 template <class T>
 __global__ void __launch_bounds__(kBlock) rows_diag_kernel(long long total, int p, const T* __restrict__ d, const T* __restrict__ in,
                                                           T* __restrict__ out, int ldiv) {
@@ -61,69 +134,343 @@ __global__ void __launch_bounds__(kBlock) rows_diag_kernel(long long total, int 
   }
 }
 
-// G(i,j) = sum_r V[r][i] Q[r][j], column-major p x p in `G`.  Threads are (pair, group): pair = (i,j), group g
-// takes rows g, g+ngroups, ... of every staged tile; groups are combined in shared memory, CTAs through `part`.
+// ---- tiles ------------------------------------------------------------------------------------------------------
+// A tile of `rows` panel rows is staged in shared memory with an ODD row stride ps = p | 1 (bank-conflict-free
+// when consecutive lanes read consecutive rows).  Both tall-skinny products are register-blocked 4 x 4: 16 FMAs per
+// 8 shared-memory loads, which is what keeps them HBM-bound up to p = 16 (fp64 FMA issue is the limit at p = 32).
+__host__ __device__ inline int panel_stride(int p) { return p | 1; }
+__host__ __device__ inline int panel_tile_rows(int p) { return kPanelTileElems / panel_stride(p); }
+
+template <class T>
+__device__ __forceinline__ void load_tile(T* dstS, const T* __restrict__ src, int rows, int p, int ps) {
+  for (int e = threadIdx.x; e < rows * p; e += kBlock) {
+    const int r = e / p, c = e - r * p;
+    dstS[r * ps + c] = src[e];
+  }
+}
+
+// G(i,j) = sum_r L[r][i] Rt[r][j], column-major p x p.  Thread = (4 x 4 block of G, row group): the block index
+// varies fastest across lanes, group g takes rows g, g + ngroups, ... of every staged tile.
+template <class T>
+struct PairAcc {
+  T acc[4][4];
+  int nbi, nb, ngroups, bi, bj, group;
+  bool active;
+  __device__ __forceinline__ void init(int p) {
+    nbi = (p + 3) >> 2;
+    nb = nbi * nbi;                               // <= 64 for p <= 32
+    ngroups = kBlock / nb;
+    const int tid = threadIdx.x;
+    active = tid < ngroups * nb;
+    const int blk = tid % nb;
+    group = tid / nb;
+    bi = (blk % nbi) * 4;
+    bj = (blk / nbi) * 4;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc[a][b] = T(0);
+  }
+  __device__ __forceinline__ void tile(int p, int ps, int rows, const T* Ls, const T* Rs) {
+    if (!active) return;
+    for (int r = group; r < rows; r += ngroups) {
+      T l[4], q[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        l[a] = bi + a < p ? Ls[r * ps + bi + a] : T(0);
+        q[a] = bj + a < p ? Rs[r * ps + bj + a] : T(0);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] += l[a] * q[b];
+    }
+  }
+  // combine the row groups of this CTA (fixed order) through `scratch` (>= 256 * 16 entries, may alias the tiles),
+  // then the CTAs ("last block finalises", fixed order) -> G
+  __device__ __forceinline__ void finish(int p, T* scratch, T* part, unsigned* ticket, T* G) {
+    __shared__ bool is_last;
+    const int tid = threadIdx.x;
+    const int pp = p * p;
+    __syncthreads();                              // tiles are dead from here on
+    if (active) {
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) scratch[tid * 16 + a * 4 + b] = acc[a][b];
+    }
+    __syncthreads();
+    for (int pair = tid; pair < pp; pair += kBlock) {
+      const int i = pair % p, j = pair / p;
+      const int blk = (i >> 2) + (j >> 2) * nbi, off = (i & 3) * 4 + (j & 3);
+      T s = T(0);
+      for (int g = 0; g < ngroups; g++) s += scratch[(g * nb + blk) * 16 + off];
+      part[(size_t)blockIdx.x * pp + pair] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned t = atomicAdd(ticket, 1u);
+      is_last = (t == gridDim.x - 1);
+      if (is_last) *ticket = 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int pair = tid; pair < pp; pair += kBlock) {
+      T s = T(0);
+      for (int b = 0; b < (int)gridDim.x; b++) s += __ldcg(&part[(size_t)b * pp + pair]);
+      G[pair] = s;
+    }
+  }
+};
+
+// Out tile <- beta * Out + alpha * In * S for one staged tile, 4 rows x 4 columns per thread.  Consecutive lanes take
+// consecutive rows (odd stride: conflict-free) and the same column block (S loads broadcast).  Results go to global
+// memory and, when OsNew != nullptr, into that shared tile (for a following product).
+template <class T>
+__device__ __forceinline__ void nn_tile(int p, int ps, int rows, T alpha, const T* Is, const T* Ss, T beta, const T* OsOld, T* OsNew,
+                                        T* OutG) {
+  const int R4 = (rows + 3) >> 2;                 // rows are handled as r, r + R4, r + 2 R4, r + 3 R4
+  const int ncq = (p + 3) >> 2;
+  for (int item = threadIdx.x; item < R4 * ncq; item += kBlock) {
+    const int rq = item % R4, cq = (item / R4) * 4;
+    T acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc[a][b] = T(0);
+    for (int i = 0; i < p; i++) {
+      T in[4], sv[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const int r = rq + a * R4;
+        in[a] = r < rows ? Is[r * ps + i] : T(0);
+        sv[a] = cq + a < p ? Ss[i + (cq + a) * p] : T(0);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = add_rn(acc[a][b], mul_rn(in[a], sv[b]));
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const int r = rq + a * R4;
+      if (r >= rows) continue;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int cidx = cq + b;
+        if (cidx >= p) continue;
+        const T v = beta == T(0) ? mul_rn(alpha, acc[a][b]) : add_rn(mul_rn(beta, OsOld[r * ps + cidx]), mul_rn(alpha, acc[a][b]));
+        if (OsNew) OsNew[r * ps + cidx] = v;
+        OutG[(size_t)r * p + cidx] = v;
+      }
+    }
+  }
+}
+
 template <class T>
 __global__ void __launch_bounds__(kBlock) panel_tn_kernel(int n, int p, const T* __restrict__ V, const T* __restrict__ Q,
                                                          T* part, unsigned* ticket, T* G) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* Vs = reinterpret_cast<T*>(smem_raw);
-  T* Qs = Vs + kPanelTile * p;
-  T* red = Qs + kPanelTile * p;                   // kBlock entries
-  const int pp = p * p;
-  const int ngroups = pp >= kBlock ? 1 : kBlock / pp;
-  const int npairs_thr = (pp + kBlock - 1) / kBlock;          // pairs per thread when pp > kBlock
-  const int tid = threadIdx.x;
-  const int group = pp >= kBlock ? 0 : tid / pp;
-  const bool active = pp >= kBlock ? true : group < ngroups;
-  T acc[4] = {T(0), T(0), T(0), T(0)};                          // pp <= 1024 -> at most 4 pairs per thread
-  const int ntiles = (n + kPanelTile - 1) / kPanelTile;
+  const int ps = panel_stride(p), trows = panel_tile_rows(p);
+  T* Vs = reinterpret_cast<T*>(smem_raw);         // 2 tiles of kPanelTileElems; reused as the 4096-entry scratch
+  T* Qs = Vs + kPanelTileElems;
+  PairAcc<T> pa;
+  pa.init(p);
+  const int ntiles = (n + trows - 1) / trows;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int r0 = tile * kPanelTile;
-    const int rows = min(kPanelTile, n - r0);
+    const int r0 = tile * trows;
+    const int rows = min(trows, n - r0);
     __syncthreads();
-    for (int e = tid; e < rows * p; e += kBlock) {
-      Vs[e] = V[(size_t)r0 * p + e];
-      Qs[e] = Q[(size_t)r0 * p + e];
-    }
+    load_tile(Vs, V + (size_t)r0 * p, rows, p, ps);
+    load_tile(Qs, Q + (size_t)r0 * p, rows, p, ps);
     __syncthreads();
-    if (active) {
-      if (pp >= kBlock) {
-        for (int q = 0; q < npairs_thr; q++) {
-          const int pair = tid + q * kBlock;
-          if (pair < pp) {
-            const int i = pair % p, j = pair / p;
-            T a = acc[q];
-            for (int r = 0; r < rows; r++) a += Vs[r * p + i] * Qs[r * p + j];
-            acc[q] = a;
+    pa.tile(p, ps, rows, Vs, Qs);
+  }
+  pa.finish(p, Vs, part, ticket, G);
+}
+
+// Fused update + next product (one pass over the panels instead of two):
+//   Out[r][:] = beta Out[r][:] + alpha In[r][:] S        then        G = Next^T Out   (Next == nullptr: Out^T Out)
+// Block Gram-Schmidt:  Q -= V_i Psi_i and Psi_{i+1} = V_{i+1}^T Q (or the Gram matrix Q^T Q of the panel QR after
+// the last block).  Panel QR pass 1:  Q <- Q R1^-1 and the second Gram matrix.  Out may alias In.
+template <class T>
+__global__ void __launch_bounds__(kBlock) panel_nn_tn_kernel(int n, int p, T alpha, const T* In, const T* __restrict__ S, T beta,
+                                                            T* Out, const T* Next, T* part, unsigned* ticket, T* G) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int ps = panel_stride(p), trows = panel_tile_rows(p);
+  T* Is = reinterpret_cast<T*>(smem_raw);         // 3 tiles + S
+  T* Os = Is + kPanelTileElems;
+  T* Ns = Os + kPanelTileElems;
+  T* Ss = Ns + kPanelTileElems;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < p * p; e += kBlock) Ss[e] = S[e];
+  PairAcc<T> pa;
+  pa.init(p);
+  const int ntiles = (n + trows - 1) / trows;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r0 = tile * trows;
+    const int rows = min(trows, n - r0);
+    __syncthreads();
+    load_tile(Is, In + (size_t)r0 * p, rows, p, ps);
+    if (beta != T(0)) load_tile(Os, (const T*)Out + (size_t)r0 * p, rows, p, ps);
+    if (Next) load_tile(Ns, Next + (size_t)r0 * p, rows, p, ps);
+    __syncthreads();
+    nn_tile<T>(p, ps, rows, alpha, Is, Ss, beta, Os, Os, Out + (size_t)r0 * p);
+    __syncthreads();
+    pa.tile(p, ps, rows, Next ? Ns : Os, Os);
+  }
+  pa.finish(p, Is, part, ticket, G);             // Is + Os = 4096 entries of scratch
+}
+
+// Out[r][j] = beta * Out[r][j] + alpha * sum_i In[r][i] S(i,j);  S column-major p x p in device memory.
+// In is staged per tile, so Out may alias In (the in-place Q <- Q S of the panel QR).
+template <class T>
+__global__ void __launch_bounds__(kBlock) panel_nn_kernel(int n, int p, T alpha, const T* In, const T* __restrict__ S, T beta, T* Out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int ps = panel_stride(p), trows = panel_tile_rows(p);
+  T* Is = reinterpret_cast<T*>(smem_raw);
+  T* Os = Is + kPanelTileElems;
+  T* Ss = Os + kPanelTileElems;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < p * p; e += kBlock) Ss[e] = S[e];
+  const int ntiles = (n + trows - 1) / trows;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r0 = tile * trows;
+    const int rows = min(trows, n - r0);
+    __syncthreads();
+    load_tile(Is, In + (size_t)r0 * p, rows, p, ps);
+    if (beta != T(0)) load_tile(Os, (const T*)Out + (size_t)r0 * p, rows, p, ps);
+    __syncthreads();
+    nn_tile<T>(p, ps, rows, alpha, Is, Ss, beta, Os, (T*)nullptr, Out + (size_t)r0 * p);
+  }
+}
+
+// ---- register-resident fast path for P in {2, 4, 8, 16, 32} -------------------------------------------------------
+// No shared-memory tiles: TPR adjacent lanes share one panel row (1, 1, 2, 8, 16 for P = 2..32, chosen by the sweep
+// profiles/r1_sweep_block.txt), each owning a slab of
+// C = P/TPR columns of the updated row and a P x C slab (<= 64 accumulators) of the Gram-type product; operands stream from
+// global memory as 16-byte vectors (rows are contiguous), the TPR lanes of a row re-read it from L1.  ~190
+// instructions per row at P = 8 against 256 B of HBM traffic: bandwidth-bound, unlike the tiled generic kernels.
+//   UPDATE: Out[r][:] = beta Out[r][:] + alpha In[r][:] S         GRAM: G = Next^T Out  (Next == nullptr: Out^T Out)
+
+template <class T, int P, int TPR, bool UPDATE, bool GRAM>
+__global__ void __launch_bounds__(kBlock, (P * P / TPR <= 32 ? 2 : 1)) panel_fast_kernel(int n, T alpha, const T* In, const T* __restrict__ S,
+                                                                                     T beta, T* Out, const T* Next, T* part,
+                                                                                     unsigned* ticket, T* G) {
+  constexpr int C = P / TPR;
+  static_assert(P % 2 == 0 && C >= 2 && TPR <= 32, "fast path block sizes");
+  __shared__ __align__(16) T Ss[UPDATE ? P * P : 2];   // Ss[i * P + j] = S(i, j): the slab of row i is contiguous
+  __shared__ __align__(16) T Gs[GRAM ? P * P : 2];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slab = tid % TPR, c0 = slab * C;
+  if (UPDATE) {
+    for (int e = tid; e < P * P; e += kBlock) Ss[(e % P) * P + e / P] = S[e];     // column-major S -> row-major Ss
+    __syncthreads();
+  }
+  T acc[GRAM ? P : 1][C];
+  if (GRAM) {
+#pragma unroll
+    for (int i = 0; i < P; i++)
+#pragma unroll
+      for (int j = 0; j < C; j++) acc[i][j] = T(0);
+  }
+  const int rows_per_pass = gridDim.x * (kBlock / TPR);
+  const int first = blockIdx.x * (kBlock / TPR) + tid / TPR;
+  const int passes = (n + rows_per_pass - 1) / rows_per_pass;        // uniform trip count: shuffles stay convergent
+  for (int it = 0; it < passes; it++) {
+    const int row = first + it * rows_per_pass;
+    const bool valid = row < n;
+    const size_t base = (size_t)(valid ? row : 0) * P;
+    T outv[C];
+    if (UPDATE) {
+      T a[C];
+#pragma unroll
+      for (int j = 0; j < C; j++) a[j] = T(0);
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < P; i += 2) {
+          const Vec2<T> in = ld2(In + base + i);
+#pragma unroll
+          for (int j = 0; j < C; j++) a[j] = add_rn(add_rn(a[j], mul_rn(in.x, Ss[i * P + c0 + j])), mul_rn(in.y, Ss[(i + 1) * P + c0 + j]));
+        }
+        if (beta != T(0)) {
+#pragma unroll
+          for (int j = 0; j < C; j += 2) {
+            const Vec2<T> o = ld2(Out + base + c0 + j);
+            outv[j] = add_rn(mul_rn(beta, o.x), mul_rn(alpha, a[j]));
+            outv[j + 1] = add_rn(mul_rn(beta, o.y), mul_rn(alpha, a[j + 1]));
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < C; j++) outv[j] = mul_rn(alpha, a[j]);
         }
       } else {
-        const int pair = tid - group * pp;
-        const int i = pair % p, j = pair / p;
-        T a = acc[0];
-        for (int r = group; r < rows; r += ngroups) a += Vs[r * p + i] * Qs[r * p + j];
-        acc[0] = a;
+#pragma unroll
+        for (int j = 0; j < C; j++) outv[j] = T(0);
+      }
+      if (TPR > 1) __syncwarp();                   // Out may alias In: every lane of the row has read it by now
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < C; j += 2) {
+          Vec2<T> o; o.x = outv[j]; o.y = outv[j + 1];
+          *reinterpret_cast<Vec2<T>*>(Out + base + c0 + j) = o;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < C; j += 2) {
+        Vec2<T> o; o.x = T(0); o.y = T(0);
+        if (valid) o = ld2(Out + base + c0 + j);
+        outv[j] = o.x; outv[j + 1] = o.y;
+      }
+    }
+    if (GRAM) {
+      if (Next) {
+#pragma unroll
+        for (int i = 0; i < P; i += 2) {
+          Vec2<T> l; l.x = T(0); l.y = T(0);
+          if (valid) l = ld2(Next + base + i);
+#pragma unroll
+          for (int j = 0; j < C; j++) { acc[i][j] += l.x * outv[j]; acc[i + 1][j] += l.y * outv[j]; }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < TPR; k++) {            // the full updated row, slab by slab, from the lanes that own it
+#pragma unroll
+          for (int jj = 0; jj < C; jj++) {
+            const T l = TPR == 1 ? outv[jj] : __shfl_sync(0xffffffffu, outv[jj], (lane - slab) + k);
+#pragma unroll
+            for (int j = 0; j < C; j++) acc[k * C + jj][j] += l * outv[j];
+          }
+        }
       }
     }
   }
-  // combine the row groups of this CTA (fixed order), then the CTAs
-  __shared__ bool is_last;
-  if (pp < kBlock) {
-    __syncthreads();
-    red[tid] = active ? acc[0] : T(0);
-    __syncthreads();
-    if (tid < pp) {
-      T s = T(0);
-      for (int g = 0; g < ngroups; g++) s += red[g * pp + tid];
-      part[(size_t)blockIdx.x * pp + tid] = s;
+  if (!GRAM) return;
+  // rows of this warp (lanes with the same slab), then the warps in order, then the CTAs in order
+#pragma unroll
+  for (int i = 0; i < P; i++)
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+      T v = acc[i][j];
+      for (int off = TPR; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      acc[i][j] = v;
     }
-  } else {
-    for (int q = 0; q < npairs_thr; q++) {
-      const int pair = tid + q * kBlock;
-      if (pair < pp) part[(size_t)blockIdx.x * pp + pair] = acc[q];
+  for (int e = tid; e < P * P; e += kBlock) Gs[e] = T(0);
+  __syncthreads();
+  for (int w = 0; w < kBlock / 32; w++) {
+    if (warp == w && lane < TPR) {
+#pragma unroll
+      for (int i = 0; i < P; i++)
+#pragma unroll
+        for (int j = 0; j < C; j++) Gs[i + (c0 + j) * P] += acc[i][j];
     }
+    __syncthreads();
   }
+  for (int e = tid; e < P * P; e += kBlock) part[(size_t)blockIdx.x * (P * P) + e] = Gs[e];
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -134,36 +481,10 @@ __global__ void __launch_bounds__(kBlock) panel_tn_kernel(int n, int p, const T*
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  for (int pair = tid; pair < pp; pair += kBlock) {
+  for (int pair = tid; pair < P * P; pair += kBlock) {
     T s = T(0);
-    for (int b = 0; b < (int)gridDim.x; b++) s += __ldcg(&part[(size_t)b * pp + pair]);
+    for (int b = 0; b < (int)gridDim.x; b++) s += __ldcg(&part[(size_t)b * (P * P) + pair]);
     G[pair] = s;
-  }
-}
-
-// Out[r][j] = beta * Out[r][j] + alpha * sum_i In[r][i] S(i,j);  S column-major p x p in device memory.
-// In is staged per tile, so Out may alias In (the in-place Q <- Q S of the panel QR).
-template <class T>
-__global__ void __launch_bounds__(kBlock) panel_nn_kernel(int n, int p, T alpha, const T* In, const T* __restrict__ S, T beta, T* Out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* Is = reinterpret_cast<T*>(smem_raw);
-  T* Ss = Is + kPanelTile * p;
-  const int tid = threadIdx.x;
-  for (int e = tid; e < p * p; e += kBlock) Ss[e] = S[e];
-  const int ntiles = (n + kPanelTile - 1) / kPanelTile;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int r0 = tile * kPanelTile;
-    const int rows = min(kPanelTile, n - r0);
-    __syncthreads();
-    for (int e = tid; e < rows * p; e += kBlock) Is[e] = In[(size_t)r0 * p + e];
-    __syncthreads();
-    for (int e = tid; e < rows * p; e += kBlock) {
-      const int r = e / p, j = e % p;
-      T acc = T(0);
-      for (int i = 0; i < p; i++) acc = add_rn(acc, mul_rn(Is[r * p + i], Ss[i + j * p]));
-      const size_t g = (size_t)r0 * p + e;
-      Out[g] = beta == T(0) ? mul_rn(alpha, acc) : add_rn(mul_rn(beta, Out[g]), mul_rn(alpha, acc));
-    }
   }
 }
 
@@ -275,17 +596,45 @@ template <class T> static void householder_signs(int p, T* W, T* s) {
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
-template <class T> static int panel_grid(int n) {
-  const int ntiles = (n + kPanelTile - 1) / kPanelTile;
+template <class T> static int panel_grid(int n, int p) {
+  const int trows = panel_tile_rows(p);
+  const int ntiles = (n + trows - 1) / trows;
   return std::max(1, std::min(ntiles, sm_count() * 4));
 }
+// k_transpose(rows, cols): `in` is rows x cols row-major, `out` cols x rows row-major.  Only two shapes occur:
+// (p, n) = column-major block -> panel, and (n, p) = panel -> column-major block.
 template <class T> static void k_transpose(Ctx& c, int rows, int cols, const T* in, T* out) {
   if ((long long)rows * cols <= 0) return;
-  transpose_kernel<T><<<stream_grid((long long)rows * cols, 1, 8), kBlock, 0, c.stream>>>(rows, cols, in, out);
+  const bool to_panel = rows <= cols;          // p <= 32 < n on this path (n >= p is checked at creation)
+  const int n = to_panel ? cols : rows, p = to_panel ? rows : cols;
+  if (to_panel) relayout_kernel<T, true><<<stream_grid(n, 1, 8), kBlock, 0, c.stream>>>(n, p, in, out);
+  else relayout_kernel<T, false><<<stream_grid(n, 1, 8), kBlock, 0, c.stream>>>(n, p, in, out);
   KB_CUDA(cudaGetLastError()); c.launches++;
+}
+template <class T, int P> static void launch_spmm_tma(Ctx& c, const Csr<T>& A, const T* X, T* Y) {
+  static bool attr = false;
+  if (!attr) { KB_CUDA(cudaFuncSetAttribute(spmm_tma_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+  int occ = 0;
+  KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_tma_kernel<T, P>, kTileThreads, A.smem_bytes));
+  if (occ < 1) throw std::runtime_error("spmm_tma_kernel does not fit on an SM with the planned shared-memory ring");
+  const int grid = std::min(std::min(occ, A.ctas_per_sm) * sm_count(), std::max(1, A.ntiles));
+  spmm_tma_kernel<T, P><<<grid, kTileThreads, A.smem_bytes, c.stream>>>(A, X, Y);
 }
 template <class T> static void k_spmm(Ctx& c, const Csr<T>& A, int p, const T* X, T* Y) {
   if (A.n <= 0) return;
+  static const char* spmm_env = getenv("KB200_SPMM");          // "rows": force the generic kernel (A/B runs)
+  if (A.tma_ok && !getenv("KB200_BLOCK_GENERIC") && !(spmm_env && !strcmp(spmm_env, "rows"))) {
+    bool done = true;
+    switch (p) {
+      case 2: launch_spmm_tma<T, 2>(c, A, X, Y); break;
+      case 4: launch_spmm_tma<T, 4>(c, A, X, Y); break;
+      case 8: launch_spmm_tma<T, 8>(c, A, X, Y); break;
+      case 16: launch_spmm_tma<T, 16>(c, A, X, Y); break;
+      case 32: launch_spmm_tma<T, 32>(c, A, X, Y); break;
+      default: done = false;
+    }
+    if (done) { KB_CUDA(cudaGetLastError()); c.launches++; return; }
+  }
   spmm_rows_kernel<T><<<stream_grid((long long)A.n * p, 1, 8), kBlock, 0, c.stream>>>(A, p, X, Y);
   KB_CUDA(cudaGetLastError()); c.launches++;
 }
@@ -293,17 +642,53 @@ template <class T> static void k_rows_diag(Ctx& c, int n, int p, const T* d, con
   rows_diag_kernel<T><<<stream_grid((long long)n * p, 1, 8), kBlock, 0, c.stream>>>((long long)n * p, p, d, in, out, ldiv ? 1 : 0);
   KB_CUDA(cudaGetLastError()); c.launches++;
 }
+// fast-path dispatch: true when p has a register-resident specialization
+template <class T, bool UPDATE, bool GRAM>
+static bool launch_fast(BlockWorkspace<T>& ws, T alpha, const T* In, const T* S, T beta, T* Out, const T* Next, T* G) {
+  Ctx& c = ws.ctx;
+  if (ws.generic_kernels) return false;
+  const int grid = ws.fast_grid;
+  // KB200_FAST_TPR=alt selects the second lanes-per-row shape of P = 8 / 16 (sweeps, profiles/README.md)
+  static const bool alt = getenv("KB200_FAST_TPR") != nullptr;
+#define KB_FAST(PV, TV)                                                                                                   \
+  panel_fast_kernel<T, PV, TV, UPDATE, GRAM><<<grid, kBlock, 0, c.stream>>>(ws.n, alpha, In, S, beta, Out, Next, ws.part, \
+                                                                            c.tickets + 6, G)
+  switch (ws.p) {
+    case 2: KB_FAST(2, 1); break;
+    case 4: KB_FAST(4, 1); break;
+    case 8: if (alt) KB_FAST(8, 4); else KB_FAST(8, 2); break;
+    case 16: if (alt) KB_FAST(16, 4); else KB_FAST(16, 8); break;
+    case 32: KB_FAST(32, 16); break;
+    default: return false;
+  }
+#undef KB_FAST
+  KB_CUDA(cudaGetLastError()); c.launches++;
+  return true;
+}
+
 template <class T> static void k_panel_tn(BlockWorkspace<T>& ws, const T* V, const T* Q, T* G) {
   Ctx& c = ws.ctx;
   const int p = ws.p;
-  const size_t smem = sizeof(T) * ((size_t)2 * kPanelTile * p + kBlock);
+  if (launch_fast<T, false, true>(ws, T(0), (const T*)nullptr, (const T*)nullptr, T(0), const_cast<T*>(Q), V == Q ? (const T*)nullptr : V, G)) return;
+  const size_t smem = sizeof(T) * ((size_t)2 * kPanelTileElems);
   panel_tn_kernel<T><<<ws.grid, kBlock, smem, c.stream>>>(ws.n, p, V, Q, ws.part, c.tickets + 6, G);
+  KB_CUDA(cudaGetLastError()); c.launches++;
+}
+template <class T> static void k_panel_nn_tn(BlockWorkspace<T>& ws, T alpha, const T* In, const T* S, T beta, T* Out, const T* Next, T* G) {
+  Ctx& c = ws.ctx;
+  const int p = ws.p;
+  if (launch_fast<T, true, true>(ws, alpha, In, S, beta, Out, Next, G)) return;
+  const size_t smem = sizeof(T) * ((size_t)3 * kPanelTileElems + (size_t)p * p);
+  static bool attr = false;
+  if (!attr) { KB_CUDA(cudaFuncSetAttribute(panel_nn_tn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+  panel_nn_tn_kernel<T><<<ws.grid, kBlock, smem, c.stream>>>(ws.n, p, alpha, In, S, beta, Out, Next, ws.part, c.tickets + 6, G);
   KB_CUDA(cudaGetLastError()); c.launches++;
 }
 template <class T> static void k_panel_nn(BlockWorkspace<T>& ws, T alpha, const T* In, const T* S, T beta, T* Out) {
   Ctx& c = ws.ctx;
   const int p = ws.p;
-  const size_t smem = sizeof(T) * ((size_t)kPanelTile * p + (size_t)p * p);
+  if (launch_fast<T, true, false>(ws, alpha, In, S, beta, Out, (const T*)nullptr, (T*)nullptr)) return;
+  const size_t smem = sizeof(T) * ((size_t)2 * kPanelTileElems + (size_t)p * p);
   panel_nn_kernel<T><<<ws.grid, kBlock, smem, c.stream>>>(ws.n, p, alpha, In, S, beta, Out);
   KB_CUDA(cudaGetLastError()); c.launches++;
 }
@@ -336,57 +721,65 @@ template <class T> static void block_apply(BlockWorkspace<T>& ws, const BlockOp<
   }
 }
 
-// householder!(Q, R, tau) with compact = false on an n x p device panel: Q <- orthonormal factor, Rout <- p x p R
-template <class T> static void panel_qr(BlockWorkspace<T>& ws, T* Q, T* Rout) {
+// householder!(Q, R, tau) with compact = false on an n x p device panel: dst <- orthonormal factor (dst may be Q),
+// Rout <- p x p R.  Q is used as scratch.  gram_ready: Q^T Q is already in the pinned G block (the fused
+// Gram-Schmidt chain produced it and the caller synchronised).
+// Pinned layout of ws.hsmall: [G | top p rows of Q | Tinv pass 0 | Tinv pass 1 | slots...].
+template <class T> static void panel_qr(BlockWorkspace<T>& ws, T* Q, T* Rout, T* dst, bool gram_ready) {
   Ctx& c = ws.ctx;
   const int n = ws.n, p = ws.p, pp = p * p;
-  T* hG = ws.hsmall;            // pinned: [G | top]
+  T* hG = ws.hsmall;
   T* hTop = ws.hsmall + pp;
-  std::vector<T> R1(pp), R2(pp), Tinv(pp), tmp(pp), sgn(p);
-  bool ok = true;
+  T* hT[2] = {ws.hsmall + 2 * pp, ws.hsmall + 3 * pp};
+  std::vector<T> R1(pp), R2(pp), tmp(pp), sgn(p);
   int failed_pass = -1;
-  for (int pass = 0; pass < 2 && ok; pass++) {
+  if (!gram_ready) {
     k_panel_tn<T>(ws, Q, Q, ws.dG);
     KB_CUDA(cudaMemcpyAsync(hG, ws.dG, sizeof(T) * pp, cudaMemcpyDeviceToHost, c.stream));
-    if (pass == 1) KB_CUDA(cudaMemcpyAsync(hTop, Q, sizeof(T) * pp, cudaMemcpyDeviceToHost, c.stream));   // first p rows
     c.sync();
-    std::vector<T>& R = pass == 0 ? R1 : R2;
-    ok = dense::cholesky_upper<T>(p, hG, R.data());
-    if (!ok) { failed_pass = pass; break; }
-    dense::inv_upper<T>(p, R.data(), Tinv.data());
-    if (pass == 1) {
-      // top block of the final Q = (top of Q after pass 1) * R2^-1 ; rows of the row-major panel are rows of Q
-      std::vector<T> W(pp);
+  }
+  // pass 0: Q <- Q R1^-1, fused with the Gram matrix of the result
+  if (dense::cholesky_upper<T>(p, hG, R1.data())) {
+    dense::inv_upper<T>(p, R1.data(), hT[0]);
+    KB_CUDA(cudaMemcpyAsync(ws.dS, hT[0], sizeof(T) * pp, cudaMemcpyHostToDevice, c.stream));
+    k_panel_nn_tn<T>(ws, T(1), Q, ws.dS, T(0), Q, (const T*)nullptr, ws.dG);
+    KB_CUDA(cudaMemcpyAsync(hG, ws.dG, sizeof(T) * pp, cudaMemcpyDeviceToHost, c.stream));
+    KB_CUDA(cudaMemcpyAsync(hTop, Q, sizeof(T) * pp, cudaMemcpyDeviceToHost, c.stream));   // first p rows (row-major panel)
+    c.sync();
+    // pass 1: dst <- Q R2^-1 S with S the Householder signs
+    if (dense::cholesky_upper<T>(p, hG, R2.data())) {
+      T* Tinv = hT[1];
+      dense::inv_upper<T>(p, R2.data(), Tinv);
+      std::vector<T> W(pp);                      // top block of the final orthonormal factor
       for (int r = 0; r < p; r++)
         for (int j = 0; j < p; j++) {
-          T s = 0;
-          for (int i = 0; i < p; i++) s += hTop[r * p + i] * Tinv[i + j * p];
-          W[r + j * p] = s;
+          T sacc = 0;
+          for (int i = 0; i < p; i++) sacc += hTop[r * p + i] * Tinv[i + j * p];
+          W[r + j * p] = sacc;
         }
       dense::householder_signs<T>(p, W.data(), sgn.data());
-      for (int j = 0; j < p; j++) for (int i = 0; i < p; i++) Tinv[i + j * p] *= sgn[j];      // fold S into Q <- Q R2^-1 S
+      for (int j = 0; j < p; j++) for (int i = 0; i < p; i++) Tinv[i + j * p] *= sgn[j];
+      KB_CUDA(cudaMemcpyAsync(ws.dS, Tinv, sizeof(T) * pp, cudaMemcpyHostToDevice, c.stream));
+      k_panel_nn<T>(ws, T(1), Q, ws.dS, T(0), dst);
+      dense::matmul<T>(p, R2.data(), R1.data(), tmp.data());               // R = S R2 R1
+      for (int j = 0; j < p; j++) for (int i = 0; i < p; i++) Rout[i + j * p] = i <= j ? sgn[i] * tmp[i + j * p] : T(0);
+      return;
     }
-    KB_CUDA(cudaMemcpyAsync(ws.dS, Tinv.data(), sizeof(T) * pp, cudaMemcpyHostToDevice, c.stream));
-    k_panel_nn<T>(ws, T(1), Q, ws.dS, T(0), Q);
-    c.sync();                    // Tinv is a pageable host buffer reused by the next pass
+    failed_pass = 1;
+  } else {
+    failed_pass = 0;
   }
-  if (ok) {
-    dense::matmul<T>(p, R2.data(), R1.data(), tmp.data());               // R = S R2 R1
-    for (int j = 0; j < p; j++) for (int i = 0; i < p; i++) Rout[i + j * p] = i <= j ? sgn[i] * tmp[i + j * p] : T(0);
-    return;
-  }
-  // rank-deficient block: LAPACK's algorithm on the host (column-major), then back to the device
+  // rank-deficient (or too ill-conditioned) block: LAPACK's algorithm on the host (column-major), then back
   ws.qr_fallbacks++;
   if (n < p) throw std::runtime_error("block size exceeds the number of rows");
-  std::vector<T> hq((size_t)n * p), tau(p);
+  std::vector<T> hq((size_t)n * p), tau(p), Rh(pp);
   k_transpose<T>(c, n, p, Q, ws.tmp);
   KB_CUDA(cudaMemcpyAsync(hq.data(), ws.tmp, sizeof(T) * (size_t)n * p, cudaMemcpyDeviceToHost, c.stream));
   c.sync();
-  std::vector<T> Rh(pp);
   dense::householder_compact<T>(n, p, hq.data(), Rh.data(), tau.data());
   dense::org2r<T>(n, p, hq.data(), n, tau.data());
   KB_CUDA(cudaMemcpyAsync(ws.tmp, hq.data(), sizeof(T) * (size_t)n * p, cudaMemcpyHostToDevice, c.stream));
-  k_transpose<T>(c, p, n, ws.tmp, Q);
+  k_transpose<T>(c, p, n, ws.tmp, dst);
   c.sync();
   if (failed_pass == 1) { dense::matmul<T>(p, Rh.data(), R1.data(), tmp.data()); Rh = tmp; }   // Q was already Q R1^-1
   for (int i = 0; i < pp; i++) Rout[i] = Rh[i];
@@ -396,14 +789,14 @@ template <class T> static void panel_qr(BlockWorkspace<T>& ws, T* Q, T* Rout) {
 // workspace
 // ---------------------------------------------------------------------------
 template <class T> static void ensure_small(BlockWorkspace<T>& ws, int nblocks) {
-  // device Psi blocks and pinned slots for `nblocks` p x p blocks (+2 pinned blocks for the panel QR)
+  // device Psi blocks and pinned slots for `nblocks` p x p blocks (+4 pinned blocks for the panel QR)
   const size_t pp = (size_t)ws.p * ws.p;
   while ((int)ws.dPsi.size() < nblocks) {
     T* d = nullptr;
     KB_CUDA(cudaMalloc(&d, sizeof(T) * pp));
     ws.dPsi.push_back(d);
   }
-  const size_t need = (size_t)(nblocks + 2) * pp;
+  const size_t need = (size_t)(nblocks + 4) * pp;
   if (need > ws.hsmall_cap) {
     ws.ctx.sync();
     if (ws.hsmall) KB_CUDA(cudaFreeHost(ws.hsmall));
@@ -411,12 +804,13 @@ template <class T> static void ensure_small(BlockWorkspace<T>& ws, int nblocks) 
     KB_CUDA(cudaHostAlloc(&ws.hsmall, sizeof(T) * ws.hsmall_cap, cudaHostAllocDefault));
   }
 }
-template <class T> static T* slot(BlockWorkspace<T>& ws, int i) { return ws.hsmall + (size_t)(2 + i) * ws.p * ws.p; }
+template <class T> static T* slot(BlockWorkspace<T>& ws, int i) { return ws.hsmall + (size_t)(4 + i) * ws.p * ws.p; }
 
 template <class T> BlockWorkspace<T>* block_ws_create(int m, int n, int p, int memory, int device) {
   const double t0 = now_seconds();
   if (m != n) throw std::runtime_error("System must be square");
   if (p < 1 || p > kMaxBlockP) throw std::runtime_error("block size p must be in 1..32 on the B200 path");
+  if (n < p) throw std::runtime_error("block size exceeds the number of rows");
   BlockWorkspace<T>* ws = new BlockWorkspace<T>();
   try {
     ws->m = m; ws->n = n; ws->p = p;
@@ -431,8 +825,10 @@ template <class T> BlockWorkspace<T>* block_ws_create(int m, int n, int p, int m
     ws->Z.assign(mem, std::vector<T>(pp)); ws->R.assign((size_t)mem * (mem + 1) / 2, std::vector<T>(pp));
     ws->H.assign(mem, std::vector<T>(2 * pp)); ws->tau.assign(mem, std::vector<T>(p));
     ws->C.assign(pp, T(0)); ws->D.assign(2 * pp, T(0));
-    ws->grid = panel_grid<T>(n);
-    ws->part = dev_alloc<T>((size_t)ws->grid * pp);
+    ws->grid = panel_grid<T>(n, p);
+    ws->fast_grid = std::max(1, std::min(sm_count() * 2, (int)(((long long)n + kBlock - 1) / kBlock)));
+    ws->generic_kernels = getenv("KB200_BLOCK_GENERIC") != nullptr;     // tests: force the tiled any-p kernels
+    ws->part = dev_alloc<T>((size_t)std::max(ws->grid, ws->fast_grid) * pp);
     KB_CUDA(cudaMalloc(&ws->dG, sizeof(T) * pp));
     KB_CUDA(cudaMalloc(&ws->dS, sizeof(T) * pp));
     ensure_small(*ws, mem + 1);
@@ -553,8 +949,7 @@ void block_gmres_solve(BlockWorkspace<T>& ws, const BlockOp<T>& A, const T* B_co
         if (!MisI) block_apply(ws, M, W, R0, ldiv);
       }
     }
-    k_copy<T>(cx, np, V[0], R0);
-    panel_qr<T>(ws, V[0], Z[0].data());         // Gamma (Z[1]) and V_1
+    panel_qr<T>(ws, R0, Z[0].data(), V[0], false);   // copyto!(V[1], R0); householder!: Gamma (Z[1]) and V_1
     npass = npass + 1;
     inner_iter = 0;
     inner_tired = false;
@@ -574,25 +969,37 @@ void block_gmres_solve(BlockWorkspace<T>& ws, const BlockOp<T>& A, const T* B_co
       if (!NisI) block_apply(ws, N, Vk, P, ldiv);
       block_apply(ws, A, P, W, false);
       if (!MisI) block_apply(ws, M, W, Q, ldiv);
-      // block modified Gram-Schmidt: the Psi blocks stay on the device between the product that makes them and the
-      // update that consumes them; the host copies are fetched asynchronously and read after one sync
-      for (int i = 0; i < inner_iter; i++) {
-        k_panel_tn<T>(ws, V[i], Q, ws.dPsi[i]);
-        k_panel_nn<T>(ws, T(-1), V[i], ws.dPsi[i], T(1), Q);
-        KB_CUDA(cudaMemcpyAsync(slot(ws, i), ws.dPsi[i], sizeof(T) * pp, cudaMemcpyDeviceToHost, cx.stream));
-      }
-      cx.sync();
-      for (int i = 0; i < inner_iter; i++) std::memcpy(R[nr + i].data(), slot(ws, i), sizeof(T) * pp);
-      if (reorth) {
+      // block modified Gram-Schmidt.  The Psi blocks stay on the device between the product that makes them and the
+      // update that consumes them; each update Q -= V_i Psi_i also forms the next product (Psi_{i+1} = V_{i+1}^T Q,
+      // or the Gram matrix Q^T Q the panel QR starts from) in the same pass; host copies arrive after one sync.
+      T* dst = inner_iter < (int)V.size() ? V[inner_iter] : Q;      // where V_{k+1} goes (no separate copy)
+      if (!reorth) {
+        k_panel_tn<T>(ws, V[0], Q, ws.dPsi[0]);
         for (int i = 0; i < inner_iter; i++) {
-          k_panel_tn<T>(ws, V[i], Q, ws.dPsi[i]);
-          k_panel_nn<T>(ws, T(-1), V[i], ws.dPsi[i], T(1), Q);
+          const bool last = i + 1 == inner_iter;
+          k_panel_nn_tn<T>(ws, T(-1), V[i], ws.dPsi[i], T(1), Q, last ? (const T*)nullptr : V[i + 1], last ? ws.dG : ws.dPsi[i + 1]);
           KB_CUDA(cudaMemcpyAsync(slot(ws, i), ws.dPsi[i], sizeof(T) * pp, cudaMemcpyDeviceToHost, cx.stream));
         }
+        KB_CUDA(cudaMemcpyAsync(ws.hsmall, ws.dG, sizeof(T) * pp, cudaMemcpyDeviceToHost, cx.stream));
         cx.sync();
-        for (int i = 0; i < inner_iter; i++) { const T* t = slot(ws, i); for (size_t k = 0; k < pp; k++) R[nr + i][k] += t[k]; }
+        for (int i = 0; i < inner_iter; i++) std::memcpy(R[nr + i].data(), slot(ws, i), sizeof(T) * pp);
+        panel_qr<T>(ws, Q, C.data(), dst, true);  // V_{k+1} in dst, Psi_{k+1,k} in C
+      } else {
+        for (int pass = 0; pass < 2; pass++) {    // second pass: reorthogonalization, block_gmres.jl:250-256
+          for (int i = 0; i < inner_iter; i++) {
+            k_panel_tn<T>(ws, V[i], Q, ws.dPsi[i]);
+            k_panel_nn<T>(ws, T(-1), V[i], ws.dPsi[i], T(1), Q);
+            KB_CUDA(cudaMemcpyAsync(slot(ws, i), ws.dPsi[i], sizeof(T) * pp, cudaMemcpyDeviceToHost, cx.stream));
+          }
+          cx.sync();
+          for (int i = 0; i < inner_iter; i++) {
+            const T* t = slot(ws, i);
+            if (pass == 0) std::memcpy(R[nr + i].data(), t, sizeof(T) * pp);
+            else for (size_t k = 0; k < pp; k++) R[nr + i][k] += t[k];
+          }
+        }
+        panel_qr<T>(ws, Q, C.data(), dst, false);
       }
-      panel_qr<T>(ws, Q, C.data());             // V_{k+1} in Q, Psi_{k+1,k} in C
       for (int i = 0; i < inner_iter - 1; i++) {  // previous reflections, block_gmres.jl:268-274
         for (int c = 0; c < p; c++) for (int r = 0; r < p; r++) { D1[r + c * ldd] = R[nr + i][r + c * p]; D2[r + c * ldd] = R[nr + i + 1][r + c * p]; }
         dense::orm2r_lt<T>(2 * p, p, p, H[i].data(), 2 * p, tau[i].data(), D.data(), ldd);
@@ -620,7 +1027,7 @@ void block_gmres_solve(BlockWorkspace<T>& ws, const BlockOp<T>& A, const T* B_co
           Z.push_back(std::vector<T>(pp, T(0)));
           stats.allocation_timer += now_seconds() - t0;
         }
-        k_copy<T>(cx, np, V[inner_iter], Q);
+        if (dst != V[inner_iter]) k_copy<T>(cx, np, V[inner_iter], Q);     // only when V grew just now (copyto!(V[k+1], Q))
         for (int c = 0; c < p; c++) for (int r = 0; r < p; r++) Z[inner_iter][r + c * p] = D2[r + c * ldd];
       }
     }

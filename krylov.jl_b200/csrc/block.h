@@ -39,7 +39,9 @@ struct BlockWorkspace {
   T* hsmall = nullptr;                                  // pinned host staging (p x p blocks): [Gram | top of Q | slots...]
   size_t hsmall_cap = 0;
   T *hX = nullptr, *hY = nullptr;                       // pinned panels for host block callbacks
-  int grid = 1;
+  int grid = 1;                                         // tiled generic kernels
+  int fast_grid = 1;                                    // register-resident kernels (p = 2, 4, 8, 16, 32)
+  bool generic_kernels = false;
   long long qr_fallbacks = 0;
 };
 

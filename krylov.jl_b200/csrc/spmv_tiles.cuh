@@ -111,6 +111,39 @@ struct NoRowBegin {
   __device__ __forceinline__ int operator()(int) const { return 0; }
 };
 
+// The producer of the tile pipeline (one elected lane): for every tile of this CTA, wait for a free ring slot and
+// issue the three bulk copies (rowptr slice, values, column indices) that complete on the slot's `full` barrier.
+template <class T>
+__device__ __forceinline__ void tile_producer(const Csr<T>& A, const TileLayout<T>& L, int S, unsigned char* ring, uint64_t* full,
+                                              uint64_t* empty) {
+  constexpr int VA = 16 / sizeof(T);
+  const uint64_t pol = l2_evict_first_policy();
+  int it = 0;
+  int t = blockIdx.x;
+  int k0 = 0, k1 = 0;
+  if (t < A.ntiles) { k0 = __ldg(&A.rowptr[t * kTileRows]); k1 = __ldg(&A.rowptr[min(t * kTileRows + kTileRows, A.n)]); }
+  for (; t < A.ntiles; t += gridDim.x, it++) {
+    // start fetching the NEXT tile's nnz range before blocking on the ring slot
+    const int tn = t + gridDim.x;
+    int nk0 = 0, nk1 = 0;
+    if (tn < A.ntiles) { nk0 = __ldg(&A.rowptr[tn * kTileRows]); nk1 = __ldg(&A.rowptr[min(tn * kTileRows + kTileRows, A.n)]); }
+    const int s = it % S;
+    mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
+    unsigned char* st = ring + (size_t)s * L.stage_bytes();
+    const int r0 = t * kTileRows;
+    const int k0v = k0 & ~(VA - 1), k1v = (k1 + VA - 1) & ~(VA - 1);
+    const int k0c = k0 & ~3, k1c = (k1 + 3) & ~3;
+    const unsigned rp_b = (kTileRows + 4) * sizeof(int);
+    const unsigned v_b = (unsigned)(k1v - k0v) * sizeof(T);
+    const unsigned c_b = (unsigned)(k1c - k0c) * sizeof(int);
+    mbar_expect_tx(&full[s], rp_b + v_b + c_b);
+    tma_load_1d(st, A.rowptr + r0, rp_b, &full[s], pol);
+    if (v_b) tma_load_1d(st + L.rp_bytes(), A.val + k0v, v_b, &full[s], pol);
+    if (c_b) tma_load_1d(st + L.rp_bytes() + L.val_bytes(), A.colind + k0c, c_b, &full[s], pol);
+    k0 = nk0; k1 = nk1;
+  }
+}
+
 // Runs the tile pipeline.  Every thread of the CTA must call it (blockDim.x ==
 // kTileThreads).  `gather(j)` returns the x value for column j; `row_begin(row)`
 // is evaluated before the row's gathers (use it to start loads the epilogue
@@ -138,33 +171,7 @@ __device__ __forceinline__ void spmv_tiles_run(const Csr<T>& A, unsigned char* s
     // (Tried and removed, profiles/r1_sweep_k1.txt + r1_ab.txt: letting the whole producer warp walk the column
     //  indices of the queued tile and prefetch its x entries into L2 -- no gain at 3 stages, and the extra live
     //  state cost the kernel its 3-CTAs/SM register budget: 335 vs 299 us per iteration on the same GPU.)
-    if (lane == 0) {
-      const uint64_t pol = l2_evict_first_policy();
-      int it = 0;
-      int t = blockIdx.x;
-      int k0 = 0, k1 = 0;
-      if (t < A.ntiles) { k0 = __ldg(&A.rowptr[t * kTileRows]); k1 = __ldg(&A.rowptr[min(t * kTileRows + kTileRows, A.n)]); }
-      for (; t < A.ntiles; t += gridDim.x, it++) {
-        // start fetching the NEXT tile's nnz range before blocking on the ring slot
-        const int tn = t + gridDim.x;
-        int nk0 = 0, nk1 = 0;
-        if (tn < A.ntiles) { nk0 = __ldg(&A.rowptr[tn * kTileRows]); nk1 = __ldg(&A.rowptr[min(tn * kTileRows + kTileRows, A.n)]); }
-        const int s = it % S;
-        mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
-        unsigned char* st = ring + (size_t)s * L.stage_bytes();
-        const int r0 = t * kTileRows;
-        const int k0v = k0 & ~(VA - 1), k1v = (k1 + VA - 1) & ~(VA - 1);
-        const int k0c = k0 & ~3, k1c = (k1 + 3) & ~3;
-        const unsigned rp_b = (kTileRows + 4) * sizeof(int);
-        const unsigned v_b = (unsigned)(k1v - k0v) * sizeof(T);
-        const unsigned c_b = (unsigned)(k1c - k0c) * sizeof(int);
-        mbar_expect_tx(&full[s], rp_b + v_b + c_b);
-        tma_load_1d(st, A.rowptr + r0, rp_b, &full[s], pol);
-        if (v_b) tma_load_1d(st + L.rp_bytes(), A.val + k0v, v_b, &full[s], pol);
-        if (c_b) tma_load_1d(st + L.rp_bytes() + L.val_bytes(), A.colind + k0c, c_b, &full[s], pol);
-        k0 = nk0; k1 = nk1;
-      }
-    }
+    if (lane == 0) tile_producer<T>(A, L, S, ring, full, empty);
   } else {
     // ------------------------------ consumers -----------------------------
     int it = 0;

@@ -27,8 +27,13 @@ def _check(st, X, so, Xo, tol=1e-6):
     assert np.linalg.norm(X - Xo) <= 1e-6 * np.linalg.norm(Xo)
 
 
-@pytest.mark.parametrize("p", [1, 2, 3, 4, 8, 16, 32])
-def test_block_gmres_block_sizes(kb, O, p):
+@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 8, 16, 32])
+def test_block_gmres_block_sizes(kb, O, p, generic, monkeypatch):
+    """p = 2, 4, 8, 16, 32 run the register-resident panel kernels, every other p (and KB200_BLOCK_GENERIC=1) the tiled
+    any-p kernels; both against the oracle."""
+    if generic:
+        monkeypatch.setenv("KB200_BLOCK_GENERIC", "1")
     A, _ = O.kron_unsymmetric(8)
     A = sp.csr_matrix(A)
     B = A @ _rhs(A.shape[0], p)
