@@ -239,6 +239,15 @@ int kb200_fill(void *ctx, int dtype, int n, void *x, double v);
 void *kb200_csr_create(void *ctx, int dtype, int n, long long nnz, const void *rowptr, const void *colind,
                        const void *values, int index_base, int index_bytes, int location);
 void kb200_csr_destroy(void *csr);
+/* Data formats either side of the path.  kb200_csr_read_mtx: Matrix Market `matrix coordinate
+ * {real|integer|pattern} {general|symmetric|skew-symmetric}` (what benchmark/benchmarks.jl:23-33 reads through
+ * MatrixMarket.jl), duplicates summed, symmetric storage expanded; NULL on error (krylov_b200_last_error).
+ * kb200_csr_transpose: a new object holding A^T (= A^H for the real types here, docs/src/matrix_free.md:36-44). */
+void *kb200_csr_read_mtx(void *ctx, const char *path, int dtype);
+void *kb200_csr_transpose(void *ctx, void *csr);
+int kb200_csr_info(void *csr, int *n, long long *nnz);
+/* rowptr[n+1], colind[nnz] (0-based int32), values[nnz] in the object's dtype; any pointer may be NULL */
+int kb200_csr_download(void *ctx, void *csr, int *rowptr, int *colind, void *values);
 /* y = A x.  variant: 0 auto, 1 row-per-thread LDG kernel, 2 TMA-staged kernel. */
 int kb200_spmv_csr(void *ctx, void *csr, const void *x, void *y, int variant);
 /* staging plan of a CSR object: out[0]=ntiles out[1]=tile_cap out[2]=max_row out[3]=tma_ok out[4]=stages out[5]=grid out[6]=smem_bytes */

@@ -15,6 +15,7 @@
 #include "../../include/krylov_b200.h"
 #include "kb_internal.h"
 #include "block.h"
+#include "mtx.h"
 
 using namespace kb;
 
@@ -845,6 +846,66 @@ void* kb200_csr_create(void* ctx, int dtype, int n, long long nnz, const void* r
   } catch (const std::exception& e) { fail("kb200_csr_create", e); return nullptr; }
 }
 void kb200_csr_destroy(void* csr) { delete (CsrAny*)csr; }
+
+// Matrix Market ingestion and the transposed operator (mtx.cu)
+void* kb200_csr_read_mtx(void* ctx, const char* path, int dtype) {
+  try {
+    if (!ctx || !path) throw std::runtime_error("bad arguments");
+    Ctx& c = *(Ctx*)ctx;
+    HostCsr h;
+    read_matrix_market(path, h);
+    CsrAny* a = new CsrAny();
+    a->dtype = dtype; a->owner_ctx = &c;
+    try {
+      if (dtype == KRYLOV_FLOAT64) csr_from_host<double>(c, a->d, h);
+      else if (dtype == KRYLOV_FLOAT32) csr_from_host<float>(c, a->f, h);
+      else throw std::runtime_error("unsupported dtype");
+    } catch (...) { delete a; throw; }
+    return a;
+  } catch (const std::exception& e) { fail("kb200_csr_read_mtx", e); return nullptr; }
+}
+
+void* kb200_csr_transpose(void* ctx, void* csr) {
+  try {
+    if (!ctx || !csr) throw std::runtime_error("bad arguments");
+    Ctx& c = *(Ctx*)ctx;
+    CsrAny* src = (CsrAny*)csr;
+    HostCsr h, ht;
+    if (src->dtype == KRYLOV_FLOAT64) csr_to_host<double>(c, src->d, h); else csr_to_host<float>(c, src->f, h);
+    transpose_csr(h, ht);
+    CsrAny* a = new CsrAny();
+    a->dtype = src->dtype; a->owner_ctx = &c;
+    try {
+      if (a->dtype == KRYLOV_FLOAT64) csr_from_host<double>(c, a->d, ht); else csr_from_host<float>(c, a->f, ht);
+    } catch (...) { delete a; throw; }
+    return a;
+  } catch (const std::exception& e) { fail("kb200_csr_transpose", e); return nullptr; }
+}
+
+int kb200_csr_info(void* csr, int* n, long long* nnz) {
+  CsrAny* a = (CsrAny*)csr;
+  if (!a) return -1;
+  if (n) *n = a->dtype == KRYLOV_FLOAT64 ? a->d.n : a->f.n;
+  if (nnz) *nnz = a->dtype == KRYLOV_FLOAT64 ? a->d.nnz : a->f.nnz;
+  return 0;
+}
+
+int kb200_csr_download(void* ctx, void* csr, int* rowptr, int* colind, void* values) {
+  try {
+    if (!ctx || !csr) throw std::runtime_error("bad arguments");
+    Ctx& c = *(Ctx*)ctx;
+    CsrAny* a = (CsrAny*)csr;
+    HostCsr h;
+    if (a->dtype == KRYLOV_FLOAT64) csr_to_host<double>(c, a->d, h); else csr_to_host<float>(c, a->f, h);
+    if (rowptr) for (size_t i = 0; i < h.rowptr.size(); i++) rowptr[i] = (int)h.rowptr[i];
+    if (colind) for (size_t i = 0; i < h.colind.size(); i++) colind[i] = (int)h.colind[i];
+    if (values) {
+      if (a->dtype == KRYLOV_FLOAT64) std::memcpy(values, h.val.data(), sizeof(double) * h.val.size());
+      else for (size_t i = 0; i < h.val.size(); i++) ((float*)values)[i] = (float)h.val[i];
+    }
+    return 0;
+  } catch (const std::exception& e) { return fail("kb200_csr_download", e); }
+}
 
 int kb200_spmv_csr(void* ctx, void* csr, const void* x, void* y, int variant) {
   try {

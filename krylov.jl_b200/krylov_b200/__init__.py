@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Optional
 
@@ -34,7 +35,7 @@ __all__ = ["CgWorkspace", "GmresWorkspace", "BicgstabWorkspace", "MinresWorkspac
            "krylov_solve", "krylov_solve_", "solution", "statistics", "results", "issolved", "iteration_count",
            "elapsed_time", "Aprod_count", "warm_start_", "device_count", "B200Error",
            "FomWorkspace", "FgmresWorkspace", "CgsWorkspace", "CgLanczosWorkspace", "fom", "fom_", "fgmres", "fgmres_",
-           "cgs", "cgs_", "cg_lanczos", "cg_lanczos_", "BlockGmresWorkspace", "block_gmres", "block_gmres_"]
+           "cgs", "cgs_", "cg_lanczos", "cg_lanczos_", "BlockGmresWorkspace", "block_gmres", "block_gmres_", "CsrOperator"]
 
 
 class B200Error(RuntimeError):
@@ -83,6 +84,97 @@ def _ptr(a):
         a = a.contiguous()
         return C.c_void_p(a.data_ptr()), a
     return a.ctypes.data_as(C.c_void_p), a
+
+
+class CsrOperator:
+    """A CSR operator resident in HBM, independent of any workspace:
+
+        A = CsrOperator.read_mtx("bcsstk01.mtx")     # Matrix Market ingestion (benchmark/benchmarks.jl:23-33)
+        At = A.transpose()                           # A^T = A^H for the real types of this path
+        kb.cg(A, b)                                  # solvers accept it like a SciPy matrix
+    """
+
+    def __init__(self, csr_handle, ctx, dtype, owns_ctx=True):
+        self._csr, self._ctx, self.dtype, self._owns_ctx = csr_handle, ctx, np.dtype(dtype), owns_ctx
+        n, nnz = C.c_int(), C.c_longlong()
+        lib().kb200_csr_info(self._csr, C.byref(n), C.byref(nnz))
+        self.shape, self.nnz = (n.value, n.value), nnz.value
+
+    @classmethod
+    def read_mtx(cls, path, dtype=np.float64, device: int = -1):
+        ctx = lib().kb200_ctx_create(device)
+        if not ctx:
+            raise B200Error(_lib.last_error())
+        h = lib().kb200_csr_read_mtx(ctx, os.fsencode(path), _dtype_id(dtype))
+        if not h:
+            lib().kb200_ctx_destroy(ctx)
+            raise B200Error(_lib.last_error())
+        return cls(h, ctx, dtype)
+
+    @classmethod
+    def from_scipy(cls, A, dtype=None, device: int = -1):
+        import scipy.sparse as sp
+        M = sp.csr_matrix(A)
+        M.sort_indices()
+        dtype = np.dtype(dtype or M.dtype)
+        ctx = lib().kb200_ctx_create(device)
+        rp, ci, va = np.ascontiguousarray(M.indptr), np.ascontiguousarray(M.indices), np.ascontiguousarray(M.data, dtype=dtype)
+        h = lib().kb200_csr_create(ctx, _dtype_id(dtype), M.shape[0], int(M.nnz), rp.ctypes.data_as(C.c_void_p),
+                                   ci.astype(rp.dtype).ctypes.data_as(C.c_void_p), va.ctypes.data_as(C.c_void_p), 0, rp.dtype.itemsize, 0)
+        if not h:
+            lib().kb200_ctx_destroy(ctx)
+            raise B200Error(_lib.last_error())
+        return cls(h, ctx, dtype)
+
+    def transpose(self):
+        h = lib().kb200_csr_transpose(self._ctx, self._csr)
+        if not h:
+            raise B200Error(_lib.last_error())
+        out = CsrOperator(h, self._ctx, self.dtype, owns_ctx=False)
+        out._parent = self                       # shares (and keeps alive) the context
+        return out
+
+    T = property(transpose)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        n = self.shape[0]
+        rp, ci, va = np.empty(n + 1, np.int32), np.empty(self.nnz, np.int32), np.empty(self.nnz, self.dtype)
+        if lib().kb200_csr_download(self._ctx, self._csr, rp.ctypes.data_as(C.c_void_p), ci.ctypes.data_as(C.c_void_p),
+                                    va.ctypes.data_as(C.c_void_p)) != 0:
+            raise B200Error(_lib.last_error())
+        return sp.csr_matrix((va, ci, rp), shape=self.shape)
+
+    def matvec(self, x):
+        """y = A x on the GPU (host arrays in and out)."""
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        n = self.shape[0]
+        L = lib()
+        dx, dy = L.kb200_alloc(x.nbytes), L.kb200_alloc(x.nbytes)
+        try:
+            L.kb200_h2d(dx, x.ctypes.data_as(C.c_void_p), x.nbytes)
+            if L.kb200_spmv_csr(self._ctx, self._csr, dx, dy, 0) != 0 or L.kb200_sync(self._ctx) != 0:
+                raise B200Error(_lib.last_error())
+            y = np.empty(n, self.dtype)
+            L.kb200_d2h(y.ctypes.data_as(C.c_void_p), dy, y.nbytes)
+            return y
+        finally:
+            L.kb200_free(dx)
+            L.kb200_free(dy)
+
+    def free(self):
+        if getattr(self, "_csr", None):
+            lib().kb200_csr_destroy(self._csr)
+            self._csr = None
+            if self._owns_ctx and self._ctx:
+                lib().kb200_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class KrylovWorkspace:
@@ -138,6 +230,14 @@ class KrylovWorkspace:
     def set_operator(self, A):
         """Upload A as the device-resident CSR operator (krylov_b200_set_operator_csr)."""
         if id(A) == self._op_id:
+            return
+        if isinstance(A, CsrOperator):  # a device-resident operator (Matrix Market file, transposed operator, ...)
+            if A.shape != (self.m, self.n):
+                raise B200Error(f"(workspace.m, workspace.n) = ({self.m}, {self.n}) is inconsistent with size(A) = {A.shape}")
+            if lib().krylov_b200_attach_csr(self._h, A._csr) != 0:
+                raise B200Error(_lib.last_error())
+            self._keep.append(A)
+            self._op_id = id(A)
             return
         if isinstance(A, tuple):        # (rowptr, colind, values[, index_base]) NumPy or torch
             rp, ci, va = A[:3]

@@ -113,6 +113,10 @@ SIGNATURES = {
     "kb200_fill": (_I, [_P, _I, _I, _P, _D]),
     "kb200_csr_create": (_P, [_P, _I, _I, _LL, _P, _P, _P, _I, _I, _I]),
     "kb200_csr_destroy": (None, [_P]),
+    "kb200_csr_read_mtx": (_P, [_P, C.c_char_p, _I]),
+    "kb200_csr_transpose": (_P, [_P, _P]),
+    "kb200_csr_info": (_I, [_P, C.POINTER(_I), C.POINTER(_LL)]),
+    "kb200_csr_download": (_I, [_P, _P, _P, _P, _P]),
     "kb200_spmv_csr": (_I, [_P, _P, _P, _P, _I]),
     "kb200_csr_plan": (_I, [_P, C.POINTER(_LL)]),
 }
