@@ -70,7 +70,7 @@ int fail(const char* where, const char* msg) {
 
 bool supported_solver(int s) {
   return s == S_CG || s == S_MINRES || s == S_GMRES || s == S_BICGSTAB || s == S_FOM || s == S_FGMRES || s == S_CGS ||
-         s == S_CG_LANCZOS;
+         s == S_CG_LANCZOS || s == S_CR || s == S_DIOM || s == S_DQGMRES;
 }
 
 int pick_device() {
@@ -153,7 +153,9 @@ SolveOpts map_opts(const Handle* h, const KrylovOptions* o) {
   s.itmax = o->itmax;
   s.verbose = o->verbose;
   s.timemax = std::isnan(o->timemax) ? INFINITY : o->timemax;
-  if (h->solver == S_CG) { s.radius = o->radius; s.linesearch = o->linesearch != 0; }
+  if (h->solver == S_CG || h->solver == S_CR) { s.radius = o->radius; s.linesearch = o->linesearch != 0; }   // _typed_solve_cg!
+  if (h->solver == S_DIOM || h->solver == S_DQGMRES) s.reorthogonalization = o->reorthogonalization != 0;      // _typed_solve_mn_reorth!
+  s.cr_gamma = std::isnan(h->ext.cr_gamma) ? -1 : h->ext.cr_gamma;
   if (h->solver == S_MINRES) { s.lambda = o->lambda; s.linesearch = o->linesearch != 0; }
   // _typed_solve_gmres! serves GMRES, FGMRES and FOM (c_stores.jl:376-398)
   if (h->solver == S_GMRES || h->solver == S_FGMRES || h->solver == S_FOM) {
@@ -195,6 +197,9 @@ int do_solve(Handle* h, KrylovMatvec fA, KrylovMatvec fM, KrylovMatvec fN, const
     case S_FOM: fom_solve<T>(*ws, A, bd, M, N, so); break;
     case S_FGMRES: fgmres_solve<T>(*ws, A, bd, M, N, so); break;
     case S_CG_LANCZOS: cg_lanczos_solve<T>(*ws, A, bd, M, so); break;
+    case S_CR: cr_solve<T>(*ws, A, bd, M, so); break;
+    case S_DQGMRES: dqgmres_solve<T>(*ws, A, bd, M, N, so); break;
+    case S_DIOM: diom_solve<T>(*ws, A, bd, M, N, so); break;
     case S_CGS: {
       const T* cd = stage_in<T>(h, ws, c, ws->cbuf);
       cgs_solve<T>(*ws, A, bd, cd, M, N, so);
@@ -246,6 +251,9 @@ template <class T> void* vec_by_name(Workspace<T>* ws, const char* nm) {
       {"r1", ws->r1}, {"r2", ws->r2}, {"w1", ws->w1}, {"w2", ws->w2}, {"y", ws->y}, {"w", ws->w}, {"q", ws->q},
       {"u", ws->u}, {"ts", ws->ts}, {"vw", ws->vw}, {"Mv", ws->Mv}, {"Mv_prev", ws->Mv_prev}, {"Mv_next", ws->Mv_next}};
   for (auto& e : tab) if (!strcmp(e.n, nm)) return e.p;
+  if (nm[0] == 'P' && nm[1]) { int i = atoi(nm + 1); if (i >= 1 && i <= (int)ws->Z.size()) return ws->Z[i - 1]; return nullptr; }
+  if (!strcmp(nm, "Ar")) return ws->Ap;
+  if (!strcmp(nm, "Mq")) return ws->z;
   if (nm[0] == 'Z') { int i = atoi(nm + 1); if (i >= 1 && i <= (int)ws->Z.size()) return ws->Z[i - 1]; return nullptr; }
   if (nm[0] == 'V') { int i = atoi(nm + 1); if (i >= 1 && i <= (int)ws->V.size()) return ws->V[i - 1]; }
   return nullptr;
@@ -549,7 +557,7 @@ int krylov_b200_set_preconditioner_diag(void* ws, int which, const void* d, int 
 KrylovB200Options krylov_b200_default_options(void) {
   KrylovB200Options o;
   memset(&o, 0, sizeof(o));
-  o.etol = NAN; o.conlim = NAN; o.fused = 1;
+  o.etol = NAN; o.conlim = NAN; o.fused = 1; o.cr_gamma = NAN;
   return o;
 }
 

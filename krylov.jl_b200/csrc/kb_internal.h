@@ -131,6 +131,7 @@ struct SolveOpts {
   bool restart = false;             // GMRES, FOM, FGMRES
   bool reorthogonalization = false; // GMRES, FOM, FGMRES
   bool check_curvature = false;     // CG-Lanczos
+  double cr_gamma = -1;             // CR: kwarg γ (<0 => sqrt(eps(T)))
   bool ldiv = false;
   int (*callback)(void* ws, void* user) = nullptr;   // returns nonzero => user-requested exit
   void* callback_user = nullptr;
@@ -151,7 +152,8 @@ struct Stats {
 };
 
 // values of KrylovSolverType (interfaces/include/krylov.h:48-83); cg_lanczos has no slot in the reference's C enum
-enum SolverKind { S_CG = 0, S_MINRES = 3, S_FOM = 7, S_GMRES = 8, S_FGMRES = 9, S_BICGSTAB = 10, S_CGS = 11, S_CG_LANCZOS = 100 };
+enum SolverKind { S_CG = 0, S_CR = 1, S_MINRES = 3, S_DIOM = 5, S_DQGMRES = 6, S_FOM = 7, S_GMRES = 8, S_FGMRES = 9, S_BICGSTAB = 10,
+                  S_CGS = 11, S_CG_LANCZOS = 100 };
 
 // One workspace per (solver, dtype): owns every device vector of the solver
 // (src/krylov_workspaces.jl; SURVEY.md appendix B for fields and aliasing).
@@ -172,7 +174,7 @@ struct Workspace {
   T *u = nullptr, *ts = nullptr, *vw = nullptr;                                       // CGS (+ r, p, q, yz)
   T *Mv = nullptr, *Mv_prev = nullptr, *Mv_next = nullptr;                            // CG-Lanczos (+ p, vv)
   std::vector<T*> V;
-  std::vector<T*> Z;                   // FGMRES: Z[k] = N_k V[k]
+  std::vector<T*> Z;                   // FGMRES: Z[k] = N_k V[k];  DQGMRES / DIOM: the direction stack P
   std::vector<T> c, sgiv, zg, R;       // GMRES host-side Givens data
   std::vector<T> err_vec;              // MINRES window
   int memory = 20, window = 5;
@@ -223,6 +225,9 @@ template <class T> void cgs_solve(Workspace<T>& ws, const LinOp<T>& A, const T* 
 template <class T> void cg_lanczos_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const SolveOpts& o);
 template <class T> void fom_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const LinOp<T>& N, const SolveOpts& o);
 template <class T> void fgmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const LinOp<T>& N, const SolveOpts& o);
+template <class T> void dqgmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const LinOp<T>& N, const SolveOpts& o);
+template <class T> void diom_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const LinOp<T>& N, const SolveOpts& o);
+template <class T> void cr_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const SolveOpts& o);
 
 // Fused CG (cg_fused.cu).  Returns false if the configuration is not eligible
 // (caller falls back to the generic primitive path, still on the GPU).

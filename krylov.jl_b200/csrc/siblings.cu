@@ -426,11 +426,401 @@ void fgmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T
   arnoldi_family_solve<T, true>(ws, A, b, M, N, o);
 }
 
+// ---------------------------------------------------------------------------
+// dqgmres! (src/dqgmres.jl:121-335) and diom! (src/diom.jl:121-332): the truncated
+// (incomplete orthogonalization) variants; circular stacks V, P of `memory` vectors.
+// One driver: QR by Givens rotations (DQGMRES) or LU without pivoting (DIOM) of the
+// band Hessenberg matrix, kept on the host.  Indices are 1-based like the reference.
+//   workspace fields: t (ws.t), z (ws.yz), w (ws.vw), V, P (ws.Z), c, s / L (ws.sgiv), H (ws.R)
+// ---------------------------------------------------------------------------
+template <class T, bool QR>
+static void truncated_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const LinOp<T>& N, const SolveOpts& o) {
+  const double start_time = now_seconds();
+  Ctx& cx = ws.ctx;
+  const int n = ws.n;
+  const bool history = o.history, ldiv = o.ldiv, reorth = o.reorthogonalization;
+  if (o.verbose > 0) printf("%s: system of size %d\n", QR ? "DQGMRES" : "DIOM", n);
+  const bool MisI = M.is_identity(), NisI = N.is_identity();
+  allocate_if(!MisI, ws, ws.vw);
+  allocate_if(!NisI, ws, ws.yz);
+  T *dx = ws.dx, *x = ws.x, *t = ws.t;
+  std::vector<T*>&P = ws.Z, &V = ws.V;
+  std::vector<T>&c = ws.c, &s = ws.sgiv, &H = ws.R;
+  std::vector<T>& L = ws.sgiv;
+  Stats& stats = ws.stats;
+  const bool warm_start = ws.warm_start;
+  stats.reset();
+  T* w = MisI ? t : ws.vw;
+  T* r0 = MisI ? t : ws.vw;
+
+  k_fill<T>(cx, n, x, T(0));
+  if (warm_start) { op_apply(cx, A, dx, t); k_axpby<T>(cx, n, T(1), b, T(-1), t); }
+  else k_copy<T>(cx, n, t, b);
+  if (!MisI) op_apply(cx, M, t, r0, ldiv);
+  T rNorm = k_nrm2<T>(cx, n, r0);
+  if (history) stats.residuals.push_back(rNorm);
+  if (rNorm == 0) {
+    stats.niter = 0; stats.solved = true; stats.inconsistent = false;
+    stats.timer = now_seconds() - start_time;
+    stats.status = "x is a zero-residual solution";
+    if (warm_start) k_axpy<T>(cx, n, T(1), dx, x);
+    ws.warm_start = false;
+    cx.sync();
+    return;
+  }
+  int iter = 0;
+  const int itmax = default_itmax(ws, o.itmax);
+  const T eps_tol = tol_of<T>(o.atol) + tol_of<T>(o.rtol) * rNorm;
+  if (o.verbose > 0) printf("%5s  %7s  %5s\n", "k", "‖rₖ‖", "timer");
+  if (kdisplay(iter, o.verbose)) printf("%5d  %7.1e  %.2fs\n", iter, (double)rNorm, now_seconds() - start_time);
+  const int mem = (int)V.size();
+  for (int i = 0; i < mem; i++) k_fill<T>(cx, n, V[i], T(0));
+  for (size_t i = 0; i < P.size(); i++) k_fill<T>(cx, n, P[i], T(0));
+  std::fill(H.begin(), H.end(), T(0));
+  std::fill(s.begin(), s.end(), T(0));          // DQGMRES sines / DIOM pivots L
+  if (QR) std::fill(c.begin(), c.end(), T(0));
+  T gamma_k = rNorm;                            // DQGMRES: last component of g_k;  DIOM: xi
+  k_divcopy<T>(cx, n, V[0], r0, rNorm);
+  bool solved = rNorm <= eps_tol, tired = iter >= itmax, user_exit = false, overtimed = false;
+  std::string status = "unknown";
+
+  while (!(solved || tired || user_exit || overtimed)) {
+    iter = iter + 1;
+    const int pos = (iter - 1) % mem + 1, next_pos = iter % mem + 1;
+    T* z = NisI ? V[pos - 1] : ws.yz;
+    if (!NisI) op_apply(cx, N, V[pos - 1], z, ldiv);
+    op_apply(cx, A, z, t);
+    if (!MisI) op_apply(cx, M, t, w, ldiv);
+    const int lo = std::max(1, iter - mem + 1);
+    for (int i = lo; i <= iter; i++) {          // incomplete orthogonalization
+      const int ipos = (i - 1) % mem + 1, diag = iter - i + 1;
+      H[diag - 1] = k_dot<T>(cx, n, w, V[ipos - 1]);
+      k_axpy<T>(cx, n, -H[diag - 1], V[ipos - 1], w);
+    }
+    if (reorth) {
+      for (int i = lo; i <= iter; i++) {
+        const int ipos = (i - 1) % mem + 1, diag = iter - i + 1;
+        const T Htmp = k_dot<T>(cx, n, w, V[ipos - 1]);
+        H[diag - 1] += Htmp;
+        k_axpy<T>(cx, n, -Htmp, V[ipos - 1], w);
+      }
+    }
+    const T Haux = k_nrm2<T>(cx, n, w);
+    if (Haux != 0) k_divcopy<T>(cx, n, V[next_pos - 1], w, Haux);
+    int ppos;                                   // position of p_k in the circular stack P
+    T step;                                     // x += step * p_k
+    if (QR) {                                   // dqgmres.jl:268-289
+      if (iter >= mem + 2) H[mem] = T(0);
+      const int lo2 = std::max(1, iter - mem);
+      for (int i = lo2; i <= iter - 1; i++) {
+        const int irot = (i - 1) % mem + 1, diag = iter - i, next_diag = diag + 1;
+        const T Htmp = c[irot - 1] * H[next_diag - 1] + s[irot - 1] * H[diag - 1];
+        H[diag - 1] = s[irot - 1] * H[next_diag - 1] - c[irot - 1] * H[diag - 1];
+        H[next_diag - 1] = Htmp;
+      }
+      sym_givens<T>(H[0], Haux, &c[pos - 1], &s[pos - 1], &H[0]);
+      const T gamma_next = s[pos - 1] * gamma_k;
+      gamma_k = c[pos - 1] * gamma_k;
+      ppos = pos;
+      for (int i = lo2; i <= iter - 1; i++) {
+        const int ipos = (i - 1) % mem + 1, diag = iter - i + 1;
+        if (ipos == ppos) k_scal<T>(cx, n, -H[diag - 1], P[ppos - 1]);
+        else k_axpy<T>(cx, n, -H[diag - 1], P[ipos - 1], P[ppos - 1]);
+      }
+      step = gamma_k;
+      rNorm = std::fabs(gamma_next);
+      gamma_k = gamma_next;
+    } else {                                    // diom.jl:262-289
+      if (iter >= 2) {
+        for (int i = std::max(2, iter - mem + 2); i <= iter; i++) {
+          const int lpos = (i - 1) % (mem - 1) + 1, diag = iter - i + 1, next_diag = diag + 1;
+          H[diag - 1] = H[diag - 1] - L[lpos - 1] * H[next_diag - 1];
+          if (i == iter) gamma_k = -L[lpos - 1] * gamma_k;
+        }
+      }
+      const int next_lpos = iter % (mem - 1) + 1;
+      L[next_lpos - 1] = Haux / H[0];
+      ppos = (iter - 1) % (mem - 1) + 1;
+      for (int i = lo; i <= iter - 1; i++) {
+        const int ipos = (i - 1) % (mem - 1) + 1, diag = iter - i + 1;
+        if (ipos == ppos) k_scal<T>(cx, n, -H[diag - 1], P[ppos - 1]);
+        else k_axpy<T>(cx, n, -H[diag - 1], P[ipos - 1], P[ppos - 1]);
+      }
+      step = gamma_k;
+      rNorm = Haux * std::fabs(gamma_k / H[0]);
+    }
+    k_axpy<T>(cx, n, T(1), z, P[ppos - 1]);
+    k_scal<T>(cx, n, T(1) / H[0], P[ppos - 1]);   // kdiv!(n, P[pos], H[1])
+    k_axpy<T>(cx, n, step, P[ppos - 1], x);
+    if (history) stats.residuals.push_back(rNorm);
+    const bool resid_decrease_mach = (rNorm + T(1) <= T(1));
+    if (o.callback) { cx.sync(); stats.niter = iter; user_exit = o.callback(&ws, o.callback_user) != 0; }
+    solved = (rNorm <= eps_tol) || resid_decrease_mach;
+    tired = iter >= itmax;
+    overtimed = (now_seconds() - start_time) > o.timemax;
+    if (kdisplay(iter, o.verbose)) printf("%5d  %7.1e  %.2fs\n", iter, (double)rNorm, now_seconds() - start_time);
+  }
+  if (o.verbose > 0) printf("\n");
+  if (QR) {                                     // dqgmres.jl:319-322 assigns in this order (tired overrides solved)
+    if (solved) status = "solution good enough given atol and rtol";
+    if (tired) status = "maximum number of iterations exceeded";
+  } else {
+    if (tired) status = "maximum number of iterations exceeded";
+    if (solved) status = "solution good enough given atol and rtol";
+  }
+  if (user_exit) status = "user-requested exit";
+  if (overtimed) status = "time limit exceeded";
+  if (warm_start) k_axpy<T>(cx, n, T(1), dx, x);
+  ws.warm_start = false;
+  cx.sync();
+  stats.niter = iter; stats.solved = solved; stats.inconsistent = false;
+  stats.timer = now_seconds() - start_time;
+  stats.status = status;
+}
+
+template <class T>
+void dqgmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const LinOp<T>& N, const SolveOpts& o) {
+  truncated_solve<T, true>(ws, A, b, M, N, o);
+}
+template <class T>
+void diom_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const LinOp<T>& N, const SolveOpts& o) {
+  truncated_solve<T, false>(ws, A, b, M, N, o);
+}
+
+// ===========================================================================
+// cr!  (src/cr.jl:128-478), trust region and linesearch included
+//   workspace fields: r, p, q, Ar (ws.Ap), Mq (ws.z), npc_dir
+// ===========================================================================
+// to_boundary(n, x, d, z, radius; flip = false, xNorm2, dNorm2) with M = I (src/krylov_utils.jl:375-402)
+template <class T>
+static void cr_to_boundary(Ctx& c, int n, const T* x, const T* d, T radius, T xNorm2, T dNorm2, T* lo, T* hi) {
+  if (!(radius > 0)) throw std::runtime_error("radius must be positive");
+  const T rxd = k_dot<T>(c, n, x, d);
+  if (dNorm2 == T(0)) dNorm2 = k_dot<T>(c, n, d, d);
+  if (xNorm2 == T(0)) xNorm2 = k_dot<T>(c, n, x, x);
+  if (dNorm2 == T(0)) throw std::runtime_error("zero direction");
+  const T radius2 = radius * radius;
+  if (!(xNorm2 <= radius2)) throw std::runtime_error("outside of the trust region");
+  T s1, s2;
+  if (roots_quadratic<T>(dNorm2, 2 * rxd, xNorm2 - radius2, 1, &s1, &s2)) throw std::runtime_error("negative discriminant");
+  *hi = std::max(s1, s2); *lo = std::min(s1, s2);
+}
+
+template <class T>
+void cr_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M, const SolveOpts& o) {
+  const double start_time = now_seconds();
+  Ctx& c = ws.ctx;
+  const int n = ws.n;
+  const bool history = o.history, ldiv = o.ldiv, linesearch = o.linesearch;
+  const T radius = (T)o.radius;
+  const T gam = o.cr_gamma < 0 ? std::sqrt(eps_of<T>()) : (T)o.cr_gamma;
+  if (linesearch && radius > 0) throw std::runtime_error("'linesearch' set to 'true' but radius > 0");
+  if (o.verbose > 0) printf("CR: system of %d equations in %d variables\n", n, n);
+  if (ws.warm_start && linesearch) throw std::runtime_error("warm_start and linesearch cannot be used together");
+  const bool MisI = M.is_identity();
+  allocate_if(!MisI, ws, ws.z);
+  allocate_if(linesearch || radius > 0, ws, ws.npc_dir);
+  T *dx = ws.dx, *x = ws.x, *r = ws.r, *p = ws.p, *q = ws.q, *Ar = ws.Ap;
+  Stats& stats = ws.stats;
+  const bool warm_start = ws.warm_start;
+  stats.reset();
+  T* Mq = MisI ? q : ws.z;
+  T* npc_dir = ws.npc_dir;
+
+  k_fill<T>(c, n, x, T(0));
+  if (warm_start) { op_apply(c, A, dx, p); k_axpby<T>(c, n, T(1), b, T(-1), p); }
+  else k_copy<T>(c, n, p, b);
+  if (MisI) k_copy<T>(c, n, r, p); else op_apply(c, M, p, r, ldiv);
+  T rNorm = std::sqrt(k_dot<T>(c, n, r, p));                  // knorm_elliptic(n, r, p)
+  if (history) stats.residuals.push_back(rNorm);
+  if (rNorm == 0) {
+    stats.niter = 0; stats.solved = true; stats.inconsistent = false;
+    stats.timer = now_seconds() - start_time;
+    stats.status = "x is a zero-residual solution";
+    if (history) stats.Aresiduals.push_back(0);
+    if (warm_start) k_axpy<T>(c, n, T(1), dx, x);
+    ws.warm_start = false;
+    c.sync();
+    return;
+  }
+  op_apply(c, A, r, Ar);
+  T rho = k_dot<T>(c, n, r, Ar);
+  if (rho == 0) {
+    stats.niter = 0; stats.solved = true; stats.inconsistent = false;
+    stats.timer = now_seconds() - start_time;
+    stats.status = "b is a zero-curvature direction";
+    if (history) stats.Aresiduals.push_back(0);
+    ws.warm_start = false;
+    if (linesearch || radius > 0) {
+      k_copy<T>(c, n, x, p);
+      k_copy<T>(c, n, npc_dir, p);
+      stats.npcCount = 1; stats.indefinite = true;
+    }
+    c.sync();
+    return;
+  }
+  k_copy<T>(c, n, p, r);
+  k_copy<T>(c, n, q, Ar);
+  T mquad = 0;                                                // quadratic model (verbose only)
+  int iter = 0;
+  const int itmax = default_itmax(ws, o.itmax);
+  T rNorm2 = rNorm * rNorm, pNorm = rNorm, pNorm2 = rNorm2, pr = rNorm2, abspr = pr, pAp = rho, abspAp = std::fabs(pAp);
+  T xNorm = 0;
+  T ArNorm = k_nrm2<T>(c, n, Ar);
+  if (history) stats.Aresiduals.push_back(ArNorm);
+  const T eps_tol = tol_of<T>(o.atol) + tol_of<T>(o.rtol) * rNorm;
+  if (o.verbose > 0) printf("%5s  %8s  %8s  %8s  %5s\n", "k", "‖x‖", "‖r‖", "quad", "timer");
+  if (kdisplay(iter, o.verbose)) printf("%5d  %8.1e  %8.1e  %8.1e  %.2fs\n", iter, (double)xNorm, (double)rNorm, (double)mquad, now_seconds() - start_time);
+  bool descent = pr > 0, solved = rNorm <= eps_tol, tired = iter >= itmax, on_boundary = false, npcurv = false;
+  bool user_exit = false, overtimed = false;
+  std::string status = "unknown";
+  const T sqeps = std::sqrt(eps_of<T>());
+
+  while (!(solved || tired || user_exit || overtimed)) {
+    T alpha = 0;
+    if (linesearch) {
+      const bool p_curv = pAp <= gam * pNorm * pNorm, r_curv = rho <= gam * rNorm * rNorm;
+      if (p_curv || r_curv) {                                 // cr.jl:233-262
+        npcurv = true;
+        if (o.verbose > 0) printf("nonpositive curvature detected: pᴴAp = %8.1e and rᴴAr = %8.1e\n", (double)pAp, (double)rho);
+        stats.solved = true; stats.niter = iter; stats.inconsistent = false;
+        stats.timer = now_seconds() - start_time;
+        stats.status = "nonpositive curvature";
+        ws.warm_start = false;
+        stats.indefinite = true;
+        if (iter == 0) {
+          k_copy<T>(c, n, npc_dir, p);
+          k_copy<T>(c, n, x, p);
+          stats.npcCount = 1;
+        } else {
+          if (r_curv) { k_copy<T>(c, n, npc_dir, r); stats.npcCount += 1; }
+          if (p_curv) { stats.npcCount += 1; if (!r_curv) k_copy<T>(c, n, npc_dir, p); }
+        }
+        c.sync();
+        return;
+      }
+    } else if (pAp <= 0 && radius == 0) {
+      throw std::runtime_error("Indefinite system and no trust region");
+    }
+    if (!MisI) op_apply(c, M, q, Mq, ldiv);
+    if (radius > 0) {                                         // cr.jl:268-373
+      const T xNorm2 = xNorm * xNorm;
+      T t1, t2, tr, tlo;
+      cr_to_boundary<T>(c, n, x, p, radius, xNorm2, pNorm2, &t2, &t1);
+      cr_to_boundary<T>(c, n, x, r, radius, xNorm2, rNorm2, &tlo, &tr);
+      if (abspAp <= gam * pNorm * k_nrm2<T>(c, n, q)) {       // pᴴAp ≃ 0
+        npcurv = true; stats.indefinite = true; stats.npcCount = 1;
+        k_copy<T>(c, n, npc_dir, p);
+        if (abspr <= gam * pNorm * rNorm) {                   // pᴴr ≃ 0: p := r
+          p = r; q = Ar;
+          if (rho > 0) alpha = std::min(tr, rNorm2 / rho);
+          else { alpha = tr; if (iter > 0) { stats.npcCount = 2; k_copy<T>(c, n, npc_dir, r); } }
+        } else {
+          alpha = descent ? t1 : t2;
+          if (rho > 0) tr = std::min(tr, rNorm2 / rho);
+          const T Delta = -alpha * pr + tr * rNorm2 - tr * tr * rho / 2;
+          if (Delta > 0) { p = r; q = Ar; alpha = tr; }
+        }
+      } else if (pAp > 0 && rho > 0) {
+        alpha = rho / k_dot<T>(c, n, q, Mq);
+        if (alpha >= t1) { alpha = t1; on_boundary = true; }
+      } else if (pAp > 0 && rho < 0) {
+        npcurv = true; stats.indefinite = true; stats.npcCount = 1;
+        k_copy<T>(c, n, npc_dir, r);
+        alpha = descent ? std::min(t1, pr / pAp) : std::max(t2, pr / pAp);
+        const T Delta = -alpha * pr + tr * rNorm2 + (alpha * alpha * pAp - tr * tr * rho) / 2;
+        if (Delta > 0) { p = r; q = Ar; alpha = tr; }
+      } else if (pAp < 0 && rho > 0) {
+        npcurv = true; stats.indefinite = true; stats.npcCount = 1;
+        k_copy<T>(c, n, npc_dir, p);
+        alpha = descent ? t1 : t2;
+        tr = std::min(tr, rNorm2 / rho);
+        const T Delta = -alpha * pr + tr * rNorm2 + (alpha * alpha * pAp - tr * tr * rho) / 2;
+        if (Delta > 0) { p = r; q = Ar; alpha = tr; }
+      } else if (pAp < 0 && rho < 0) {
+        npcurv = true; stats.indefinite = true; stats.npcCount = 2;
+        k_copy<T>(c, n, npc_dir, r);
+        alpha = descent ? t1 : t2;
+        const T Delta = -alpha * pr + tr * rNorm2 + (alpha * alpha * pAp - tr * tr * rho) / 2;
+        if (Delta > 0) { p = r; q = Ar; alpha = tr; }
+      }
+      // (when the branches above rebind p := r, q := Ar, `Mq` keeps naming the ORIGINAL q array, as in the reference
+      //  where Mq was bound once at cr.jl:155; the rebinding always ends the solve in this iteration)
+    } else if (radius == 0) {
+      alpha = rho / k_dot<T>(c, n, q, Mq);
+    }
+    k_axpy<T>(c, n, alpha, p, x);
+    xNorm = k_nrm2<T>(c, n, x);
+    if (radius > 0 && std::fabs(xNorm - radius) <= sqeps * std::max(std::fabs(xNorm), std::fabs(radius))) on_boundary = true;   // xNorm ≈ radius
+    k_axpy<T>(c, n, -alpha, Mq, r);
+    if (MisI) { rNorm2 = k_dot<T>(c, n, r, r); rNorm = std::sqrt(rNorm2); }
+    else {
+      const T omega = std::sqrt(alpha) * std::sqrt(rho);
+      rNorm = std::sqrt(std::fabs(rNorm + omega)) * std::sqrt(std::fabs(rNorm - omega));
+      rNorm2 = rNorm * rNorm;
+    }
+    if (history) stats.residuals.push_back(rNorm);
+    op_apply(c, A, r, Ar);
+    ArNorm = k_nrm2<T>(c, n, Ar);
+    if (history) stats.Aresiduals.push_back(ArNorm);
+    iter = iter + 1;
+    if (kdisplay(iter, o.verbose)) {
+      mquad = mquad - alpha * pr + alpha * alpha * pAp / 2;
+      printf("%5d  %8.1e  %8.1e  %8.1e  %.2fs\n", iter, (double)xNorm, (double)rNorm, (double)mquad, now_seconds() - start_time);
+    }
+    const bool resid_decrease_mach = (rNorm + T(1) <= T(1));
+    if (o.callback) { c.sync(); stats.niter = iter; user_exit = o.callback(&ws, o.callback_user) != 0; }
+    const bool resid_decrease = (rNorm <= eps_tol) || resid_decrease_mach;
+    solved = resid_decrease || npcurv || on_boundary;
+    tired = iter >= itmax;
+    overtimed = (now_seconds() - start_time) > o.timemax;
+    if (solved || tired || user_exit || overtimed) continue;
+    const T rhobar = rho;
+    rho = k_dot<T>(c, n, r, Ar);
+    const T beta = rho / rhobar;
+    k_axpby<T>(c, n, T(1), r, beta, p);
+    k_axpby<T>(c, n, T(1), Ar, beta, q);
+    pNorm2 = rNorm2 + 2 * beta * pr - 2 * beta * alpha * pAp + beta * beta * pNorm2;
+    if (pNorm2 > sqeps) pNorm = std::sqrt(pNorm2);
+    else if (std::fabs(pNorm2) <= sqeps) pNorm = T(0);
+    else {
+      stats.niter = iter; stats.solved = solved; stats.inconsistent = false;
+      stats.timer = now_seconds() - start_time;
+      stats.status = "solver encountered numerical issues";
+      if (warm_start) k_axpy<T>(c, n, T(1), dx, x);
+      ws.warm_start = false;
+      c.sync();
+      return;
+    }
+    pr = rNorm2 + beta * pr - beta * alpha * pAp;
+    abspr = std::fabs(pr);
+    pAp = rho + beta * beta * pAp;
+    abspAp = std::fabs(pAp);
+    descent = pr > 0;
+  }
+  if (o.verbose > 0) printf("\n");
+  if (tired) status = "maximum number of iterations exceeded";
+  if (solved) status = "solution good enough given atol and rtol";
+  if (user_exit) status = "user-requested exit";
+  if (overtimed) status = "time limit exceeded";
+  if (npcurv) status = "nonpositive curvature";
+  if (on_boundary) status = "on trust-region boundary";
+  if (warm_start) k_axpy<T>(c, n, T(1), dx, x);
+  ws.warm_start = false;
+  c.sync();
+  stats.niter = iter; stats.solved = solved; stats.inconsistent = false;
+  stats.timer = now_seconds() - start_time;
+  stats.status = status;
+}
+
 #define INST(T)                                                                                                          \
   template void cgs_solve<T>(Workspace<T>&, const LinOp<T>&, const T*, const T*, const LinOp<T>&, const LinOp<T>&, const SolveOpts&); \
   template void cg_lanczos_solve<T>(Workspace<T>&, const LinOp<T>&, const T*, const LinOp<T>&, const SolveOpts&);        \
   template void fom_solve<T>(Workspace<T>&, const LinOp<T>&, const T*, const LinOp<T>&, const LinOp<T>&, const SolveOpts&); \
-  template void fgmres_solve<T>(Workspace<T>&, const LinOp<T>&, const T*, const LinOp<T>&, const LinOp<T>&, const SolveOpts&);
+  template void fgmres_solve<T>(Workspace<T>&, const LinOp<T>&, const T*, const LinOp<T>&, const LinOp<T>&, const SolveOpts&); \
+  template void dqgmres_solve<T>(Workspace<T>&, const LinOp<T>&, const T*, const LinOp<T>&, const LinOp<T>&, const SolveOpts&); \
+  template void diom_solve<T>(Workspace<T>&, const LinOp<T>&, const T*, const LinOp<T>&, const LinOp<T>&, const SolveOpts&); \
+  template void cr_solve<T>(Workspace<T>&, const LinOp<T>&, const T*, const LinOp<T>&, const SolveOpts&);
 INST(double)
 INST(float)
 #undef INST

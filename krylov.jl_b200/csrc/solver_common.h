@@ -38,4 +38,37 @@ template <class T> static inline void sym_givens(T a, T b, T* c, T* s, T* rho) {
   }
 }
 
+// roots_quadratic (src/krylov_utils.jl:110-152); returns nonzero where the reference raises.
+template <class T> static inline int roots_quadratic(T q2, T q1, T q0, int nitref, T* r1, T* r2) {
+  T root1, root2;
+  if (q2 == T(0)) {
+    T root;
+    if (q1 == T(0)) { if (q0 != T(0)) return 1; root = T(0); }
+    else root = -q0 / q1;
+    *r1 = root; *r2 = root;
+    return 0;
+  }
+  const T rhs = std::sqrt(eps_of<T>()) * q1 * q1;
+  if (std::fabs(q0 * q2) > rhs) {
+    const T rho = q1 * q1 - 4 * q2 * q0;
+    if (rho < 0) return 1;
+    const T d = -(q1 + std::copysign(std::sqrt(rho), q1)) / 2;
+    root1 = d / q2; root2 = q0 / d;
+  } else {
+    root1 = -q1 / q2; root2 = T(0);
+  }
+  for (int it = 0; it < nitref; it++) {
+    const T q = (q2 * root1 + q1) * root1 + q0, dq = 2 * q2 * root1 + q1;
+    if (dq == T(0)) continue;
+    root1 = root1 - q / dq;
+  }
+  for (int it = 0; it < nitref; it++) {
+    const T q = (q2 * root2 + q1) * root2 + q0, dq = 2 * q2 * root2 + q1;
+    if (dq == T(0)) continue;
+    root2 = root2 - q / dq;
+  }
+  *r1 = root1; *r2 = root2;
+  return 0;
+}
+
 }  // namespace kb

@@ -45,6 +45,21 @@ template <class T> Workspace<T>* ws_create(SolverKind kind, int m, int n, int me
         break;
       }
       case S_CGS: ws->r = A(); ws->u = A(); ws->p = A(); ws->q = A(); ws->ts = A(); break;          // CgsWorkspace :1527-1545
+      case S_CR: ws->r = A(); ws->p = A(); ws->q = A(); ws->Ap = A(); break;                        // CrWorkspace :343-360 (Ar == Ap)
+      case S_DQGMRES: case S_DIOM: {                // DqgmresWorkspace :832-852, DiomWorkspace :914-933
+        ws->t = A();
+        int mem = memory > 0 ? memory : 20;
+        if (mem > m) mem = m;
+        if (kind == S_DIOM && mem < 2) throw std::runtime_error("diom needs memory >= 2");
+        ws->memory = mem;
+        const int np_ = kind == S_DIOM ? mem - 1 : mem;
+        for (int i = 0; i < mem; i++) ws->V.push_back(A());
+        for (int i = 0; i < np_; i++) ws->Z.push_back(A());                       // P
+        ws->c.assign(mem, T(0));
+        ws->sgiv.assign(kind == S_DIOM ? mem - 1 : mem, T(0));                    // s / L
+        ws->R.assign(kind == S_DIOM ? mem : mem + 1, T(0));                       // H
+        break;
+      }
       case S_CG_LANCZOS: ws->Mv = A(); ws->Mv_prev = A(); ws->p = A(); ws->Mv_next = A(); break;    // CgLanczosWorkspace :575-591
       default: throw std::runtime_error("unsupported solver");
     }
@@ -225,39 +240,6 @@ void cg_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
   stats.niter = iter; stats.solved = solved; stats.inconsistent = inconsistent;
   stats.timer = now_seconds() - start_time;
   stats.status = status;
-}
-
-// roots_quadratic (src/krylov_utils.jl:110-152); returns nonzero where the reference raises.
-template <class T> static int roots_quadratic(T q2, T q1, T q0, int nitref, T* r1, T* r2) {
-  T root1, root2;
-  if (q2 == T(0)) {
-    T root;
-    if (q1 == T(0)) { if (q0 != T(0)) return 1; root = T(0); }
-    else root = -q0 / q1;
-    *r1 = root; *r2 = root;
-    return 0;
-  }
-  const T rhs = std::sqrt(eps_of<T>()) * q1 * q1;
-  if (std::fabs(q0 * q2) > rhs) {
-    const T rho = q1 * q1 - 4 * q2 * q0;
-    if (rho < 0) return 1;
-    const T d = -(q1 + std::copysign(std::sqrt(rho), q1)) / 2;
-    root1 = d / q2; root2 = q0 / d;
-  } else {
-    root1 = -q1 / q2; root2 = T(0);
-  }
-  for (int it = 0; it < nitref; it++) {
-    const T q = (q2 * root1 + q1) * root1 + q0, dq = 2 * q2 * root1 + q1;
-    if (dq == T(0)) continue;
-    root1 = root1 - q / dq;
-  }
-  for (int it = 0; it < nitref; it++) {
-    const T q = (q2 * root2 + q1) * root2 + q0, dq = 2 * q2 * root2 + q1;
-    if (dq == T(0)) continue;
-    root2 = root2 - q / dq;
-  }
-  *r1 = root1; *r2 = root2;
-  return 0;
 }
 
 // to_boundary (src/krylov_utils.jl:375-402)

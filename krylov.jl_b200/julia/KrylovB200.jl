@@ -114,7 +114,8 @@ LinearAlgebra.mul!(y::B200Vector, A::B200CSR, x::B200Vector) = kmul!(y, A, x)
 # ---- solver level: one C call per solve (fused kernels) ------------------------------------------------
 # The workspace keeps Krylov.jl's type (CgWorkspace{T,T,B200Vector{T}}) for its stats and public fields;
 # the device vectors of the fused solve live in a libkrylov_b200 workspace (KRYLOV_CUDA: device pointers).
-const SOLVER_ID = Dict(:cg => 0, :minres => 3, :gmres => 8, :bicgstab => 10)
+const SOLVER_ID = Dict(:cg => 0, :cr => 1, :minres => 3, :diom => 5, :dqgmres => 6, :fom => 7, :gmres => 8, :fgmres => 9,
+                       :bicgstab => 10, :cgs => 11, :cg_lanczos => 100)
 struct COpts   # KrylovOptions, interfaces/src/c_enums.jl:40-62
   atol::Cdouble; rtol::Cdouble; itmax::Cint; verbose::Cint; lambda::Cdouble; tau::Cdouble; nu::Cdouble
   timemax::Cdouble; radius::Cdouble; restart::Cint; reorthogonalization::Cint; linesearch::Cint
@@ -150,5 +151,14 @@ Krylov.cg!(ws::CgWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; 
 Krylov.minres!(ws::MinresWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:minres, ws, A, b; kw...)
 Krylov.gmres!(ws::GmresWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:gmres, ws, A, b; memory = length(ws.c), kw...)
 Krylov.bicgstab!(ws::BicgstabWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:bicgstab, ws, A, b; kw...)
+# sibling solvers served by the same library (SURVEY.md 8f-3); every other method keeps running through the k*
+# overloads above, one kernel per call
+Krylov.cr!(ws::CrWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:cr, ws, A, b; kw...)
+Krylov.cgs!(ws::CgsWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:cgs, ws, A, b; kw...)
+Krylov.cg_lanczos!(ws::CgLanczosWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:cg_lanczos, ws, A, b; kw...)
+Krylov.fom!(ws::FomWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:fom, ws, A, b; memory = length(ws.l), kw...)
+Krylov.fgmres!(ws::FgmresWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:fgmres, ws, A, b; memory = length(ws.c), kw...)
+Krylov.dqgmres!(ws::DqgmresWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:dqgmres, ws, A, b; memory = length(ws.V), kw...)
+Krylov.diom!(ws::DiomWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:diom, ws, A, b; memory = length(ws.V), kw...)
 
 end # module

@@ -35,7 +35,8 @@ __all__ = ["CgWorkspace", "GmresWorkspace", "BicgstabWorkspace", "MinresWorkspac
            "krylov_solve", "krylov_solve_", "solution", "statistics", "results", "issolved", "iteration_count",
            "elapsed_time", "Aprod_count", "warm_start_", "device_count", "B200Error",
            "FomWorkspace", "FgmresWorkspace", "CgsWorkspace", "CgLanczosWorkspace", "fom", "fom_", "fgmres", "fgmres_",
-           "cgs", "cgs_", "cg_lanczos", "cg_lanczos_", "BlockGmresWorkspace", "block_gmres", "block_gmres_", "CsrOperator"]
+           "cgs", "cgs_", "cg_lanczos", "cg_lanczos_", "CrWorkspace", "DiomWorkspace", "DqgmresWorkspace", "cr", "cr_", "diom",
+           "diom_", "dqgmres", "dqgmres_", "BlockGmresWorkspace", "block_gmres", "block_gmres_", "CsrOperator"]
 
 
 class B200Error(RuntimeError):
@@ -304,7 +305,7 @@ class KrylovWorkspace:
     def solve(self, A, b, *, c=None, M=None, N=None, atol=None, rtol=None, itmax=0, timemax=math.inf, verbose=0,
               history=False, callback=None, radius=0.0, linesearch=False, lambda_=0.0, etol=None, conlim=None,
               restart=False, reorthogonalization=False, ldiv=False, fused=True, batch=0, time_kernels=False,
-              check_curvature=False):
+              check_curvature=False, gamma=None):
         """solver!(ws, A, b; kwargs...)  -- kwargs as in cg.jl:100-111, gmres.jl:96-108,
         bicgstab.jl:105-116, minres.jl:138-151.  M / N: None (identity), a 1-D array
         (Diagonal preconditioner) or a host callable."""
@@ -321,6 +322,8 @@ class KrylovWorkspace:
         e.history, e.ldiv, e.fused, e.batch = int(history), int(ldiv), int(fused), int(batch)
         e.time_kernels = int(time_kernels)
         e.check_curvature = int(check_curvature)
+        if gamma is not None:
+            e.cr_gamma = float(gamma)
         if etol is not None:
             e.etol = float(etol)
         if conlim is not None:
@@ -482,6 +485,18 @@ class CgLanczosWorkspace(KrylovWorkspace):
     solver = "cg_lanczos"
 
 
+class CrWorkspace(KrylovWorkspace):
+    solver = "cr"
+
+
+class DiomWorkspace(KrylovWorkspace):
+    solver = "diom"
+
+
+class DqgmresWorkspace(KrylovWorkspace):
+    solver = "dqgmres"
+
+
 class BlockGmresWorkspace(KrylovWorkspace):
     """BlockGmresWorkspace(m, n, p, dtype; memory=5) (src/block_krylov_workspaces.jl:108-171): block_gmres! on
     n x p blocks of right-hand sides.  B, X0 and X are n x p arrays (any layout on the Python
@@ -640,7 +655,8 @@ def block_gmres_(ws: BlockGmresWorkspace, A, B, X0=None, **kw):
 
 
 _WS = {"cg": CgWorkspace, "minres": MinresWorkspace, "gmres": GmresWorkspace, "bicgstab": BicgstabWorkspace,
-       "fom": FomWorkspace, "fgmres": FgmresWorkspace, "cgs": CgsWorkspace, "cg_lanczos": CgLanczosWorkspace}
+       "fom": FomWorkspace, "fgmres": FgmresWorkspace, "cgs": CgsWorkspace, "cg_lanczos": CgLanczosWorkspace,
+       "cr": CrWorkspace, "diom": DiomWorkspace, "dqgmres": DqgmresWorkspace}
 
 
 def krylov_workspace(method: str, *args, **kw) -> KrylovWorkspace:
@@ -688,11 +704,13 @@ cg_, gmres_, bicgstab_, minres_ = (_make_inplace(s) for s in ("cg", "gmres", "bi
 cg, gmres, bicgstab, minres = (_make_outofplace(s) for s in ("cg", "gmres", "bicgstab", "minres"))
 fom_, fgmres_, cgs_, cg_lanczos_ = (_make_inplace(s) for s in ("fom", "fgmres", "cgs", "cg_lanczos"))
 fom, fgmres, cgs, cg_lanczos = (_make_outofplace(s) for s in ("fom", "fgmres", "cgs", "cg_lanczos"))
+cr_, diom_, dqgmres_ = (_make_inplace(s) for s in ("cr", "diom", "dqgmres"))
+cr, diom, dqgmres = (_make_outofplace(s) for s in ("cr", "diom", "dqgmres"))
 
 
 def krylov_solve(method: str, A, b, x0=None, **kw):
     return {"cg": cg, "gmres": gmres, "bicgstab": bicgstab, "minres": minres, "fom": fom, "fgmres": fgmres, "cgs": cgs,
-            "cg_lanczos": cg_lanczos}[method](A, b, x0, **kw)
+            "cg_lanczos": cg_lanczos, "cr": cr, "diom": diom, "dqgmres": dqgmres}[method](A, b, x0, **kw)
 
 
 # workspace_accessors.jl:140-152

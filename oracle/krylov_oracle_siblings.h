@@ -9,6 +9,9 @@
  *   cg_lanczos!  src/cg_lanczos.jl:110-264
  *   fom!         src/fom.jl:121-368
  *   fgmres!      src/fgmres.jl:128-388
+ *   dqgmres!     src/dqgmres.jl:121-335
+ *   diom!        src/diom.jl:121-332
+ *   cr!          src/cr.jl:128-478  (trust region and linesearch included)
  * Parity pinning: checked against the properties the reference's own tests
  * assert (test/test_cgs.jl, test_cg_lanczos.jl, test_fom.jl, test_fgmres.jl:
  * residual <= atol + rtol*||b||, stats.solved, status strings) in
@@ -492,6 +495,391 @@ done:
   for (int i = 0; i < zvlen; i++) free(Z[i]);
   free(V); free(Z); free(cc); free(ss); free(zz); free(R); free(w); free(qbuf); free(dx);
   return 0;
+}
+
+/* ========================== dqgmres!  (src/dqgmres.jl:121-335) ========================== */
+int SUF(oracle_dqgmres)(int n, const int *rowptr, const int *colind, const REAL *val,
+                        const REAL *b, const REAL *x0, const REAL *Mdiag, const REAL *Ndiag,
+                        const oracle_opts *o, REAL *x, REAL *residuals, oracle_stats *st) {
+  SUF(csr) A = {n, rowptr, colind, val};
+  memset(st, 0, sizeof(*st));
+  set_status(st, "unknown");
+  int history = o->history, ldiv = o->ldiv, warm_start = (x0 != NULL), reorth = o->reorthogonalization;
+  int MisI = (Mdiag == NULL), NisI = (Ndiag == NULL);
+  REAL atol = SUF(tol)(o->atol), rtol = SUF(tol)(o->rtol);
+  int itmax = o->itmax;
+  int mem = o->memory == 0 ? 20 : o->memory;
+  if (mem > n) mem = n;                                           /* krylov_workspaces.jl:834 */
+  size_t nb = sizeof(REAL) * (size_t)n;
+  REAL *t = malloc(nb), *wbuf = MisI ? NULL : malloc(nb), *zbuf = NisI ? NULL : malloc(nb);
+  REAL **P = malloc(sizeof(REAL *) * mem), **V = malloc(sizeof(REAL *) * mem);
+  for (int i = 0; i < mem; i++) { P[i] = malloc(nb); V[i] = malloc(nb); }
+  REAL *c = calloc(mem, sizeof(REAL)), *s = calloc(mem, sizeof(REAL)), *H = calloc(mem + 1, sizeof(REAL));
+  REAL *w = MisI ? t : wbuf, *r0 = MisI ? t : wbuf;
+
+  SUF(kfill)(n, x, 0);
+  if (warm_start) { SUF(spmv)(&A, x0, t); SUF(kaxpby)(n, 1, b, -1, t); }
+  else SUF(kcopy)(n, t, b);
+  if (!MisI) SUF(diagmul)(n, r0, Mdiag, t, ldiv);
+  REAL rNorm = SUF(knorm)(n, r0);
+  if (history) PUSH(residuals, st->nres, rNorm);
+  if (rNorm == 0) {
+    st->niter = 0; st->solved = 1; st->inconsistent = 0;
+    set_status(st, "x is a zero-residual solution");
+    if (warm_start) SUF(kaxpy)(n, 1, x0, x);
+    goto done;
+  }
+  int iter = 0;
+  if (itmax == 0) itmax = 2 * n;
+  REAL eps_ = atol + rtol * rNorm;
+  for (int i = 0; i < mem; i++) { SUF(kfill)(n, V[i], 0); SUF(kfill)(n, P[i], 0); }
+  REAL gamma_k = rNorm;
+  SUF(kdivcopy)(n, V[0], r0, rNorm);
+  int solved = rNorm <= eps_, tired = iter >= itmax;
+  while (!(solved || tired)) {
+    iter = iter + 1;
+    int pos = (iter - 1) % mem + 1, next_pos = iter % mem + 1;    /* 1-based like the reference */
+    REAL *z = NisI ? V[pos - 1] : zbuf;
+    if (!NisI) SUF(diagmul)(n, z, Ndiag, V[pos - 1], ldiv);
+    SUF(spmv)(&A, z, t);
+    if (!MisI) SUF(diagmul)(n, w, Mdiag, t, ldiv);
+    int lo = iter - mem + 1 > 1 ? iter - mem + 1 : 1;
+    for (int i = lo; i <= iter; i++) {                            /* incomplete orthogonalization */
+      int ipos = (i - 1) % mem + 1, diag = iter - i + 1;
+      H[diag - 1] = SUF(kdot)(n, w, V[ipos - 1]);
+      SUF(kaxpy)(n, -H[diag - 1], V[ipos - 1], w);
+    }
+    if (reorth) {
+      for (int i = lo; i <= iter; i++) {
+        int ipos = (i - 1) % mem + 1, diag = iter - i + 1;
+        REAL Htmp = SUF(kdot)(n, w, V[ipos - 1]);
+        H[diag - 1] += Htmp;
+        SUF(kaxpy)(n, -Htmp, V[ipos - 1], w);
+      }
+    }
+    REAL Haux = SUF(knorm)(n, w);
+    if (Haux != 0) SUF(kdivcopy)(n, V[next_pos - 1], w, Haux);
+    if (iter >= mem + 2) H[mem] = 0;                              /* H[mem+1] = 0 */
+    int lo2 = iter - mem > 1 ? iter - mem : 1;
+    for (int i = lo2; i <= iter - 1; i++) {                       /* previous rotations */
+      int irot = (i - 1) % mem + 1, diag = iter - i, next_diag = diag + 1;
+      REAL Htmp = c[irot - 1] * H[next_diag - 1] + s[irot - 1] * H[diag - 1];
+      H[diag - 1] = s[irot - 1] * H[next_diag - 1] - c[irot - 1] * H[diag - 1];
+      H[next_diag - 1] = Htmp;
+    }
+    SUF(oracle_sym_givens)(H[0], Haux, &c[pos - 1], &s[pos - 1], &H[0]);
+    REAL gamma_next = s[pos - 1] * gamma_k;
+    gamma_k = c[pos - 1] * gamma_k;
+    for (int i = lo2; i <= iter - 1; i++) {                       /* direction p_k */
+      int ipos = (i - 1) % mem + 1, diag = iter - i + 1;
+      if (ipos == pos) SUF(kscal)(n, -H[diag - 1], P[pos - 1]);
+      else SUF(kaxpy)(n, -H[diag - 1], P[ipos - 1], P[pos - 1]);
+    }
+    SUF(kaxpy)(n, 1, z, P[pos - 1]);
+    SUF(kdiv)(n, P[pos - 1], H[0]);
+    SUF(kaxpy)(n, gamma_k, P[pos - 1], x);
+    rNorm = FABS(gamma_next);
+    if (history) PUSH(residuals, st->nres, rNorm);
+    gamma_k = gamma_next;
+    int resid_decrease_mach = (rNorm + (REAL)1 <= (REAL)1);
+    solved = (rNorm <= eps_) || resid_decrease_mach;
+    tired = iter >= itmax;
+  }
+  if (solved) set_status(st, "solution good enough given atol and rtol");      /* dqgmres.jl:319-320: this order */
+  if (tired) set_status(st, "maximum number of iterations exceeded");
+  if (warm_start) SUF(kaxpy)(n, 1, x0, x);
+  st->niter = iter; st->solved = solved; st->inconsistent = 0;
+done:
+  for (int i = 0; i < mem; i++) { free(P[i]); free(V[i]); }
+  free(P); free(V); free(c); free(s); free(H); free(t); free(wbuf); free(zbuf);
+  return 0;
+}
+
+/* ============================ diom!  (src/diom.jl:121-332) ============================ */
+int SUF(oracle_diom)(int n, const int *rowptr, const int *colind, const REAL *val,
+                     const REAL *b, const REAL *x0, const REAL *Mdiag, const REAL *Ndiag,
+                     const oracle_opts *o, REAL *x, REAL *residuals, oracle_stats *st) {
+  SUF(csr) A = {n, rowptr, colind, val};
+  memset(st, 0, sizeof(*st));
+  set_status(st, "unknown");
+  int history = o->history, ldiv = o->ldiv, warm_start = (x0 != NULL), reorth = o->reorthogonalization;
+  int MisI = (Mdiag == NULL), NisI = (Ndiag == NULL);
+  REAL atol = SUF(tol)(o->atol), rtol = SUF(tol)(o->rtol);
+  int itmax = o->itmax;
+  int mem = o->memory == 0 ? 20 : o->memory;
+  if (mem > n) mem = n;                                           /* krylov_workspaces.jl:916 */
+  if (mem < 2) { st->error = 20; set_status(st, "memory must be at least 2"); return 20; }   /* mod(., mem-1) */
+  size_t nb = sizeof(REAL) * (size_t)n;
+  REAL *t = malloc(nb), *wbuf = MisI ? NULL : malloc(nb), *zbuf = NisI ? NULL : malloc(nb);
+  REAL **P = malloc(sizeof(REAL *) * (mem - 1)), **V = malloc(sizeof(REAL *) * mem);
+  for (int i = 0; i < mem - 1; i++) P[i] = malloc(nb);
+  for (int i = 0; i < mem; i++) V[i] = malloc(nb);
+  REAL *L = calloc(mem - 1, sizeof(REAL)), *H = calloc(mem, sizeof(REAL));
+  REAL *w = MisI ? t : wbuf, *r0 = MisI ? t : wbuf;
+
+  SUF(kfill)(n, x, 0);
+  if (warm_start) { SUF(spmv)(&A, x0, t); SUF(kaxpby)(n, 1, b, -1, t); }
+  else SUF(kcopy)(n, t, b);
+  if (!MisI) SUF(diagmul)(n, r0, Mdiag, t, ldiv);
+  REAL rNorm = SUF(knorm)(n, r0);
+  if (history) PUSH(residuals, st->nres, rNorm);
+  if (rNorm == 0) {
+    st->niter = 0; st->solved = 1; st->inconsistent = 0;
+    set_status(st, "x is a zero-residual solution");
+    if (warm_start) SUF(kaxpy)(n, 1, x0, x);
+    goto done;
+  }
+  int iter = 0;
+  if (itmax == 0) itmax = 2 * n;
+  REAL eps_ = atol + rtol * rNorm;
+  for (int i = 0; i < mem; i++) SUF(kfill)(n, V[i], 0);
+  for (int i = 0; i < mem - 1; i++) SUF(kfill)(n, P[i], 0);
+  REAL xi = rNorm;
+  SUF(kdivcopy)(n, V[0], r0, rNorm);
+  int solved = rNorm <= eps_, tired = iter >= itmax;
+  while (!(solved || tired)) {
+    iter = iter + 1;
+    int pos = (iter - 1) % mem + 1, next_pos = iter % mem + 1;
+    REAL *z = NisI ? V[pos - 1] : zbuf;
+    if (!NisI) SUF(diagmul)(n, z, Ndiag, V[pos - 1], ldiv);
+    SUF(spmv)(&A, z, t);
+    if (!MisI) SUF(diagmul)(n, w, Mdiag, t, ldiv);
+    int lo = iter - mem + 1 > 1 ? iter - mem + 1 : 1;
+    for (int i = lo; i <= iter; i++) {
+      int ipos = (i - 1) % mem + 1, diag = iter - i + 1;
+      H[diag - 1] = SUF(kdot)(n, w, V[ipos - 1]);
+      SUF(kaxpy)(n, -H[diag - 1], V[ipos - 1], w);
+    }
+    if (reorth) {
+      for (int i = lo; i <= iter; i++) {
+        int ipos = (i - 1) % mem + 1, diag = iter - i + 1;
+        REAL Htmp = SUF(kdot)(n, w, V[ipos - 1]);
+        H[diag - 1] += Htmp;
+        SUF(kaxpy)(n, -Htmp, V[ipos - 1], w);
+      }
+    }
+    REAL Haux = SUF(knorm)(n, w);
+    if (Haux != 0) SUF(kdivcopy)(n, V[next_pos - 1], w, Haux);
+    if (iter >= 2) {                                              /* LU of the band Hessenberg, diom.jl:262-272 */
+      int lo3 = iter - mem + 2 > 2 ? iter - mem + 2 : 2;
+      for (int i = lo3; i <= iter; i++) {
+        int lpos = (i - 1) % (mem - 1) + 1, diag = iter - i + 1, next_diag = diag + 1;
+        H[diag - 1] = H[diag - 1] - L[lpos - 1] * H[next_diag - 1];
+        if (i == iter) xi = -L[lpos - 1] * xi;
+      }
+    }
+    int next_lpos = iter % (mem - 1) + 1;
+    L[next_lpos - 1] = Haux / H[0];
+    int ppos = (iter - 1) % (mem - 1) + 1;
+    for (int i = lo; i <= iter - 1; i++) {
+      int ipos = (i - 1) % (mem - 1) + 1, diag = iter - i + 1;
+      if (ipos == ppos) SUF(kscal)(n, -H[diag - 1], P[ppos - 1]);
+      else SUF(kaxpy)(n, -H[diag - 1], P[ipos - 1], P[ppos - 1]);
+    }
+    SUF(kaxpy)(n, 1, z, P[ppos - 1]);
+    SUF(kdiv)(n, P[ppos - 1], H[0]);
+    SUF(kaxpy)(n, xi, P[ppos - 1], x);
+    rNorm = Haux * FABS(xi / H[0]);
+    if (history) PUSH(residuals, st->nres, rNorm);
+    int resid_decrease_mach = (rNorm + (REAL)1 <= (REAL)1);
+    solved = (rNorm <= eps_) || resid_decrease_mach;
+    tired = iter >= itmax;
+  }
+  if (tired) set_status(st, "maximum number of iterations exceeded");
+  if (solved) set_status(st, "solution good enough given atol and rtol");
+  if (warm_start) SUF(kaxpy)(n, 1, x0, x);
+  st->niter = iter; st->solved = solved; st->inconsistent = 0;
+done:
+  for (int i = 0; i < mem - 1; i++) free(P[i]);
+  for (int i = 0; i < mem; i++) free(V[i]);
+  free(P); free(V); free(L); free(H); free(t); free(wbuf); free(zbuf);
+  return 0;
+}
+
+/* ============================== cr!  (src/cr.jl:128-478) ============================== */
+/* gamma_in: NaN -> sqrt(eps(T)).  npc_dir: output (length n) when linesearch || radius > 0.
+ * Aresiduals receives ||A r|| like stats.Aresiduals.  st->error: 1 linesearch&&radius>0, 2 warm_start&&linesearch,
+ * 5 "Indefinite system and no trust region", 10+e to_boundary errors. */
+int SUF(oracle_cr)(int n, const int *rowptr, const int *colind, const REAL *val,
+                   const REAL *b, const REAL *x0, const REAL *Mdiag, double gamma_in, const oracle_opts *o,
+                   REAL *x, REAL *residuals, REAL *Aresiduals, REAL *npc_dir, oracle_stats *st) {
+  SUF(csr) A = {n, rowptr, colind, val};
+  memset(st, 0, sizeof(*st));
+  set_status(st, "unknown");
+  int history = o->history, ldiv = o->ldiv, warm_start = (x0 != NULL), linesearch = o->linesearch;
+  REAL radius = (REAL)o->radius;
+  REAL gam = isnan(gamma_in) ? SQRT(EPS) : (REAL)gamma_in;
+  int MisI = (Mdiag == NULL);
+  REAL atol = SUF(tol)(o->atol), rtol = SUF(tol)(o->rtol);
+  int itmax = o->itmax;
+  int rc = 0;
+  if (linesearch && radius > 0) { st->error = 1; return 1; }
+  if (warm_start && linesearch) { st->error = 2; return 2; }
+  size_t nb = sizeof(REAL) * (size_t)n;
+  REAL *r = malloc(nb), *pbuf = malloc(nb), *qbuf = malloc(nb), *Ar = malloc(nb), *Mqbuf = MisI ? NULL : malloc(nb);
+  REAL *p = pbuf, *q = qbuf;                                      /* rebound to r / Ar by the trust-region logic */
+  REAL *Mq = MisI ? q : Mqbuf;
+
+  SUF(kfill)(n, x, 0);
+  if (warm_start) { SUF(spmv)(&A, x0, p); SUF(kaxpby)(n, 1, b, -1, p); }
+  else SUF(kcopy)(n, p, b);
+  if (MisI) SUF(kcopy)(n, r, p); else SUF(diagmul)(n, r, Mdiag, p, ldiv);
+  REAL rNorm = SQRT(SUF(kdot)(n, r, p));                          /* knorm_elliptic(n, r, p): r !== p */
+  if (history) PUSH(residuals, st->nres, rNorm);
+  if (rNorm == 0) {
+    st->niter = 0; st->solved = 1; st->inconsistent = 0;
+    set_status(st, "x is a zero-residual solution");
+    if (history) PUSH(Aresiduals, st->nAres, 0);
+    if (warm_start) SUF(kaxpy)(n, 1, x0, x);
+    goto done;
+  }
+  SUF(spmv)(&A, r, Ar);
+  REAL rho = SUF(kdot)(n, r, Ar);
+  if (rho == 0) {
+    st->niter = 0; st->solved = 1; st->inconsistent = 0;
+    set_status(st, "b is a zero-curvature direction");
+    if (history) PUSH(Aresiduals, st->nAres, 0);
+    if (linesearch || radius > 0) {
+      SUF(kcopy)(n, x, p);
+      SUF(kcopy)(n, npc_dir, p);
+      st->npcCount = 1; st->indefinite = 1;
+    }
+    goto done;
+  }
+  SUF(kcopy)(n, p, r);
+  SUF(kcopy)(n, q, Ar);
+  int iter = 0;
+  if (itmax == 0) itmax = 2 * n;
+  REAL rNorm2 = rNorm * rNorm, pNorm = rNorm, pNorm2 = rNorm2, pr = rNorm2, abspr = pr, pAp = rho, abspAp = FABS(pAp);
+  REAL xNorm = 0;
+  REAL ArNorm = SUF(knorm)(n, Ar);
+  if (history) PUSH(Aresiduals, st->nAres, ArNorm);
+  REAL eps_ = atol + rtol * rNorm;
+  int descent = pr > 0, solved = rNorm <= eps_, tired = iter >= itmax, on_boundary = 0, npcurv = 0;
+  REAL sqeps = SQRT(EPS);
+
+  while (!(solved || tired)) {
+    REAL alpha = 0;
+    if (linesearch) {
+      int p_curv = pAp <= gam * pNorm * pNorm, r_curv = rho <= gam * rNorm * rNorm;
+      if (p_curv || r_curv) {                                     /* cr.jl:233-262 */
+        npcurv = 1;
+        st->solved = 1; st->niter = iter; st->inconsistent = 0;
+        set_status(st, "nonpositive curvature");
+        st->indefinite = 1;
+        if (iter == 0) {
+          SUF(kcopy)(n, npc_dir, p);
+          SUF(kcopy)(n, x, p);
+          st->npcCount = 1;
+        } else {
+          if (r_curv) { SUF(kcopy)(n, npc_dir, r); st->npcCount += 1; }
+          if (p_curv) { st->npcCount += 1; if (!r_curv) SUF(kcopy)(n, npc_dir, p); }
+        }
+        goto done;
+      }
+    } else if (pAp <= 0 && radius == 0) {
+      st->error = 5; rc = 5; goto done;
+    }
+    if (!MisI) SUF(diagmul)(n, Mq, Mdiag, q, ldiv);
+    if (radius > 0) {                                             /* cr.jl:268-373 */
+      REAL xNorm2 = xNorm * xNorm, s1, s2, t1, t2, tr;
+      int e = SUF(oracle_to_boundary)(n, x, p, Mq, radius, 0, xNorm2, pNorm2, NULL, 0, &s1, &s2);
+      if (e) { st->error = 10 + e; rc = st->error; goto done; }
+      t1 = s1 > s2 ? s1 : s2; t2 = s1 < s2 ? s1 : s2;
+      e = SUF(oracle_to_boundary)(n, x, r, Mq, radius, 0, xNorm2, rNorm2, NULL, 0, &s1, &s2);
+      if (e) { st->error = 10 + e; rc = st->error; goto done; }
+      tr = s1 > s2 ? s1 : s2;
+      if (abspAp <= gam * pNorm * SUF(knorm)(n, q)) {             /* p'Ap ~ 0 */
+        npcurv = 1; st->indefinite = 1; st->npcCount = 1;
+        SUF(kcopy)(n, npc_dir, p);
+        if (abspr <= gam * pNorm * rNorm) {                       /* p'r ~ 0: p := r */
+          p = r; q = Ar;
+          if (rho > 0) alpha = tr < rNorm2 / rho ? tr : rNorm2 / rho;
+          else { alpha = tr; if (iter > 0) { st->npcCount = 2; SUF(kcopy)(n, npc_dir, r); } }
+        } else {
+          alpha = descent ? t1 : t2;
+          if (rho > 0) tr = tr < rNorm2 / rho ? tr : rNorm2 / rho;
+          REAL Delta = -alpha * pr + tr * rNorm2 - tr * tr * rho / 2;
+          if (Delta > 0) { p = r; q = Ar; alpha = tr; }
+        }
+      } else if (pAp > 0 && rho > 0) {
+        alpha = rho / SUF(kdot)(n, q, Mq);
+        if (alpha >= t1) { alpha = t1; on_boundary = 1; }
+      } else if (pAp > 0 && rho < 0) {
+        npcurv = 1; st->indefinite = 1; st->npcCount = 1;
+        SUF(kcopy)(n, npc_dir, r);
+        alpha = descent ? (t1 < pr / pAp ? t1 : pr / pAp) : (t2 > pr / pAp ? t2 : pr / pAp);
+        REAL Delta = -alpha * pr + tr * rNorm2 + (alpha * alpha * pAp - tr * tr * rho) / 2;
+        if (Delta > 0) { p = r; q = Ar; alpha = tr; }
+      } else if (pAp < 0 && rho > 0) {
+        npcurv = 1; st->indefinite = 1; st->npcCount = 1;
+        SUF(kcopy)(n, npc_dir, p);
+        alpha = descent ? t1 : t2;
+        tr = tr < rNorm2 / rho ? tr : rNorm2 / rho;
+        REAL Delta = -alpha * pr + tr * rNorm2 + (alpha * alpha * pAp - tr * tr * rho) / 2;
+        if (Delta > 0) { p = r; q = Ar; alpha = tr; }
+      } else if (pAp < 0 && rho < 0) {
+        npcurv = 1; st->indefinite = 1; st->npcCount = 2;
+        SUF(kcopy)(n, npc_dir, r);
+        alpha = descent ? t1 : t2;
+        REAL Delta = -alpha * pr + tr * rNorm2 + (alpha * alpha * pAp - tr * tr * rho) / 2;
+        if (Delta > 0) { p = r; q = Ar; alpha = tr; }
+      }
+    } else if (radius == 0) {
+      alpha = rho / SUF(kdot)(n, q, Mq);
+    }
+    SUF(kaxpy)(n, alpha, p, x);
+    xNorm = SUF(knorm)(n, x);
+    if (radius > 0) {                                             /* xNorm ≈ radius > 0  (isapprox, rtol = sqrt(eps)) */
+      REAL mx = FABS(xNorm) > FABS(radius) ? FABS(xNorm) : FABS(radius);
+      if (FABS(xNorm - radius) <= sqeps * mx) on_boundary = 1;
+    }
+    SUF(kaxpy)(n, -alpha, Mq, r);
+    if (MisI) { rNorm2 = SUF(kdot)(n, r, r); rNorm = SQRT(rNorm2); }
+    else {
+      REAL omega = SQRT(alpha) * SQRT(rho);
+      rNorm = SQRT(FABS(rNorm + omega)) * SQRT(FABS(rNorm - omega));
+      rNorm2 = rNorm * rNorm;
+    }
+    if (history) PUSH(residuals, st->nres, rNorm);
+    SUF(spmv)(&A, r, Ar);
+    ArNorm = SUF(knorm)(n, Ar);
+    if (history) PUSH(Aresiduals, st->nAres, ArNorm);
+    iter = iter + 1;
+    int resid_decrease_mach = (rNorm + (REAL)1 <= (REAL)1);
+    int resid_decrease = (rNorm <= eps_) || resid_decrease_mach;
+    solved = resid_decrease || npcurv || on_boundary;
+    tired = iter >= itmax;
+    if (solved || tired) continue;
+    REAL rhobar = rho;
+    rho = SUF(kdot)(n, r, Ar);
+    REAL beta = rho / rhobar;
+    SUF(kaxpby)(n, 1, r, beta, p);
+    SUF(kaxpby)(n, 1, Ar, beta, q);
+    pNorm2 = rNorm2 + 2 * beta * pr - 2 * beta * alpha * pAp + beta * beta * pNorm2;
+    if (pNorm2 > sqeps) pNorm = SQRT(pNorm2);
+    else if (FABS(pNorm2) <= sqeps) pNorm = 0;
+    else {
+      st->niter = iter; st->solved = solved; st->inconsistent = 0;
+      set_status(st, "solver encountered numerical issues");
+      if (warm_start) SUF(kaxpy)(n, 1, x0, x);
+      goto done;
+    }
+    pr = rNorm2 + beta * pr - beta * alpha * pAp;
+    abspr = FABS(pr);
+    pAp = rho + beta * beta * pAp;
+    abspAp = FABS(pAp);
+    descent = pr > 0;
+  }
+  if (tired) set_status(st, "maximum number of iterations exceeded");
+  if (solved) set_status(st, "solution good enough given atol and rtol");
+  if (npcurv) set_status(st, "nonpositive curvature");
+  if (on_boundary) set_status(st, "on trust-region boundary");
+  if (warm_start) SUF(kaxpy)(n, 1, x0, x);
+  st->niter = iter; st->solved = solved; st->inconsistent = 0;
+done:
+  free(r); free(pbuf); free(qbuf); free(Ar); free(Mqbuf);
+  return rc;
 }
 
 #undef PUSH

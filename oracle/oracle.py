@@ -223,6 +223,40 @@ def fgmres(A, b, x0=None, M=None, N=None, dtype=np.float64, **kw):
     return _arnoldi_family("fgmres", A, b, x0, M, N, dtype, kw)
 
 
+def dqgmres(A, b, x0=None, M=None, N=None, dtype=np.float64, **kw):
+    """dqgmres! (src/dqgmres.jl:121-335)."""
+    return _arnoldi_family("dqgmres", A, b, x0, M, N, dtype, kw)
+
+
+def diom(A, b, x0=None, M=None, N=None, dtype=np.float64, **kw):
+    """diom! (src/diom.jl:121-332)."""
+    x, st = _arnoldi_family("diom", A, b, x0, M, N, dtype, kw)
+    if st["error"]:
+        raise ArithmeticError(st["status"])
+    return x, st
+
+
+def cr(A, b, x0=None, M=None, gamma=math.nan, dtype=np.float64, **kw):
+    """cr! (src/cr.jl:128-478).  Extra stats keys: Aresiduals, npc_dir."""
+    suf, _ = _suf(dtype)
+    n, rp, ci, va = _csr(A, dtype)
+    b, x0, M = _vec(b, dtype), _vec(x0, dtype), _vec(M, dtype)
+    o = _opts(n, kw, 1 << 22)
+    x = np.zeros(n, dtype)
+    res, ares = np.zeros(o.hist_cap, dtype), np.zeros(o.hist_cap, dtype)
+    npc = np.zeros(n, dtype)
+    st = Stats()
+    f = getattr(lib(), f"oracle_cr_{suf}")
+    f.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_double] + [C.c_void_p] * 6
+    rc = f(n, _p(rp), _p(ci), _p(va), _p(b), _p(x0), _p(M), float(gamma), C.cast(C.byref(o), C.c_void_p), _p(x), _p(res), _p(ares),
+           _p(npc), C.cast(C.byref(st), C.c_void_p))
+    if rc:
+        raise ArithmeticError({1: "'linesearch' set to 'true' but radius > 0", 2: "warm_start and linesearch cannot be used together",
+                               5: "Indefinite system and no trust region"}.get(rc, f"to_boundary error {rc - 10}"))
+    k = min(st.nAres, o.hist_cap)
+    return _result(st, x, res, dict(Aresiduals=ares[:k].copy(), npc_dir=npc))
+
+
 def block_gmres(A, B, X0=None, M=None, N=None, dtype=np.float64, **kw):
     """block_gmres! (src/block_gmres.jl:110-359).  B, X0, X: n x p (any layout; converted to column-major)."""
     suf, _ = _suf(dtype)

@@ -51,6 +51,12 @@ def build(name):
         A = _mat(P.kron_unsymmetric_csr(10)); return "fgmres", A, A @ np.ones(A.shape[0]), dict(memory=30, restart=True), f64
     if name == "cg_lanczos_divgrad16":
         A = _mat(P.div_grad_csr(16)); return "cg_lanczos", A, np.ones(A.shape[0]), {}, f64
+    if name == "dqgmres_kron10_mem8":
+        A = _mat(P.kron_unsymmetric_csr(10)); return "dqgmres", A, A @ np.ones(A.shape[0]), dict(memory=8), f64
+    if name == "diom_kron10_mem8":
+        A = _mat(P.kron_unsymmetric_csr(10)); return "diom", A, A @ np.ones(A.shape[0]), dict(memory=8), f64
+    if name == "cr_divgrad16":
+        A = _mat(P.div_grad_csr(16)); return "cr", A, np.ones(A.shape[0]), {}, f64
     raise KeyError(name)
 
 
@@ -58,7 +64,7 @@ NAMES = ["cg_divgrad16_default", "cg_divgrad32_bench", "cg_divgrad12_f32", "cg_r
          "gmres_kron10_restart30", "gmres_divgrad16_mem10_restart", "gmres_divgrad16_mem10_norestart",
          "gmres_kron8_reorth", "bicgstab_kron10", "bicgstab_random3000_f32", "minres_divgrad16", "minres_shift",
          "minres_indefinite", "cgs_kron10", "fom_kron10_mem30_restart", "fgmres_kron10_mem30_restart",
-         "cg_lanczos_divgrad16"]
+         "cg_lanczos_divgrad16", "dqgmres_kron10_mem8", "diom_kron10_mem8", "cr_divgrad16"]
 
 
 def run_oracle(O, name):

@@ -60,7 +60,7 @@ def test_unknown_solver_and_bad_handles():         # test_api.c:131-139, 175-182
     ws = C.c_void_p()
     assert L.krylov_workspace_create(999, 4, 4, 1, 0, None, C.byref(ws)) == -2 and not ws.value
     assert L.krylov_workspace_create(_lib.KRYLOV_CG, 4, 4, 2, 0, None, C.byref(ws)) == -2      # complex: outside the path
-    assert L.krylov_workspace_create(6, 4, 4, 1, 0, None, C.byref(ws)) == -2                   # DQGMRES: outside the path
+    assert L.krylov_workspace_create(2, 4, 4, 1, 0, None, C.byref(ws)) == -2                   # SYMMLQ: outside the path
     bogus = C.c_void_p(0x1234)
     assert L.krylov_workspace_free(bogus) == 1
     assert L.krylov_is_solved(bogus) == -1 and L.krylov_niter(bogus) == -1 and L.krylov_elapsed_time(bogus) == -1.0

@@ -158,21 +158,26 @@ def test_sibling_float32_and_callback(kb, O):
 
 
 def test_sibling_solvers_through_the_reference_c_abi(kb, O):
-    """krylov_workspace_create accepts the reference's enum values KRYLOV_FOM / KRYLOV_FGMRES / KRYLOV_CGS
-    (interfaces/include/krylov.h:56-60) and still answers -2 for what is not built."""
+    """krylov_workspace_create accepts the reference's enum values KRYLOV_CR / DIOM / DQGMRES / FOM / FGMRES / CGS
+    (interfaces/include/krylov.h:50-60) and still answers -2 for what is not built."""
     from krylov_b200 import _lib
     L = _lib.lib()
-    A, b = O.kron_unsymmetric(6)
-    A = sp.csr_matrix(A)
-    n = A.shape[0]
+    Ak, bk = O.kron_unsymmetric(6)
+    Al, bl = O.sparse_laplacian(6)                # cr! needs a symmetric operator
+    n = Ak.shape[0]
+    assert Al.shape[0] == n
+    cur = {}
 
     def matvec(xp, yp, _ud):
+        A = cur["A"]
         xv = np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), shape=(n,))
         yv = np.ctypeslib.as_array(C.cast(yp, C.POINTER(C.c_double)), shape=(n,))
         yv[:] = A @ xv
     cb = _lib.MATVEC(matvec)
     null = _lib.MATVEC()
-    for sid, name in ((7, "fom"), (9, "fgmres"), (11, "cgs")):
+    for sid, name in ((7, "fom"), (9, "fgmres"), (11, "cgs"), (1, "cr"), (5, "diom"), (6, "dqgmres")):
+        A, b = (sp.csr_matrix(Al), bl) if name == "cr" else (sp.csr_matrix(Ak), bk)
+        cur["A"] = A
         h = C.c_void_p()
         assert L.krylov_workspace_create(sid, n, n, 1, 0, None, C.byref(h)) == 0
         o = L.krylov_default_options()
@@ -184,4 +189,85 @@ def test_sibling_solvers_through_the_reference_c_abi(kb, O):
         assert np.linalg.norm(x - xo) <= 1e-6 * np.linalg.norm(xo)
         assert L.krylov_workspace_free(h) == 0
     h = C.c_void_p()
-    assert L.krylov_workspace_create(1, n, n, 1, 0, None, C.byref(h)) == -2       # KRYLOV_CR: not built
+    assert L.krylov_workspace_create(2, n, n, 1, 0, None, C.byref(h)) == -2       # KRYLOV_SYMMLQ: not built
+
+
+@pytest.mark.parametrize("name", ["dqgmres", "diom"])
+@pytest.mark.parametrize("kw", [dict(), dict(M=True), dict(N=True), dict(M=True, N=True), dict(reorthogonalization=True),
+                                dict(x0=True), dict(memory=40)])
+def test_dqgmres_diom_match_oracle(kb, O, name, kw):
+    _, (A, b) = _problems(O)
+    d = 1.0 / A.diagonal()
+    args = dict(reorthogonalization=kw.get("reorthogonalization", False))
+    if kw.get("M"):
+        args["M"] = d
+    if kw.get("N"):
+        args["N"] = 1.0 / np.sqrt(A.diagonal()) if kw.get("M") else d
+    x0 = 0.5 * np.ones(len(b)) if kw.get("x0") else None
+    mem = kw.get("memory", 6)                    # truncated: memory << niter
+    x, st = getattr(kb, name)(A, b, x0, memory=mem, history=True, **args)
+    xo, so = getattr(O, name)(A, b, x0=x0, memory=mem, **args)
+    # incomplete orthogonalization amplifies reduction-order noise more than the full methods do
+    _check(st, x, so, xo, tol=1e-5, xtol=1e-6)
+
+
+def test_dqgmres_status_order_and_diom_memory(kb, O):
+    _, (A, b) = _problems(O)
+    x, st = kb.dqgmres(A, b, memory=4, itmax=3, history=True)            # dqgmres.jl:319-320: "tired" overrides "solved"
+    xo, so = O.dqgmres(A, b, memory=4, itmax=3)
+    assert st.status == so["status"] == "maximum number of iterations exceeded" and st.niter == 3
+    with pytest.raises(kb.B200Error):
+        kb.DiomWorkspace(10, 10, np.float64, memory=1)                   # mod(., memory - 1) in the reference
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(M=True), dict(x0=True), dict(linesearch=True), dict(radius=10.0), dict(radius=30.0),
+                                dict(radius=0.5), dict(itmax=5)])
+def test_cr_matches_oracle(kb, O, kw):
+    (A, b), _ = _problems(O)
+    args = {k: v for k, v in kw.items() if k in ("linesearch", "radius", "itmax")}
+    if kw.get("M"):
+        # with M != I cr! tracks ||r||_M through rNorm^2 -= alpha rho (cr.jl:382-384), which stagnates near 1e-7 by
+        # cancellation: the reference's own test runs this case with atol = 1e-5, rtol = 0 (test_cr.jl)
+        args.update(M=1.0 / A.diagonal(), atol=1e-5, rtol=0.0)
+    x0 = 0.5 * np.ones(len(b)) if kw.get("x0") else None
+    x, st = kb.cr(A, b, x0, history=True, **args)
+    xo, so = O.cr(A, b, x0=x0, **args)
+    _check(st, x, so, xo)
+    assert np.allclose(st.Aresiduals, so["Aresiduals"], rtol=1e-6, atol=1e-9 * so["Aresiduals"][0])
+    assert st.indefinite == so["indefinite"] and st.npcCount == so["npcCount"]
+
+
+def test_cr_curvature_cases(kb, O):
+    """test/test_cr.jl: linesearch / trust-region exits on indefinite and zero-curvature systems."""
+    A, b = O.symmetric_indefinite(shift=10)
+    ws = kb.CrWorkspace(A, b)
+    kb.cr_(ws, A, b, linesearch=True)
+    st, npc = ws.stats, ws.npc_dir
+    assert st.status == "nonpositive curvature" and st.niter == 0 and st.solved and st.indefinite
+    assert npc @ (A @ npc) <= 0 and np.array_equal(ws.x, b)
+    A2 = sp.csr_matrix(np.array([[1.0, 0.0], [0.0, 0.0]]))
+    ws = kb.CrWorkspace(A2, np.ones(2))
+    kb.cr_(ws, A2, np.ones(2), linesearch=True)
+    xo, so = O.cr(A2, np.ones(2), linesearch=True)
+    assert ws.stats.npcCount == so["npcCount"] == 2 and ws.stats.status == so["status"]
+    A4 = sp.csr_matrix(np.array([[0.0, 1.0], [1.0, 0.0]]))
+    x, st = kb.cr(A4, np.array([1.0, 0.0]))
+    assert st.status == "b is a zero-curvature direction" and np.linalg.norm(x) == 0 and st.solved and st.niter == 0
+    # indefinite systems inside a trust region: the negative-curvature branches of cr.jl:268-373 (npcCount 0 and 2,
+    # exits after 1, 2 and 4 iterations), same branch and same point on the boundary as the oracle
+    for n, shift, radius in ((12, 0, 5.0), (12, 0, 50.0), (12, 3, 5.0), (20, 2, 50.0), (30, 1, 500.0), (12, 10, 5000.0)):
+        Ai, bi = O.symmetric_indefinite(n=n, shift=shift)
+        ws = kb.CrWorkspace(Ai, bi)
+        kb.cr_(ws, Ai, bi, radius=radius, history=True)
+        x, st = ws.x, ws.stats
+        xo, so = O.cr(Ai, bi, radius=radius)
+        assert st.status == so["status"] and st.niter == so["niter"] and st.npcCount == so["npcCount"], (n, shift, radius)
+        assert st.indefinite == so["indefinite"]
+        assert np.linalg.norm(x - xo) <= 1e-8 * max(1.0, np.linalg.norm(xo)), (n, shift, radius)
+        if so["npcCount"]:
+            assert np.allclose(ws.npc_dir, so["npc_dir"], rtol=1e-8, atol=1e-10)
+    Ai, bi = O.symmetric_indefinite(n=12)
+    with pytest.raises(kb.B200Error):
+        kb.cr(Ai, bi)                            # "Indefinite system and no trust region"
+    with pytest.raises(kb.B200Error):
+        kb.cr(A, b, linesearch=True, radius=1.0)

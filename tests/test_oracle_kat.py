@@ -372,3 +372,84 @@ def test_block_gmres_with_one_column_is_gmres(O):
     for kw in (dict(restart=True, memory=5), dict(reorthogonalization=True)):
         X, st = O.block_gmres(A, np.stack([b, b[::-1].copy(), np.cos(np.arange(len(b)))], axis=1), **kw)
         assert st["solved"]
+
+
+# ---- remaining siblings of SURVEY.md 8(f)-3: dqgmres!, diom!, cr! --------------------------------------------
+# test/test_dqgmres.jl, test/test_diom.jl
+@pytest.mark.parametrize("name", ["dqgmres", "diom"])
+def test_dqgmres_diom_reference_cases(O, name):
+    f = getattr(O, name)
+    tol = 1e-6
+    for gen in (O.symmetric_definite, O.symmetric_indefinite, O.sparse_laplacian):
+        A, b = gen()
+        x, st = f(A, b)
+        assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.kron_unsymmetric(8)
+    x, st = f(A, b)
+    assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.zero_rhs()
+    x, st = f(A, b)
+    assert np.linalg.norm(x) == 0 and st["status"] == "x is a zero-residual solution"
+    A, b, M = O.square_preconditioned()
+    x, st = f(A, b, M=M)
+    assert resid(A, x, b) <= tol and st["solved"]
+    x, st = f(A, b, N=M)
+    assert resid(A, x, b) <= tol and st["solved"]
+    A, b = O.cartesian_poisson(12, 12)
+    x, st = f(A, b, memory=100, reorthogonalization=True)
+    assert resid(A, x, b) <= tol and st["solved"]
+
+
+def test_truncated_methods_with_full_memory_are_the_full_methods(O):
+    """DQGMRES / DIOM with memory >= niter run the arithmetic of GMRES / FOM (same Arnoldi, same rotations / LU)."""
+    A, b = O.kron_unsymmetric(8)
+    for trunc, full in (("dqgmres", "gmres"), ("diom", "fom")):
+        xt, st = getattr(O, trunc)(A, b, memory=40)
+        xf, sf = getattr(O, full)(A, b, memory=40)
+        assert st["niter"] == sf["niter"] and np.allclose(st["residuals"], sf["residuals"], rtol=1e-12)
+        assert np.allclose(xt, xf, rtol=1e-9, atol=1e-12)
+
+
+# test/test_cr.jl
+def test_cr_reference_cases(O):
+    tol = 1e-6
+    A, b = O.symmetric_definite()
+    x, st = O.cr(A, b)
+    assert resid(A, x, b) <= tol and st["solved"] and not st["indefinite"]
+    radius = 0.75 * np.linalg.norm(x)
+    x, st = O.cr(A, b, radius=radius)
+    assert st["solved"] and abs(np.linalg.norm(x) - radius) <= tol * radius
+    A, _ = O.sparse_laplacian()
+    b = np.random.default_rng(0).standard_normal(A.shape[0])
+    x, st = O.cr(A, b, radius=10.0)                                   # ||x*|| > radius
+    assert abs(np.linalg.norm(x) - 10.0) <= tol * 10.0 and st["solved"]
+    x, st = O.cr(A, b, radius=30.0)                                   # ||x*|| < radius
+    assert resid(A, x, b) <= tol and st["solved"]
+    radius = 0.75 * np.linalg.norm(x)
+    x, st = O.cr(A, b, radius=radius)
+    assert st["solved"] and abs(radius - np.linalg.norm(x)) <= tol * radius
+    A, b = O.zero_rhs()
+    x, st = O.cr(A, b)
+    assert np.linalg.norm(x) == 0 and st["status"] == "x is a zero-residual solution"
+    A, b, M = O.square_preconditioned()
+    x, st = O.cr(A, b, M=M, atol=1e-5, rtol=0.0)
+    r = b - A @ x
+    assert np.sqrt(r @ (M * r)) / np.sqrt(b @ (M * b)) <= 10 * tol and st["solved"]
+    A, b = O.symmetric_indefinite(shift=10)                           # linesearch stops at the first call
+    x, st = O.cr(A, b, linesearch=True)
+    npc = st["npc_dir"]
+    assert st["status"] == "nonpositive curvature" and st["niter"] == 0 and st["solved"] and st["indefinite"]
+    assert npc @ (A @ npc) <= 0 and np.array_equal(x, b)
+    A2 = sp.csr_matrix(np.array([[1.0, 0.0], [0.0, 0.0]]))            # 2 negative-curvature directions
+    x, st = O.cr(A2, np.ones(2), linesearch=True)
+    assert st["npcCount"] == 2
+    A3 = sp.csr_matrix(-np.eye(2))                                    # only -p negative curvature
+    x, st = O.cr(A3, np.ones(2), linesearch=True)
+    assert st["status"] == "nonpositive curvature" and st["npcCount"] == 1
+    A4 = sp.csr_matrix(np.array([[0.0, 1.0], [1.0, 0.0]]))            # system_zero_quad: b'Ab == 0
+    x, st = O.cr(A4, np.array([1.0, 0.0]), linesearch=True)
+    assert st["niter"] == 0 and st["status"] == "b is a zero-curvature direction" and st["npc_dir"] @ (A4 @ st["npc_dir"]) == 0
+    x, st = O.cr(A4, np.array([1.0, 0.0]))
+    assert st["status"] == "b is a zero-curvature direction" and np.linalg.norm(x) == 0 and st["solved"] and st["niter"] == 0
+    with pytest.raises(ArithmeticError):
+        O.cr(A, b, linesearch=True, radius=1.0)
