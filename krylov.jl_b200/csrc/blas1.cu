@@ -7,11 +7,26 @@
 // Element updates use non-contracted mul/add so they agree bit-for-bit with
 // the reference's `y[i] += s*x[i]` (Julia does not fuse); reductions are
 // deterministic two-stage tree sums finalised by the last CTA on the device.
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "kb_internal.h"
 
 #include <chrono>
 
 namespace kb {
+
+void ensure_dyn_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  KB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({func, dev})) return;
+  KB_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert({func, dev});
+}
 
 double now_seconds() {
   using namespace std::chrono;

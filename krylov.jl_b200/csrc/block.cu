@@ -612,8 +612,7 @@ template <class T> static void k_transpose(Ctx& c, int rows, int cols, const T* 
   KB_CUDA(cudaGetLastError()); c.launches++;
 }
 template <class T, int P> static void launch_spmm_tma(Ctx& c, const Csr<T>& A, const T* X, T* Y) {
-  static bool attr = false;
-  if (!attr) { KB_CUDA(cudaFuncSetAttribute(spmm_tma_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+  ensure_dyn_smem((const void*)spmm_tma_kernel<T, P>, 220 * 1024);
   int occ = 0;
   KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_tma_kernel<T, P>, kTileThreads, A.smem_bytes));
   if (occ < 1) throw std::runtime_error("spmm_tma_kernel does not fit on an SM with the planned shared-memory ring");
@@ -679,8 +678,7 @@ template <class T> static void k_panel_nn_tn(BlockWorkspace<T>& ws, T alpha, con
   const int p = ws.p;
   if (launch_fast<T, true, true>(ws, alpha, In, S, beta, Out, Next, G)) return;
   const size_t smem = sizeof(T) * ((size_t)3 * kPanelTileElems + (size_t)p * p);
-  static bool attr = false;
-  if (!attr) { KB_CUDA(cudaFuncSetAttribute(panel_nn_tn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+  ensure_dyn_smem((const void*)panel_nn_tn_kernel<T>, 96 * 1024);
   panel_nn_tn_kernel<T><<<ws.grid, kBlock, smem, c.stream>>>(ws.n, p, alpha, In, S, beta, Out, Next, ws.part, c.tickets + 6, G);
   KB_CUDA(cudaGetLastError()); c.launches++;
 }

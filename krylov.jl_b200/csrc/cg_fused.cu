@@ -319,7 +319,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   // occupancy below the plan's CTAs/SM would otherwise run the tiles in 1.5 waves (measured: K1 2.2x slower).
   int k1_grid = A.grid;
   if (A.tma_ok) {
-    KB_CUDA(cudaFuncSetAttribute((const void*)k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ensure_dyn_smem((const void*)k1, 220 * 1024);
     int occ = 0;
     KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1, kTileThreads, A.smem_bytes));
     if (occ < 1) throw std::runtime_error("cg_k1_tma does not fit on an SM with the planned shared-memory ring");

@@ -97,6 +97,10 @@ __device__ __forceinline__ bool grid_sum_last(const T (&mine)[K], T* part, unsig
   return true;
 }
 
+// Opt a kernel into > 48 KB of dynamic shared memory, once per (kernel, device): the attribute belongs to the
+// device's context, so a process that drives several GPUs must set it on each (blas1.cu).
+void ensure_dyn_smem(const void* func, int bytes);
+
 inline int sm_count() {
   static int n = 0;
   if (!n) {

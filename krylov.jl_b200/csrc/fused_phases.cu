@@ -95,8 +95,7 @@ struct NoFin {
 template <class T, int K, class Epi, class Fin, class G>
 static void launch_spmv_epi_g(Ctx& c, const Csr<T>& A, G xg, Epi epi, Fin fin, int ticket) {
   if (A.tma_ok) {
-    static bool attr = false;
-    if (!attr) { KB_CUDA(cudaFuncSetAttribute(spmv_epi_tma<T, K, Epi, Fin, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+    ensure_dyn_smem((const void*)spmv_epi_tma<T, K, Epi, Fin, G>, 220 * 1024);
     int occ = 0;          // persistent grid = what is really co-resident (never more than one wave)
     KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_epi_tma<T, K, Epi, Fin, G>, kTileThreads, A.smem_bytes));
     if (occ < 1) throw std::runtime_error("spmv_epi_tma does not fit on an SM with the planned shared-memory ring");

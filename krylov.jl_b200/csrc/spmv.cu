@@ -211,11 +211,7 @@ static void spmv_launch_g(Ctx& c, const Csr<T>& A, G xg, T* y, int slot, int var
   const bool staged = variant == 2 || (variant == 0 && A.tma_ok);
   if (staged) {
     if (!A.tma_ok) throw std::runtime_error("TMA-staged SpMV requested but the tile plan does not fit shared memory");
-    static bool attr_set = false;                // one flag per <T, DOT, G> instantiation
-    if (!attr_set) {
-      KB_CUDA(cudaFuncSetAttribute(spmv_tma_kernel<T, DOT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr_set = true;
-    }
+    ensure_dyn_smem((const void*)spmv_tma_kernel<T, DOT, G>, 220 * 1024);
     int occ = 0;   // persistent grid = what is really co-resident (never more than one wave)
     KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_tma_kernel<T, DOT, G>, kTileThreads, A.smem_bytes));
     if (occ < 1) throw std::runtime_error("spmv_tma_kernel does not fit on an SM with the planned shared-memory ring");

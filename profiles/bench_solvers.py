@@ -18,7 +18,7 @@ from krylov_b200 import problems as P  # noqa: E402
 
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 small = "--small" in sys.argv
-which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["gmres", "bicgstab", "minres"]
+which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["gmres", "bicgstab", "minres", "siblings"]
 dev = torch.device("cuda", 0)
 
 
@@ -92,3 +92,30 @@ if "minres" in which:     # MINRES on the config-2 matrix
         ws.free()
     B = nnz * 12 + (n + 1) * 4 + 13 * n * 8
     report("minres", f"get_div_grad({N}) f64, 100 iterations/solve", B, res)
+
+if "siblings" in which:   # the sibling solvers on the same two matrices (it/s only; primitives + shared fused Arnoldi)
+    N = 64 if small else 215
+    rp, ci, va = P.kron_unsymmetric_csr(N, xp=torch, device=dev)
+    n = N ** 3
+    b = P.csr_matvec_ones(rp, ci, va)
+    for name, mem, kw in (("fom", 30, dict(restart=True, itmax=60)), ("fgmres", 30, dict(restart=True, itmax=60)),
+                          ("dqgmres", 20, dict(itmax=60)), ("diom", 20, dict(itmax=60)), ("cgs", 0, dict(itmax=50))):
+        ws = kb.krylov_workspace(name, n, n, np.float64, memory=mem, device="cuda")
+        ws.set_operator((rp, ci, va))
+        sec, niter, launches = timed(ws, b, 2, atol=0.0, rtol=0.0, **kw)
+        print(json.dumps(dict(solver=name, workload=f"kron_unsymmetric({N}) f64, {niter} iterations/solve" + (f", memory {mem}" if mem else ""),
+                              iterations_per_s=round(niter / sec, 1), us_per_iteration=round(1e6 * sec / niter, 1),
+                              launches_per_iteration=round(launches / niter, 2))), flush=True)
+        ws.free()
+    del rp, ci, va, b
+    torch.cuda.empty_cache()
+    rp, ci, va = P.div_grad_csr(N, xp=torch, device=dev)
+    b = torch.ones(n, dtype=torch.float64, device=dev)
+    for name in ("cr", "cg_lanczos"):
+        ws = kb.krylov_workspace(name, n, n, np.float64, device="cuda")
+        ws.set_operator((rp, ci, va))
+        sec, niter, launches = timed(ws, b, 2, atol=0.0, rtol=0.0, itmax=100)
+        print(json.dumps(dict(solver=name, workload=f"get_div_grad({N}) f64, {niter} iterations/solve",
+                              iterations_per_s=round(niter / sec, 1), us_per_iteration=round(1e6 * sec / niter, 1),
+                              launches_per_iteration=round(launches / niter, 2))), flush=True)
+        ws.free()
