@@ -251,7 +251,7 @@ __device__ __forceinline__ void nn_tile(int p, int ps, int rows, T alpha, const 
 #pragma unroll
       for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = add_rn(acc[a][b], mul_rn(in[a], sv[b]));
+        for (int b = 0; b < 4; b++) acc[a][b] = fma(in[a], sv[b], acc[a][b]);
     }
 #pragma unroll
     for (int a = 0; a < 4; a++) {
@@ -351,8 +351,9 @@ __global__ void __launch_bounds__(kBlock) panel_nn_kernel(int n, int p, T alpha,
 // No shared-memory tiles: TPR adjacent lanes share one panel row (1, 1, 2, 8, 16 for P = 2..32, chosen by the sweep
 // profiles/r1_sweep_block.txt), each owning a slab of
 // C = P/TPR columns of the updated row and a P x C slab (<= 64 accumulators) of the Gram-type product; operands stream from
-// global memory as 16-byte vectors (rows are contiguous), the TPR lanes of a row re-read it from L1.  ~190
-// instructions per row at P = 8 against 256 B of HBM traffic: bandwidth-bound, unlike the tiled generic kernels.
+// global memory as 16-byte vectors, every panel element is loaded by exactly one lane (its slab owner) and the TPR
+// lanes of a row exchange slabs by warp shuffle.  ~190 instructions per row at P = 8 against 256 B of HBM traffic:
+// bandwidth-bound, unlike the tiled generic kernels.
 //   UPDATE: Out[r][:] = beta Out[r][:] + alpha In[r][:] S         GRAM: G = Next^T Out  (Next == nullptr: Out^T Out)
 
 template <class T, int P, int TPR, bool UPDATE, bool GRAM>
@@ -385,34 +386,42 @@ __global__ void __launch_bounds__(kBlock, (P * P / TPR <= 32 ? 2 : 1)) panel_fas
     const bool valid = row < n;
     const size_t base = (size_t)(valid ? row : 0) * P;
     T outv[C];
+    const int lane0 = lane - slab;                 // first of the TPR lanes that share this row
     if (UPDATE) {
-      T a[C];
+      // each lane loads only ITS slab of the In row (the row is read once, coalesced); the other slabs arrive by
+      // shuffle from the lanes that hold them, in ascending column order (the order of the row-times-matrix sum)
+      T inv[C], a[C];
+#pragma unroll
+      for (int j = 0; j < C; j += 2) {
+        Vec2<T> v; v.x = T(0); v.y = T(0);
+        if (valid) v = ld2(In + base + c0 + j);
+        inv[j] = v.x; inv[j + 1] = v.y;
+      }
 #pragma unroll
       for (int j = 0; j < C; j++) a[j] = T(0);
-      if (valid) {
 #pragma unroll
-        for (int i = 0; i < P; i += 2) {
-          const Vec2<T> in = ld2(In + base + i);
+      for (int k = 0; k < TPR; k++) {
 #pragma unroll
-          for (int j = 0; j < C; j++) a[j] = add_rn(add_rn(a[j], mul_rn(in.x, Ss[i * P + c0 + j])), mul_rn(in.y, Ss[(i + 1) * P + c0 + j]));
+        for (int jj = 0; jj < C; jj++) {
+          const T in = TPR == 1 ? inv[jj] : __shfl_sync(0xffffffffu, inv[jj], lane0 + k);
+          const int i = k * C + jj;
+#pragma unroll
+          for (int j = 0; j < C; j++) a[j] = fma(in, Ss[i * P + c0 + j], a[j]);     // contracted: this is a GEMM, not a k* primitive
         }
-        if (beta != T(0)) {
+      }
+      if (beta != T(0)) {
 #pragma unroll
-          for (int j = 0; j < C; j += 2) {
-            const Vec2<T> o = ld2(Out + base + c0 + j);
-            outv[j] = add_rn(mul_rn(beta, o.x), mul_rn(alpha, a[j]));
-            outv[j + 1] = add_rn(mul_rn(beta, o.y), mul_rn(alpha, a[j + 1]));
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < C; j++) outv[j] = mul_rn(alpha, a[j]);
+        for (int j = 0; j < C; j += 2) {
+          Vec2<T> o; o.x = T(0); o.y = T(0);
+          if (valid) o = ld2(Out + base + c0 + j);
+          outv[j] = fma(alpha, a[j], mul_rn(beta, o.x));
+          outv[j + 1] = fma(alpha, a[j + 1], mul_rn(beta, o.y));
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < C; j++) outv[j] = T(0);
+        for (int j = 0; j < C; j++) outv[j] = mul_rn(alpha, a[j]);
       }
-      if (TPR > 1) __syncwarp();                   // Out may alias In: every lane of the row has read it by now
-      if (valid) {
+      if (valid) {                                 // Out may alias In: each lane rewrites exactly the slab it read
 #pragma unroll
         for (int j = 0; j < C; j += 2) {
           Vec2<T> o; o.x = outv[j]; o.y = outv[j + 1];
@@ -428,23 +437,25 @@ __global__ void __launch_bounds__(kBlock, (P * P / TPR <= 32 ? 2 : 1)) panel_fas
       }
     }
     if (GRAM) {
+      T lv[C];                                     // this lane's slab of the left operand row
       if (Next) {
 #pragma unroll
-        for (int i = 0; i < P; i += 2) {
-          Vec2<T> l; l.x = T(0); l.y = T(0);
-          if (valid) l = ld2(Next + base + i);
-#pragma unroll
-          for (int j = 0; j < C; j++) { acc[i][j] += l.x * outv[j]; acc[i + 1][j] += l.y * outv[j]; }
+        for (int j = 0; j < C; j += 2) {
+          Vec2<T> v; v.x = T(0); v.y = T(0);
+          if (valid) v = ld2(Next + base + c0 + j);
+          lv[j] = v.x; lv[j + 1] = v.y;
         }
       } else {
 #pragma unroll
-        for (int k = 0; k < TPR; k++) {            // the full updated row, slab by slab, from the lanes that own it
+        for (int j = 0; j < C; j++) lv[j] = outv[j];
+      }
 #pragma unroll
-          for (int jj = 0; jj < C; jj++) {
-            const T l = TPR == 1 ? outv[jj] : __shfl_sync(0xffffffffu, outv[jj], (lane - slab) + k);
+      for (int k = 0; k < TPR; k++) {
 #pragma unroll
-            for (int j = 0; j < C; j++) acc[k * C + jj][j] += l * outv[j];
-          }
+        for (int jj = 0; jj < C; jj++) {
+          const T l = TPR == 1 ? lv[jj] : __shfl_sync(0xffffffffu, lv[jj], lane0 + k);
+#pragma unroll
+          for (int j = 0; j < C; j++) acc[k * C + jj][j] += l * outv[j];
         }
       }
     }
