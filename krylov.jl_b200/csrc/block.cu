@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kBlock) panel_nn_kernel(int n, int p, T alpha,
 // bandwidth-bound, unlike the tiled generic kernels.
 //   UPDATE: Out[r][:] = beta Out[r][:] + alpha In[r][:] S         GRAM: G = Next^T Out  (Next == nullptr: Out^T Out)
 
-template <class T, int P, int TPR, bool UPDATE, bool GRAM>
+template <class T, int P, int TPR, bool UPDATE, bool GRAM, bool PREFETCH>
 __global__ void __launch_bounds__(kBlock, (P * P / TPR <= 32 ? 2 : 1)) panel_fast_kernel(int n, T alpha, const T* In, const T* __restrict__ S,
                                                                                      T beta, T* Out, const T* Next, T* part,
                                                                                      unsigned* ticket, T* G) {
@@ -381,84 +381,77 @@ __global__ void __launch_bounds__(kBlock, (P * P / TPR <= 32 ? 2 : 1)) panel_fas
   const int rows_per_pass = gridDim.x * (kBlock / TPR);
   const int first = blockIdx.x * (kBlock / TPR) + tid / TPR;
   const int passes = (n + rows_per_pass - 1) / rows_per_pass;        // uniform trip count: shuffles stay convergent
-  for (int it = 0; it < passes; it++) {
+  const int lane0 = lane - slab;                   // first of the TPR lanes that share a row
+  const bool need_out = !UPDATE || beta != T(0);
+  // this lane's slabs of one panel row: every panel element is loaded by exactly one lane, as 16-byte vectors
+  struct Slabs { T in[C], out[C], nx[C]; bool valid; size_t base; };
+  auto load_row = [&](int it, Slabs& r) {
     const int row = first + it * rows_per_pass;
-    const bool valid = row < n;
-    const size_t base = (size_t)(valid ? row : 0) * P;
-    T outv[C];
-    const int lane0 = lane - slab;                 // first of the TPR lanes that share this row
-    if (UPDATE) {
-      // each lane loads only ITS slab of the In row (the row is read once, coalesced); the other slabs arrive by
-      // shuffle from the lanes that hold them, in ascending column order (the order of the row-times-matrix sum)
-      T inv[C], a[C];
+    r.valid = row < n;
+    r.base = (size_t)(r.valid ? row : 0) * P;
 #pragma unroll
-      for (int j = 0; j < C; j += 2) {
-        Vec2<T> v; v.x = T(0); v.y = T(0);
-        if (valid) v = ld2(In + base + c0 + j);
-        inv[j] = v.x; inv[j + 1] = v.y;
+    for (int j = 0; j < C; j += 2) {
+      Vec2<T> z; z.x = T(0); z.y = T(0);
+      Vec2<T> vi = z, vo = z, vn = z;
+      if (r.valid) {
+        if (UPDATE) vi = ld2(In + r.base + c0 + j);
+        if (need_out) vo = ld2(Out + r.base + c0 + j);
+        if (GRAM && Next) vn = ld2(Next + r.base + c0 + j);
       }
+      r.in[j] = vi.x; r.in[j + 1] = vi.y;
+      r.out[j] = vo.x; r.out[j + 1] = vo.y;
+      r.nx[j] = vn.x; r.nx[j + 1] = vn.y;
+    }
+  };
+  Slabs cur;
+  load_row(0, cur);
+  for (int it = 0; it < passes; it++) {
+    Slabs nxt;
+    if (PREFETCH && it + 1 < passes) load_row(it + 1, nxt);      // next row's loads in flight during this row's math
+    T outv[C];
+    if (UPDATE) {
+      // the other slabs of the In row arrive by shuffle from the lanes that hold them, in ascending column order
+      // (the order of the row-times-matrix sum)
+      T a[C];
 #pragma unroll
       for (int j = 0; j < C; j++) a[j] = T(0);
 #pragma unroll
       for (int k = 0; k < TPR; k++) {
 #pragma unroll
         for (int jj = 0; jj < C; jj++) {
-          const T in = TPR == 1 ? inv[jj] : __shfl_sync(0xffffffffu, inv[jj], lane0 + k);
+          const T in = TPR == 1 ? cur.in[jj] : __shfl_sync(0xffffffffu, cur.in[jj], lane0 + k);
           const int i = k * C + jj;
 #pragma unroll
           for (int j = 0; j < C; j++) a[j] = fma(in, Ss[i * P + c0 + j], a[j]);     // contracted: this is a GEMM, not a k* primitive
         }
       }
-      if (beta != T(0)) {
 #pragma unroll
-        for (int j = 0; j < C; j += 2) {
-          Vec2<T> o; o.x = T(0); o.y = T(0);
-          if (valid) o = ld2(Out + base + c0 + j);
-          outv[j] = fma(alpha, a[j], mul_rn(beta, o.x));
-          outv[j + 1] = fma(alpha, a[j + 1], mul_rn(beta, o.y));
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < C; j++) outv[j] = mul_rn(alpha, a[j]);
-      }
-      if (valid) {                                 // Out may alias In: each lane rewrites exactly the slab it read
+      for (int j = 0; j < C; j++) outv[j] = beta != T(0) ? fma(alpha, a[j], mul_rn(beta, cur.out[j])) : mul_rn(alpha, a[j]);
+      if (cur.valid) {                             // Out may alias In: each lane rewrites exactly the slab it read
 #pragma unroll
         for (int j = 0; j < C; j += 2) {
           Vec2<T> o; o.x = outv[j]; o.y = outv[j + 1];
-          *reinterpret_cast<Vec2<T>*>(Out + base + c0 + j) = o;
+          *reinterpret_cast<Vec2<T>*>(Out + cur.base + c0 + j) = o;
         }
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < C; j += 2) {
-        Vec2<T> o; o.x = T(0); o.y = T(0);
-        if (valid) o = ld2(Out + base + c0 + j);
-        outv[j] = o.x; outv[j + 1] = o.y;
-      }
+      for (int j = 0; j < C; j++) outv[j] = cur.out[j];
     }
     if (GRAM) {
-      T lv[C];                                     // this lane's slab of the left operand row
-      if (Next) {
-#pragma unroll
-        for (int j = 0; j < C; j += 2) {
-          Vec2<T> v; v.x = T(0); v.y = T(0);
-          if (valid) v = ld2(Next + base + c0 + j);
-          lv[j] = v.x; lv[j + 1] = v.y;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < C; j++) lv[j] = outv[j];
-      }
 #pragma unroll
       for (int k = 0; k < TPR; k++) {
 #pragma unroll
         for (int jj = 0; jj < C; jj++) {
-          const T l = TPR == 1 ? lv[jj] : __shfl_sync(0xffffffffu, lv[jj], lane0 + k);
+          const T mine = Next ? cur.nx[jj] : outv[jj];         // this lane's slab of the left operand row
+          const T l = TPR == 1 ? mine : __shfl_sync(0xffffffffu, mine, lane0 + k);
 #pragma unroll
           for (int j = 0; j < C; j++) acc[k * C + jj][j] += l * outv[j];
         }
       }
     }
+    if (PREFETCH) cur = nxt;
+    else if (it + 1 < passes) load_row(it + 1, cur);
   }
   if (!GRAM) return;
   // rows of this warp (lanes with the same slab), then the warps in order, then the CTAs in order
@@ -660,9 +653,16 @@ static bool launch_fast(BlockWorkspace<T>& ws, T alpha, const T* In, const T* S,
   const int grid = ws.fast_grid;
   // KB200_FAST_TPR=alt selects the second lanes-per-row shape of P = 8 / 16 (sweeps, profiles/README.md)
   static const bool alt = getenv("KB200_FAST_TPR") != nullptr;
+  static const bool prefetch = getenv("KB200_FAST_PREFETCH") != nullptr;   // software-pipelined row loads (sweeps)
 #define KB_FAST(PV, TV)                                                                                                   \
-  panel_fast_kernel<T, PV, TV, UPDATE, GRAM><<<grid, kBlock, 0, c.stream>>>(ws.n, alpha, In, S, beta, Out, Next, ws.part, \
-                                                                            c.tickets + 6, G)
+  do {                                                                                                                    \
+    if (prefetch)                                                                                                         \
+      panel_fast_kernel<T, PV, TV, UPDATE, GRAM, true><<<grid, kBlock, 0, c.stream>>>(ws.n, alpha, In, S, beta, Out, Next, \
+                                                                                      ws.part, c.tickets + 6, G);         \
+    else                                                                                                                  \
+      panel_fast_kernel<T, PV, TV, UPDATE, GRAM, false><<<grid, kBlock, 0, c.stream>>>(ws.n, alpha, In, S, beta, Out, Next, \
+                                                                                       ws.part, c.tickets + 6, G);        \
+  } while (0)
   switch (ws.p) {
     case 2: KB_FAST(2, 1); break;
     case 4: KB_FAST(4, 1); break;

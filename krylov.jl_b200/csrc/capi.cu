@@ -42,7 +42,6 @@ struct Handle {
   void* Ndiag = nullptr;
   KrylovB200Options ext;
   void *hx = nullptr, *hy = nullptr;   // pinned staging for host callbacks
-  void* xstage = nullptr;              // pinned staging for b / x transfers
 };
 
 std::mutex g_mu;
@@ -113,7 +112,6 @@ template <class T> void destroy_handle(Handle* h) {
   dev_free(h->Mdiag); dev_free(h->Ndiag);
   if (h->hx) cudaFreeHost(h->hx);
   if (h->hy) cudaFreeHost(h->hy);
-  if (h->xstage) cudaFreeHost(h->xstage);
   ws_destroy<T>(ws);
   delete h;
 }

@@ -5,7 +5,11 @@
 //   blas1.cu      k* primitives on device vectors   (src/krylov_utils.jl:309-349)
 //   spmv.cu       CSR operator: plain and TMA-staged SpMV (kmul!, krylov_utils.jl:305)
 //   cg_fused.cu   two-launch CG iteration               (src/cg.jl:195-268)
+//   fused_phases.cu  fused iteration phases of bicgstab!/minres!/gmres! (+ the Arnoldi step fom!/fgmres! share)
 //   solvers.cu    host control flow of cg!/gmres!/bicgstab!/minres! on the primitives
+//   siblings.cu   cgs!, cg_lanczos!, fom!, fgmres!, dqgmres!, diom!, cr! on the same kernels
+//   block.cu      block_gmres! on row-major device panels (8f-2; block.h)
+//   mtx.cu        Matrix Market ingestion, transposed operator (8f-4; mtx.h)
 //   capi.cu       the C ABI (include/krylov_b200.h)
 #pragma once
 #include <cuda_runtime.h>
@@ -92,8 +96,6 @@ template <class T> void k_spmv(Ctx& c, const Csr<T>& A, const T* x, T* y, int va
 // Row-partitioned operators: send this rank's boundary entries of x to the peers' halo buffers and meet in the
 // in-kernel barrier (no-op on a single GPU).  Every y = A x on a distributed workspace is preceded by one.
 template <class T> void k_halo_exchange(Ctx& c, const T* x);
-// y = A x and  <x, y>  in one launch (result in dscal[slot])
-template <class T> void k_spmv_dot_dev(Ctx& c, const Csr<T>& A, const T* x, T* y, int slot);
 
 // ---------------------------------------------------------------------------
 // Operators as the solvers see them (A, M, N of the reference's kwargs).

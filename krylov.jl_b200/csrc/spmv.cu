@@ -233,7 +233,6 @@ static void spmv_launch(Ctx& c, const Csr<T>& A, const T* x, T* y, int slot, int
 }
 
 template <class T> void k_spmv(Ctx& c, const Csr<T>& A, const T* x, T* y, int variant) { spmv_launch<T, false>(c, A, x, y, 1, variant); }
-template <class T> void k_spmv_dot_dev(Ctx& c, const Csr<T>& A, const T* x, T* y, int slot) { spmv_launch<T, true>(c, A, x, y, slot, 0); }
 
 // ---------------------------------------------------------------------------
 // General x-halo exchange of row-partitioned operators (dist.cuh: DistExchange)
@@ -310,7 +309,6 @@ template <class T> void op_apply(Ctx& c, const LinOp<T>& op, const T* x, T* y, b
   template void csr_free<T>(Csr<T>&);                                                                            \
   template void csr_plan<T>(Ctx&, Csr<T>&);                                                                      \
   template void k_spmv<T>(Ctx&, const Csr<T>&, const T*, T*, int);                                               \
-  template void k_spmv_dot_dev<T>(Ctx&, const Csr<T>&, const T*, T*, int);                                       \
   template void k_halo_exchange<T>(Ctx&, const T*);                                                              \
   template void op_apply<T>(Ctx&, const LinOp<T>&, const T*, T*, bool);
 INST(double)

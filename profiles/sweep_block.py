@@ -7,8 +7,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ps = [a for a in sys.argv[1:]] or ["8", "16"]
-configs = [("default", {}), ("spmm=rows", {"KB200_SPMM": "rows"}), ("fast_tpr=alt", {"KB200_FAST_TPR": "alt"}),
-           ("generic tiled kernels", {"KB200_BLOCK_GENERIC": "1"})]
+configs = [("default", {}), ("prefetch", {"KB200_FAST_PREFETCH": "1"}), ("spmm=rows", {"KB200_SPMM": "rows"}),
+           ("fast_tpr=alt", {"KB200_FAST_TPR": "alt"}), ("generic tiled kernels", {"KB200_BLOCK_GENERIC": "1"})]
+if "--quick" in sys.argv:
+    configs = configs[:2]
+    ps = [a for a in ps if a != "--quick"]
 for name, env in configs:
     e = dict(os.environ, **env)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "bench_block.py")] + ps, env=e, capture_output=True, text=True)

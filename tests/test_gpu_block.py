@@ -27,11 +27,30 @@ def _check(st, X, so, Xo, tol=1e-6):
     assert np.linalg.norm(X - Xo) <= 1e-6 * np.linalg.norm(Xo)
 
 
-@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("generic", [False, True, "prefetch"])
 @pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 8, 16, 32])
 def test_block_gmres_block_sizes(kb, O, p, generic, monkeypatch):
-    """p = 2, 4, 8, 16, 32 run the register-resident panel kernels, every other p (and KB200_BLOCK_GENERIC=1) the tiled
-    any-p kernels; both against the oracle."""
+    """p = 2, 4, 8, 16, 32 run the register-resident panel kernels (with or without software-pipelined row loads), every
+    other p (and KB200_BLOCK_GENERIC=1) the tiled any-p kernels; all against the oracle."""
+    if generic == "prefetch":
+        import subprocess, sys, textwrap
+        # the switch is read once per process: run this variant in a child
+        code = textwrap.dedent(f"""
+            import sys; sys.path[:0] = {[ROOT, os.path.join(ROOT, "krylov.jl_b200"), os.path.join(ROOT, "tests")]!r}
+            import numpy as np, scipy.sparse as sp
+            import krylov_b200 as kb
+            from oracle import oracle as O
+            A, _ = O.kron_unsymmetric(8); A = sp.csr_matrix(A)
+            B = A @ np.random.default_rng(0).standard_normal((A.shape[0], {p}))
+            X, st = kb.block_gmres(A, B, memory=6, history=True)
+            Xo, so = O.block_gmres(A, B, memory=6)
+            assert st.niter == so["niter"] and st.status == so["status"]
+            assert np.allclose(st.residuals, so["residuals"], rtol=1e-6, atol=1e-9 * so["residuals"][0])
+            assert np.linalg.norm(X - Xo) <= 1e-6 * np.linalg.norm(Xo)
+        """)
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, KB200_FAST_PREFETCH="1"), capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return
     if generic:
         monkeypatch.setenv("KB200_BLOCK_GENERIC", "1")
     A, _ = O.kron_unsymmetric(8)
