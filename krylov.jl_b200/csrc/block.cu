@@ -5,12 +5,17 @@
 // reads A once for all p right-hand sides, and the tall-skinny products stream both panels once.  B and X are
 // transposed on the way in / out (the C ABI keeps the reference's column-major blocks).
 //
-// Kernels (all HBM-bound: p/8 flop per byte for the tall-skinny products, below the fp64 ridge for p <= 32):
-//   spmm_rows     W = A P          p threads per row, A read once
-//   panel_tn      G = V^T Q        (p x p) tile-staged, deterministic "last block finalises" reduction
-//   panel_nn      Q = beta Q + alpha V S   (S p x p read from device memory: the Gram-Schmidt chain never
-//                                           visits the host)
-//   rows_diag     P = diag(d) V    (Jacobi M / N)
+// Kernels (p/8 flop per byte in the tall-skinny products: HBM-bound for p <= 8, FP64/issue-bound from p = 16 on):
+//   spmm_tma_kernel<P>      W = A P on the TMA-staged tile pipeline of the SpMV, P lanes per row (P = 2..32);
+//   spmm_rows_kernel        the same for any p: p threads per row, plain loads
+//   panel_fast_kernel<P,..> register-resident tall-skinny products for P = 2, 4, 8, 16, 32:
+//                             product   G = V^T Q (p x p, deterministic "last block finalises" reduction)
+//                             update    Q = beta Q + alpha V S  (S p x p read from device memory: the Gram-Schmidt
+//                                       chain never visits the host)
+//                             fused     update followed by the next product in the same pass over the panels
+//   panel_tn / panel_nn / panel_nn_tn_kernel   the same three operations for any p, 4 x 4 register-blocked on
+//                             shared-memory tiles with an odd row stride
+//   rows_diag_kernel        P = diag(d) V (Jacobi M / N);  relayout_kernel: column-major block <-> panel
 // The panel QR of the reference (LAPACK geqrf + orgqr, src/block_krylov_utils.jl:201-208) is CholQR2 on the
 // device (two Gram matrices, two p x p Cholesky factorizations on the host) followed by the reconstruction of
 // the Householder signs from the top p x p block of Q (Ballard et al., "Reconstructing Householder vectors
