@@ -113,6 +113,10 @@ int krylov_block_niter(void *ws);
 double krylov_block_elapsed_time(void *ws);
 int krylov_block_warm_start(void *ws, const void *x0, int n, int p);
 int krylov_block_workspace_free(void *ws);
+/* Number of panel QR factorizations of this block workspace that left the device path: a Gram matrix that is not
+ * numerically positive definite (rank-deficient block of right-hand sides or Krylov block) makes CholQR2 impossible,
+ * and that ONE panel is then factorized by LAPACK's Householder algorithm on the host.  0 on well-posed blocks. */
+long long krylov_b200_block_qr_fallbacks(void *ws);
 
 /* ===================== PART 2: B200 additions (additive) ===================== */
 
@@ -249,6 +253,15 @@ void *kb200_csr_transpose(void *ctx, void *csr);
 int kb200_csr_info(void *csr, int *n, long long *nnz);
 /* rowptr[n+1], colind[nnz] (0-based int32), values[nnz] in the object's dtype; any pointer may be NULL */
 int kb200_csr_download(void *ctx, void *csr, int *rowptr, int *colind, void *values);
+/* Host-side pieces, callable without a GPU (they make no CUDA call): the Matrix Market parser behind
+ * kb200_csr_read_mtx (pass NULL arrays to query n / nnz first) and the small dense algebra of the block path --
+ * LAPACK-style Householder QR (householder!, src/block_krylov_utils.jl:201-208: Q m x k column-major in/out, R k x k,
+ * compact = 1 keeps the reflectors), the Cholesky factor / inverse of a Gram matrix (1: not positive definite
+ * enough for CholQR2), and the Householder-sign reconstruction from the top p x p block of an orthonormal factor. */
+int kb200_mtx_read(const char *path, int *n, long long *nnz, int *rowptr, int *colind, double *values);
+int kb200_host_householder(int m, int k, double *Q, double *R, double *tau, int compact);
+int kb200_host_cholqr_factors(int p, const double *G, double *R, double *Rinv);
+int kb200_host_householder_signs(int p, const double *top, double *s);
 /* y = A x.  variant: 0 auto, 1 row-per-thread LDG kernel, 2 TMA-staged kernel. */
 int kb200_spmv_csr(void *ctx, void *csr, const void *x, void *y, int variant);
 /* staging plan of a CSR object: out[0]=ntiles out[1]=tile_cap out[2]=max_row out[3]=tma_ok out[4]=stages out[5]=grid out[6]=smem_bytes */

@@ -16,6 +16,7 @@
 #include "kb_internal.h"
 #include "block.h"
 #include "mtx.h"
+#include "dense_small.h"
 
 using namespace kb;
 
@@ -476,6 +477,11 @@ int krylov_block_warm_start(void* ws, const void* x0, int n, int p) {
     return h->dtype == KRYLOV_FLOAT64 ? do_block_warm_start<double>(h, x0, n, p) : do_block_warm_start<float>(h, x0, n, p);
   } catch (const std::exception& e) { return fail("krylov_block_warm_start", e); }
 }
+long long krylov_b200_block_qr_fallbacks(void* ws) {
+  Handle* h = lookup_block(ws);
+  if (!h) return -1;
+  return h->dtype == KRYLOV_FLOAT64 ? BW<double>(h)->qr_fallbacks : BW<float>(h)->qr_fallbacks;
+}
 int krylov_block_workspace_free(void* ws) {
   try {
     Handle* h = lookup_block(ws);
@@ -911,6 +917,42 @@ int kb200_csr_download(void* ctx, void* csr, int* rowptr, int* colind, void* val
     }
     return 0;
   } catch (const std::exception& e) { return fail("kb200_csr_download", e); }
+}
+
+// ---- host-side pieces, callable without a GPU (tests/test_host_logic.py) ---------------------------------------
+int kb200_mtx_read(const char* path, int* n, long long* nnz, int* rowptr, int* colind, double* values) {
+  try {
+    if (!path) throw std::runtime_error("path is NULL");
+    HostCsr h;
+    read_matrix_market(path, h);
+    if (n) *n = h.n;
+    if (nnz) *nnz = (long long)h.colind.size();
+    if (rowptr) for (size_t i = 0; i < h.rowptr.size(); i++) rowptr[i] = (int)h.rowptr[i];
+    if (colind) for (size_t i = 0; i < h.colind.size(); i++) colind[i] = (int)h.colind[i];
+    if (values) std::memcpy(values, h.val.data(), sizeof(double) * h.val.size());
+    return 0;
+  } catch (const std::exception& e) { return fail("kb200_mtx_read", e); }
+}
+
+int kb200_host_householder(int m, int k, double* Q, double* R, double* tau, int compact) {
+  if (!Q || !R || !tau || m < k || k < 1) return fail("kb200_host_householder", "bad arguments");
+  dense::householder_compact<double>(m, k, Q, R, tau);
+  if (!compact) dense::org2r<double>(m, k, Q, m, tau);
+  return 0;
+}
+
+int kb200_host_cholqr_factors(int p, const double* G, double* R, double* Rinv) {
+  if (!G || !R || !Rinv || p < 1) return fail("kb200_host_cholqr_factors", "bad arguments");
+  if (!dense::cholesky_upper<double>(p, G, R)) return 1;
+  dense::inv_upper<double>(p, R, Rinv);
+  return 0;
+}
+
+int kb200_host_householder_signs(int p, const double* top, double* s) {
+  if (!top || !s || p < 1) return fail("kb200_host_householder_signs", "bad arguments");
+  std::vector<double> W(top, top + (size_t)p * p);
+  dense::householder_signs<double>(p, W.data(), s);
+  return 0;
 }
 
 int kb200_spmv_csr(void* ctx, void* csr, const void* x, void* y, int variant) {

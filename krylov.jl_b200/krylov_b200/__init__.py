@@ -630,6 +630,11 @@ class BlockGmresWorkspace(KrylovWorkspace):
 
     X = x
 
+    @property
+    def qr_fallbacks(self) -> int:
+        """Panel QR factorizations that took the host Householder path (rank-deficient blocks); 0 normally."""
+        return int(lib().krylov_b200_block_qr_fallbacks(self._h))
+
 
 def block_gmres(A, B, X0=None, *, memory=0, **kw):
     """(X, stats) = block_gmres(A, B[, X0]; memory=5, kwargs...)  (src/block_gmres.jl:1-60)"""

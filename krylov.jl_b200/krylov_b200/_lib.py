@@ -76,6 +76,7 @@ SIGNATURES = {
     "krylov_block_elapsed_time": (_D, [_P]),
     "krylov_block_warm_start": (_I, [_P, _P, _I, _I]),
     "krylov_block_workspace_free": (_I, [_P]),
+    "krylov_b200_block_qr_fallbacks": (_LL, [_P]),
     "krylov_b200_device_count": (_I, []),
     "krylov_b200_set_device": (_I, [_I]),
     "krylov_b200_last_error": (C.c_char_p, []),
@@ -119,6 +120,10 @@ SIGNATURES = {
     "kb200_csr_transpose": (_P, [_P, _P]),
     "kb200_csr_info": (_I, [_P, C.POINTER(_I), C.POINTER(_LL)]),
     "kb200_csr_download": (_I, [_P, _P, _P, _P, _P]),
+    "kb200_mtx_read": (_I, [C.c_char_p, C.POINTER(_I), C.POINTER(_LL), _P, _P, _P]),
+    "kb200_host_householder": (_I, [_I, _I, _P, _P, _P, _I]),
+    "kb200_host_cholqr_factors": (_I, [_I, _P, _P, _P]),
+    "kb200_host_householder_signs": (_I, [_I, _P, _P]),
     "kb200_spmv_csr": (_I, [_P, _P, _P, _P, _I]),
     "kb200_csr_plan": (_I, [_P, C.POINTER(_LL)]),
 }

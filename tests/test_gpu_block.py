@@ -114,7 +114,16 @@ def test_block_gmres_rank_deficient_block_falls_back(kb, O):
     host path, and the solve still matches the oracle's."""
     A, b = O.sparse_laplacian(6)
     B = np.stack([b, b, np.arange(len(b), dtype=float)], axis=1)
-    X, st = kb.block_gmres(A, B, memory=10, itmax=12, history=True)
+    ws = kb.BlockGmresWorkspace(A.shape[0], A.shape[0], 3, memory=10)
+    ws.solve(A, B, itmax=12, history=True)
+    X, st = ws.x, ws.stats
+    assert ws.qr_fallbacks >= 1                       # the fallback is counted, never silent
+    ws.free()
+    Bok = np.stack([b, np.cos(np.arange(len(b))), np.arange(len(b), dtype=float)], axis=1)
+    ws = kb.BlockGmresWorkspace(A.shape[0], A.shape[0], 3, memory=10)
+    ws.solve(A, Bok, history=True)
+    assert ws.stats.solved and ws.qr_fallbacks == 0   # well-posed blocks never leave the device
+    ws.free()
     Xo, so = O.block_gmres(A, B, memory=10, itmax=12)
     assert st.niter == so["niter"] and st.status == so["status"]
     k = min(6, len(so["residuals"]))
