@@ -113,9 +113,10 @@ int krylov_block_niter(void *ws);
 double krylov_block_elapsed_time(void *ws);
 int krylov_block_warm_start(void *ws, const void *x0, int n, int p);
 int krylov_block_workspace_free(void *ws);
-/* Number of panel QR factorizations of this block workspace that left the device path: a Gram matrix that is not
+/* Number of panel QR factorizations of this block workspace that left the fast path: a Gram matrix that is not
  * numerically positive definite (rank-deficient block of right-hand sides or Krylov block) makes CholQR2 impossible,
- * and that ONE panel is then factorized by LAPACK's Householder algorithm on the host.  0 on well-posed blocks. */
+ * and that ONE panel is then factorized by LAPACK's Householder algorithm run as 4p passes of the panel kernels
+ * (still on the device).  0 on well-posed blocks. */
 long long krylov_b200_block_qr_fallbacks(void *ws);
 
 /* ===================== PART 2: B200 additions (additive) ===================== */

@@ -20,7 +20,8 @@
 // device (two Gram matrices, two p x p Cholesky factorizations on the host) followed by the reconstruction of
 // the Householder signs from the top p x p block of Q (Ballard et al., "Reconstructing Householder vectors
 // from tall-skinny QR", 2014), so V[k] and the R factors equal LAPACK's, not only up to column signs.  A Gram
-// matrix that is not numerically positive definite (rank-deficient block) falls back to Householder on the host.
+// matrix that is not numerically positive definite (rank-deficient block) falls back to LAPACK's Householder
+// algorithm, also on the device (panel_qr).
 // Everything p x p (the Hessenberg QR, the block back substitution) stays on the host like the reference's.
 #include <cstring>
 
@@ -549,7 +550,7 @@ template <class T> static void k_rows_diag(Ctx& c, int n, int p, const T* d, con
 }
 // fast-path dispatch: true when p has a register-resident specialization
 template <class T, bool UPDATE, bool GRAM>
-static bool launch_fast(BlockWorkspace<T>& ws, T alpha, const T* In, const T* S, T beta, T* Out, const T* Next, T* G) {
+static bool launch_fast(BlockWorkspace<T>& ws, T alpha, const T* In, const T* S, T beta, T* Out, const T* Next, T* G, int rows) {
   Ctx& c = ws.ctx;
   if (ws.generic_kernels) return false;
   const int grid = ws.fast_grid;
@@ -559,10 +560,10 @@ static bool launch_fast(BlockWorkspace<T>& ws, T alpha, const T* In, const T* S,
 #define KB_FAST(PV, TV)                                                                                                   \
   do {                                                                                                                    \
     if (prefetch)                                                                                                         \
-      panel_fast_kernel<T, PV, TV, UPDATE, GRAM, true><<<grid, kBlock, 0, c.stream>>>(ws.n, alpha, In, S, beta, Out, Next, \
+      panel_fast_kernel<T, PV, TV, UPDATE, GRAM, true><<<grid, kBlock, 0, c.stream>>>(rows, alpha, In, S, beta, Out, Next, \
                                                                                       ws.part, c.tickets + 6, G);         \
     else                                                                                                                  \
-      panel_fast_kernel<T, PV, TV, UPDATE, GRAM, false><<<grid, kBlock, 0, c.stream>>>(ws.n, alpha, In, S, beta, Out, Next, \
+      panel_fast_kernel<T, PV, TV, UPDATE, GRAM, false><<<grid, kBlock, 0, c.stream>>>(rows, alpha, In, S, beta, Out, Next, \
                                                                                        ws.part, c.tickets + 6, G);        \
   } while (0)
   switch (ws.p) {
@@ -578,29 +579,32 @@ static bool launch_fast(BlockWorkspace<T>& ws, T alpha, const T* In, const T* S,
   return true;
 }
 
-template <class T> static void k_panel_tn(BlockWorkspace<T>& ws, const T* V, const T* Q, T* G) {
+// `rows` < 0: the whole panel (ws.n rows); otherwise the first `rows` rows starting at the given pointers
+template <class T> static void k_panel_tn(BlockWorkspace<T>& ws, const T* V, const T* Q, T* G, int rows = -1) {
   Ctx& c = ws.ctx;
   const int p = ws.p;
-  if (launch_fast<T, false, true>(ws, T(0), (const T*)nullptr, (const T*)nullptr, T(0), const_cast<T*>(Q), V == Q ? (const T*)nullptr : V, G)) return;
+  if (rows < 0) rows = ws.n;
+  if (launch_fast<T, false, true>(ws, T(0), (const T*)nullptr, (const T*)nullptr, T(0), const_cast<T*>(Q), V == Q ? (const T*)nullptr : V, G, rows)) return;
   const size_t smem = sizeof(T) * ((size_t)2 * kPanelTileElems);
-  panel_tn_kernel<T><<<ws.grid, kBlock, smem, c.stream>>>(ws.n, p, V, Q, ws.part, c.tickets + 6, G);
+  panel_tn_kernel<T><<<ws.grid, kBlock, smem, c.stream>>>(rows, p, V, Q, ws.part, c.tickets + 6, G);
   KB_CUDA(cudaGetLastError()); c.launches++;
 }
 template <class T> static void k_panel_nn_tn(BlockWorkspace<T>& ws, T alpha, const T* In, const T* S, T beta, T* Out, const T* Next, T* G) {
   Ctx& c = ws.ctx;
   const int p = ws.p;
-  if (launch_fast<T, true, true>(ws, alpha, In, S, beta, Out, Next, G)) return;
+  if (launch_fast<T, true, true>(ws, alpha, In, S, beta, Out, Next, G, ws.n)) return;
   const size_t smem = sizeof(T) * ((size_t)3 * kPanelTileElems + (size_t)p * p);
   ensure_dyn_smem((const void*)panel_nn_tn_kernel<T>, 96 * 1024);
   panel_nn_tn_kernel<T><<<ws.grid, kBlock, smem, c.stream>>>(ws.n, p, alpha, In, S, beta, Out, Next, ws.part, c.tickets + 6, G);
   KB_CUDA(cudaGetLastError()); c.launches++;
 }
-template <class T> static void k_panel_nn(BlockWorkspace<T>& ws, T alpha, const T* In, const T* S, T beta, T* Out) {
+template <class T> static void k_panel_nn(BlockWorkspace<T>& ws, T alpha, const T* In, const T* S, T beta, T* Out, int rows = -1) {
   Ctx& c = ws.ctx;
   const int p = ws.p;
-  if (launch_fast<T, true, false>(ws, alpha, In, S, beta, Out, (const T*)nullptr, (T*)nullptr)) return;
+  if (rows < 0) rows = ws.n;
+  if (launch_fast<T, true, false>(ws, alpha, In, S, beta, Out, (const T*)nullptr, (T*)nullptr, rows)) return;
   const size_t smem = sizeof(T) * ((size_t)2 * kPanelTileElems + (size_t)p * p);
-  panel_nn_kernel<T><<<ws.grid, kBlock, smem, c.stream>>>(ws.n, p, alpha, In, S, beta, Out);
+  panel_nn_kernel<T><<<ws.grid, kBlock, smem, c.stream>>>(rows, p, alpha, In, S, beta, Out);
   KB_CUDA(cudaGetLastError()); c.launches++;
 }
 // block operator application: CSR (SpMM), diagonal, or a user block callback on host / device panels (column-major)
@@ -680,17 +684,73 @@ template <class T> static void panel_qr(BlockWorkspace<T>& ws, T* Q, T* Rout, T*
   } else {
     failed_pass = 0;
   }
-  // rank-deficient (or too ill-conditioned) block: LAPACK's algorithm on the host (column-major), then back
+  // rank-deficient (or too ill-conditioned) block: LAPACK's Householder algorithm (dgeqr2 + dorg2r), still on the
+  // device.  Column j of the panel below row j IS the reflector direction, so applying H_j to the rows below j is a
+  // right-multiplication of those rows by an elementary p x p matrix (panel_nn on a row range); the inner products
+  // it needs are row j of the Gram matrix of the rows below j (panel_tn on the same range); only row j itself --
+  // p numbers -- is patched from the host.  4p passes over the panel instead of 4: a fallback, counted.
   ws.qr_fallbacks++;
-  if (n < p) throw std::runtime_error("block size exceeds the number of rows");
-  std::vector<T> hq((size_t)n * p), tau(p), Rh(pp);
-  k_transpose<T>(c, n, p, Q, ws.tmp);
-  KB_CUDA(cudaMemcpyAsync(hq.data(), ws.tmp, sizeof(T) * (size_t)n * p, cudaMemcpyDeviceToHost, c.stream));
-  c.sync();
-  dense::householder_compact<T>(n, p, hq.data(), Rh.data(), tau.data());
-  dense::org2r<T>(n, p, hq.data(), n, tau.data());
-  KB_CUDA(cudaMemcpyAsync(ws.tmp, hq.data(), sizeof(T) * (size_t)n * p, cudaMemcpyHostToDevice, c.stream));
-  k_transpose<T>(c, p, n, ws.tmp, dst);
+  std::vector<T> tau(p, T(0)), E(pp), Rh(pp, T(0));
+  T* hE = hT[0];                                  // pinned staging: elementary matrix, patched row
+  T* hRow = hT[1];
+  auto gram_below = [&](int j) {                  // hG <- Gram of rows j+1.., hTop <- rows 0..p-1 (after a sync)
+    const int below = n - (j + 1);
+    if (below > 0) {
+      k_panel_tn<T>(ws, Q + (size_t)(j + 1) * p, Q + (size_t)(j + 1) * p, ws.dG, below);
+      KB_CUDA(cudaMemcpyAsync(hG, ws.dG, sizeof(T) * pp, cudaMemcpyDeviceToHost, c.stream));
+    }
+    KB_CUDA(cudaMemcpyAsync(hTop, Q, sizeof(T) * pp, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    if (below <= 0) for (int i = 0; i < pp; i++) hG[i] = T(0);
+  };
+  auto apply_below = [&](int j, const std::vector<T>& Em, const T* row, int ncopy) {
+    // rows below j <- rows * Em ; row(s) 0..: ncopy leading entries of hTop-sized `row` buffer written back
+    const int below = n - (j + 1);
+    std::memcpy(hE, Em.data(), sizeof(T) * pp);
+    if (below > 0) {
+      KB_CUDA(cudaMemcpyAsync(ws.dS, hE, sizeof(T) * pp, cudaMemcpyHostToDevice, c.stream));
+      k_panel_nn<T>(ws, T(1), Q + (size_t)(j + 1) * p, ws.dS, T(0), Q + (size_t)(j + 1) * p, below);
+    }
+    KB_CUDA(cudaMemcpyAsync(Q, row, sizeof(T) * (size_t)ncopy, cudaMemcpyHostToDevice, c.stream));
+    c.sync();
+  };
+  for (int j = 0; j < p; j++) {                   // dgeqr2: reflectors H_0 .. H_{p-1}
+    gram_below(j);
+    const T alpha_j = hTop[j * p + j], xn2 = hG[j + j * p];      // hTop is row-major (rows of the panel)
+    if (xn2 == T(0)) { tau[j] = T(0); continue; }
+    const T beta_j = -std::copysign(std::sqrt(alpha_j * alpha_j + xn2), alpha_j);
+    tau[j] = (beta_j - alpha_j) / beta_j;
+    const T scal = T(1) / (alpha_j - beta_j);
+    for (int i = 0; i < pp; i++) E[i] = T(0);
+    for (int i = 0; i < p; i++) E[i + i * p] = T(1);
+    E[j + j * p] = scal;
+    std::memcpy(hRow, hTop, sizeof(T) * pp);
+    for (int k = j + 1; k < p; k++) {
+      const T vTa = hTop[j * p + k] + scal * hG[j + k * p];       // v^T A_k, v = [1; scal * A(j+1:, j)]
+      E[j + k * p] = -tau[j] * vTa * scal;
+      hRow[j * p + k] = hTop[j * p + k] - tau[j] * vTa;
+    }
+    hRow[j * p + j] = beta_j;
+    apply_below(j, E, hRow, (j + 1) * p);
+  }
+  gram_below(p - 1);                              // refresh hTop: R is its upper triangle
+  for (int jc = 0; jc < p; jc++) for (int i = 0; i <= jc; i++) Rh[i + jc * p] = hTop[i * p + jc];
+  for (int j = p - 1; j >= 0; j--) {              // dorg2r: accumulate Q = H_0 ... H_{p-1} [I; 0]
+    gram_below(j);
+    for (int i = 0; i < pp; i++) E[i] = T(0);
+    for (int i = 0; i < p; i++) E[i + i * p] = T(1);
+    std::memcpy(hRow, hTop, sizeof(T) * pp);
+    for (int k = j + 1; k < p; k++) {
+      const T w = hTop[j * p + k] + hG[j + k * p];               // v^T A_k with v_j = 1
+      E[j + k * p] = -tau[j] * w;
+      hRow[j * p + k] = hTop[j * p + k] - tau[j] * w;
+    }
+    E[j + j * p] = -tau[j];
+    hRow[j * p + j] = T(1) - tau[j];
+    for (int i = 0; i < j; i++) hRow[i * p + j] = T(0);
+    apply_below(j, E, hRow, (j + 1) * p);
+  }
+  if (dst != Q) k_copy<T>(c, n * p, dst, Q);
   c.sync();
   if (failed_pass == 1) { dense::matmul<T>(p, Rh.data(), R1.data(), tmp.data()); Rh = tmp; }   // Q was already Q R1^-1
   for (int i = 0; i < pp; i++) Rout[i] = Rh[i];

@@ -632,7 +632,7 @@ class BlockGmresWorkspace(KrylovWorkspace):
 
     @property
     def qr_fallbacks(self) -> int:
-        """Panel QR factorizations that took the host Householder path (rank-deficient blocks); 0 normally."""
+        """Panel QR factorizations that took the slow Householder path (rank-deficient blocks); 0 normally."""
         return int(lib().krylov_b200_block_qr_fallbacks(self._h))
 
 

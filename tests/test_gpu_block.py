@@ -110,8 +110,9 @@ def test_block_gmres_float32_callbacks_and_torch(kb, O):
 
 
 def test_block_gmres_rank_deficient_block_falls_back(kb, O):
-    """Two identical right-hand sides: the Gram matrix of the block is singular, the panel QR takes the LAPACK-style
-    host path, and the solve still matches the oracle's."""
+    """Two identical right-hand sides: the Gram matrix of the block is singular, the panel QR takes LAPACK's
+    Householder algorithm (still on the device, as column operations on row ranges of the panel), and the solve still
+    matches the oracle's."""
     A, b = O.sparse_laplacian(6)
     B = np.stack([b, b, np.arange(len(b), dtype=float)], axis=1)
     ws = kb.BlockGmresWorkspace(A.shape[0], A.shape[0], 3, memory=10)
@@ -124,6 +125,17 @@ def test_block_gmres_rank_deficient_block_falls_back(kb, O):
     ws.solve(A, Bok, history=True)
     assert ws.stats.solved and ws.qr_fallbacks == 0   # well-posed blocks never leave the device
     ws.free()
+    # the same with an even block size (register-resident kernels on row ranges of the panel)
+    B4 = np.stack([b, np.cos(np.arange(len(b))), b, np.arange(len(b), dtype=float)], axis=1)
+    ws = kb.BlockGmresWorkspace(A.shape[0], A.shape[0], 4, memory=10)
+    ws.solve(A, B4, itmax=10, history=True)
+    X4, st4 = ws.x, ws.stats
+    assert ws.qr_fallbacks >= 1
+    ws.free()
+    Xo4, so4 = O.block_gmres(A, B4, memory=10, itmax=10)
+    assert st4.niter == so4["niter"] and st4.status == so4["status"]
+    k4 = min(5, len(so4["residuals"]))
+    assert np.allclose(st4.residuals[:k4], so4["residuals"][:k4], rtol=1e-5, atol=1e-9 * so4["residuals"][0])
     Xo, so = O.block_gmres(A, B, memory=10, itmax=12)
     assert st.niter == so["niter"] and st.status == so["status"]
     k = min(6, len(so["residuals"]))
