@@ -654,7 +654,8 @@ template <class T> static void panel_qr(BlockWorkspace<T>& ws, T* Q, T* Rout, T*
     c.sync();
   }
   // pass 0: Q <- Q R1^-1, fused with the Gram matrix of the result
-  if (dense::cholesky_upper<T>(p, hG, R1.data())) {
+  const bool force_householder = getenv("KB200_QR_FORCE_HOUSEHOLDER") != nullptr;   // tests: exercise the slow path on full-rank panels
+  if (!force_householder && dense::cholesky_upper<T>(p, hG, R1.data())) {
     dense::inv_upper<T>(p, R1.data(), hT[0]);
     KB_CUDA(cudaMemcpyAsync(ws.dS, hT[0], sizeof(T) * pp, cudaMemcpyHostToDevice, c.stream));
     k_panel_nn_tn<T>(ws, T(1), Q, ws.dS, T(0), Q, (const T*)nullptr, ws.dG);

@@ -109,37 +109,50 @@ def test_block_gmres_float32_callbacks_and_torch(kb, O):
         kb.block_gmres(A, B, callback=lambda w: "string")
 
 
-def test_block_gmres_rank_deficient_block_falls_back(kb, O):
-    """Two identical right-hand sides: the Gram matrix of the block is singular, the panel QR takes LAPACK's
-    Householder algorithm (still on the device, as column operations on row ranges of the panel), and the solve still
-    matches the oracle's."""
+@pytest.mark.parametrize("p", [3, 4, 8])
+def test_device_householder_path_matches_oracle_on_full_rank_blocks(kb, O, p, monkeypatch):
+    """KB200_QR_FORCE_HOUSEHOLDER=1 sends EVERY panel QR through the slow path (LAPACK's dgeqr2 + dorg2r run as column
+    operations on row ranges of the device panel).  On full-rank blocks that path must give LAPACK's factors, so the
+    whole solve matches the oracle at the usual 1e-6."""
+    monkeypatch.setenv("KB200_QR_FORCE_HOUSEHOLDER", "1")
+    A, _ = O.kron_unsymmetric(8)
+    A = sp.csr_matrix(A)
+    B = A @ _rhs(A.shape[0], p, 3)
+    ws = kb.BlockGmresWorkspace(A.shape[0], A.shape[0], p, memory=6)
+    ws.solve(A, B, history=True)
+    X, st, nfall = ws.x, ws.stats, ws.qr_fallbacks
+    ws.free()
+    Xo, so = O.block_gmres(A, B, memory=6)
+    assert nfall >= st.niter
+    _check(st, X, so, Xo)
+
+
+@pytest.mark.parametrize("p", [3, 4])
+def test_block_gmres_rank_deficient_block_falls_back(kb, O, p):
+    """Two identical right-hand sides: the Gram matrix of the block is singular and the panel QR takes the Householder
+    path, which completes the basis with a direction that only rounding determines (LAPACK's does too) -- so the
+    iterates are not comparable with the oracle's beyond the first residual; what must hold is that the fallback is
+    counted, the recurrence residual is the true one, it never increases, and it ends near the oracle's."""
     A, b = O.sparse_laplacian(6)
-    B = np.stack([b, b, np.arange(len(b), dtype=float)], axis=1)
-    ws = kb.BlockGmresWorkspace(A.shape[0], A.shape[0], 3, memory=10)
+    cols = [b, b, np.arange(len(b), dtype=float), np.cos(np.arange(len(b)))][:p]
+    B = np.stack(cols, axis=1)
+    ws = kb.BlockGmresWorkspace(A.shape[0], A.shape[0], p, memory=12)
     ws.solve(A, B, itmax=12, history=True)
     X, st = ws.x, ws.stats
-    assert ws.qr_fallbacks >= 1                       # the fallback is counted, never silent
+    assert ws.qr_fallbacks >= 1                       # counted, never silent
     ws.free()
+    Xo, so = O.block_gmres(A, B, memory=12, itmax=12)
+    r = np.asarray(st.residuals)
+    assert np.isfinite(r).all() and np.isfinite(X).all()
+    assert r[0] == pytest.approx(so["residuals"][0], rel=1e-12)
+    assert np.all(np.diff(r) <= 1e-9 * r[0])          # GMRES residuals are monotone
+    assert np.linalg.norm(B - A @ X) == pytest.approx(r[-1], rel=1e-6, abs=1e-9 * r[0])
+    assert r[-1] <= 10 * so["residuals"][-1] + 1e-9 * r[0]
     Bok = np.stack([b, np.cos(np.arange(len(b))), np.arange(len(b), dtype=float)], axis=1)
     ws = kb.BlockGmresWorkspace(A.shape[0], A.shape[0], 3, memory=10)
     ws.solve(A, Bok, history=True)
-    assert ws.stats.solved and ws.qr_fallbacks == 0   # well-posed blocks never leave the device
+    assert ws.stats.solved and ws.qr_fallbacks == 0   # well-posed blocks never leave the fast path
     ws.free()
-    # the same with an even block size (register-resident kernels on row ranges of the panel)
-    B4 = np.stack([b, np.cos(np.arange(len(b))), b, np.arange(len(b), dtype=float)], axis=1)
-    ws = kb.BlockGmresWorkspace(A.shape[0], A.shape[0], 4, memory=10)
-    ws.solve(A, B4, itmax=10, history=True)
-    X4, st4 = ws.x, ws.stats
-    assert ws.qr_fallbacks >= 1
-    ws.free()
-    Xo4, so4 = O.block_gmres(A, B4, memory=10, itmax=10)
-    assert st4.niter == so4["niter"] and st4.status == so4["status"]
-    k4 = min(5, len(so4["residuals"]))
-    assert np.allclose(st4.residuals[:k4], so4["residuals"][:k4], rtol=1e-5, atol=1e-9 * so4["residuals"][0])
-    Xo, so = O.block_gmres(A, B, memory=10, itmax=12)
-    assert st.niter == so["niter"] and st.status == so["status"]
-    k = min(6, len(so["residuals"]))
-    assert np.allclose(st.residuals[:k], so["residuals"][:k], rtol=1e-5, atol=1e-9 * so["residuals"][0])
 
 
 def test_reference_test_block_program():
