@@ -32,7 +32,7 @@ for p in ps:
     ws.set_operator((rp, ci, va))
     g = torch.Generator(device=dev)
     g.manual_seed(1234)
-    B = torch.randn((n, p), dtype=torch.float64, device=dev, generator=g)      # full-rank block (a rank-deficient one takes the host QR)
+    B = torch.randn((n, p), dtype=torch.float64, device=dev, generator=g)      # full-rank block (a rank-deficient one takes the 4p-pass Householder path)
     kw = dict(atol=0.0, rtol=0.0, itmax=mem * cycles, restart=True)
     ws.solve(None, B, **kw)
     st = torch.cuda.ExternalStream(kb.lib().krylov_b200_stream(ws._h), device=dev)
