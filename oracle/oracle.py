@@ -461,3 +461,63 @@ def singular_consistent(n=10):
     A[1, :] = 1.0
     A[0, :] = 1.0
     return sp.csr_matrix(A), A @ np.ones(n)
+
+
+# ---- more generators of test/test_utils.jl and test/get_div_grad.jl (restated; dense ones returned as CSR) ------
+def nonsymmetric_definite(n=10):
+    """test/test_utils.jl:72-80 (real case): n on the diagonal, +1 above, -1 below; b = A [1..n]."""
+    A = np.where(np.eye(n, dtype=bool), float(n), np.where(np.triu(np.ones((n, n), bool), 1), 1.0, -1.0))
+    return sp.csr_matrix(A), A @ np.arange(1.0, n + 1)
+
+
+def nonsymmetric_indefinite(n=10):
+    """test/test_utils.jl:83-91 (real case): diagonal n (-1)^(i j) with 1-based i = j."""
+    A = np.where(np.triu(np.ones((n, n), bool), 1), 1.0, -1.0)
+    for i in range(1, n + 1):
+        A[i - 1, i - 1] = n * (-1.0) ** (i * i)
+    return sp.csr_matrix(A), A @ np.arange(1.0, n + 1)
+
+
+def two_preconditioners(n=10, m=20):
+    """test/test_utils.jl:310-316: A = ones + (n-1) I, b = ones, M = I/sqrt(n), N = I/sqrt(m) (as diagonals)."""
+    A = np.ones((n, n)) + (n - 1) * np.eye(n)
+    return sp.csr_matrix(A), np.ones(n), np.full(n, 1 / math.sqrt(n)), np.full(n, 1 / math.sqrt(m))
+
+
+def system_zero_quad(n=2):
+    """test/test_utils.jl:57-69: diag(1, -1, 0, ...), b = e1 + e2, so that b'Ab = 0."""
+    A = np.zeros((n, n)); A[0, 0] = 1.0; A[1, 1] = -1.0
+    b = np.zeros(n); b[0] = b[1] = 1.0
+    return sp.csr_matrix(A), b
+
+
+def bc_breakdown():
+    """test/test_utils.jl:204-209: b'c = 0."""
+    A = sp.csr_matrix(np.array([[1.0, 2.0], [3.0, 4.0]]))
+    return A, np.array([0.0, 1.0]), np.array([1.0, 0.0])
+
+
+def polar_poisson(n=50, m=50):
+    """test/get_div_grad.jl:141-176 with f = -3 cos(theta), g = 0 (test/test_utils.jl:286-291), R = 1."""
+    R = 1.0
+    dr = 2 * R / (2 * n + 1)
+    r = [(i - 0.5) * dr for i in range(1, n + 2)]
+    dth = 2 * math.pi / m
+    th = [(j - 1) * dth for j in range(1, m + 2)]
+    lam = np.array([1 / (2 * (k - 0.5)) for k in range(1, n + 1)])
+    beta = np.array([1 / ((k - 0.5) ** 2 * dth ** 2) for k in range(1, n + 1)])
+    D = sp.diags(beta)
+    T = sp.diags([1.0 - lam[1:], -2.0 * np.ones(n), 1.0 + lam[:-1]], [-1, 0, 1])
+    A = sp.lil_matrix((n * m, n * m))
+    for k in range(m):
+        A[k * n:(k + 1) * n, k * n:(k + 1) * n] = (T - 2 * D).toarray()
+        if k <= m - 2:
+            A[(k + 1) * n:(k + 2) * n, k * n:(k + 1) * n] = D.toarray()
+            A[k * n:(k + 1) * n, (k + 1) * n:(k + 2) * n] = D.toarray()
+    A[(m - 1) * n:m * n, 0:n] = D.toarray()
+    A[0:n, (m - 1) * n:m * n] = D.toarray()
+    b = np.zeros(n * m)
+    for i in range(n):
+        for j in range(m):
+            b[i + n * j] = dr * dr * (-3.0 * math.cos(th[j]))
+    return sp.csr_matrix(A), b

@@ -453,3 +453,42 @@ def test_cr_reference_cases(O):
     assert st["status"] == "b is a zero-curvature direction" and np.linalg.norm(x) == 0 and st["solved"] and st["niter"] == 0
     with pytest.raises(ArithmeticError):
         O.cr(A, b, linesearch=True, radius=1.0)
+
+
+# ---- remaining generator-driven cases of the reference's solver tests -----------------------------------------
+@pytest.mark.parametrize("name", ["gmres", "bicgstab", "cgs", "fom", "fgmres", "dqgmres", "diom"])
+def test_unsymmetric_family_on_the_reference_generators(O, name):
+    """test_gmres.jl / test_bicgstab.jl / test_cgs.jl / test_fom.jl / test_fgmres.jl / test_dqgmres.jl / test_diom.jl:
+    nonsymmetric definite and indefinite systems, split preconditioning, Poisson in polar coordinates."""
+    f = getattr(O, name)
+    tol = 1e-6
+    for gen in (O.nonsymmetric_definite, O.nonsymmetric_indefinite):
+        A, b = gen()
+        x, st = f(A, b)
+        assert resid(A, x, b) <= tol and st["solved"], gen.__name__
+    A, b, M, N = O.two_preconditioners()
+    x, st = f(A, b, M=M, N=N)
+    assert np.linalg.norm(M * (b - A @ x)) / np.linalg.norm(M * b) <= tol and st["solved"]
+    if name != "cgs":                                   # test_cgs.jl has no polar_poisson case (CGS diverges on it)
+        A, b = O.polar_poisson(12, 12)
+        kw = dict(reorthogonalization=True) if name in ("gmres", "fom", "fgmres", "dqgmres", "diom") else {}
+        if name in ("dqgmres", "diom"):
+            kw["memory"] = 100                          # test_dqgmres.jl / test_diom.jl: memory = 100
+        x, st = f(A, b, **kw)
+        assert resid(A, x, b) <= tol and st["solved"]
+    A, b, c = O.bc_breakdown()
+    if name in ("bicgstab", "cgs"):
+        x, st = f(A, b, c=c)
+        assert st["status"] == "Breakdown bᴴc = 0"
+
+
+def test_cg_cr_on_system_zero_quad(O):
+    """test_cr.jl (system_zero_quad) and the same system through cg!: b'Ab = 0 at the first iteration."""
+    A, b = O.system_zero_quad()
+    x, st = O.cr(A, b, linesearch=True)
+    assert st["niter"] == 0 and st["status"] == "b is a zero-curvature direction" and st["npc_dir"] @ (A @ st["npc_dir"]) == 0
+    x, st = O.cg(A, b, linesearch=True)                 # cg.jl:198-209: both flags set, the later status wins (:272-275)
+    assert st["status"] == "zero curvature detected" and st["niter"] == 0 and st["indefinite"] and st["npcCount"] == 1
+    assert not st["inconsistent"] and np.array_equal(x, b)
+    x, st = O.cg(A, b)                                  # zero curvature without linesearch: inconsistent = true
+    assert st["status"] == "zero curvature detected" and st["inconsistent"] and not st["indefinite"]
