@@ -77,3 +77,17 @@ def test_no_cpu_fallback_without_gpu():
     assert L.krylov_workspace_create(_lib.KRYLOV_CG, 4, 4, 1, 0, None, C.byref(ws)) == -1
     assert not ws.value
     assert "no usable CUDA device" in _lib.last_error()
+
+
+def test_fortran_interface_names_are_exported():
+    """interfaces/include/krylov.f90 binds these C names (bind(c, name='...')): a Fortran caller of the reference links
+    against libkrylov_b200.so with the reference's own module, unchanged (Fortran header parity).
+    No Fortran compiler exists in this image, so only the symbol contract is checked."""
+    names = """krylov_block_elapsed_time krylov_block_get_X krylov_block_is_solved krylov_block_niter krylov_block_solve
+               krylov_block_warm_start krylov_block_workspace_create krylov_block_workspace_free krylov_default_options
+               krylov_default_workspace_options krylov_elapsed_time krylov_get_version krylov_get_x krylov_get_y
+               krylov_is_solved krylov_niter krylov_solve krylov_warm_start krylov_warm_start2 krylov_workspace_create
+               krylov_workspace_free""".split()
+    L = C.CDLL(_lib.SO_PATH)
+    for n in names:
+        assert hasattr(L, n), n
