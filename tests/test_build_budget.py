@@ -1,0 +1,80 @@
+"""CPU: register / spill / SASS budgets of the hot kernels, read from the build artefacts (`-Xptxas -v` logs and
+cuobjdump).  Guards the occupancy assumptions the persistent grids rely on: a kernel that silently grows past its
+register budget drops a resident CTA per SM (measured once as a 2.2x slowdown of cg_k1, profiles/README.md)."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "krylov.jl_b200", "build")
+
+
+def _entries(name):
+    path = os.path.join(BUILD, name + ".ptxas.log")
+    if not os.path.exists(path):
+        pytest.skip("build logs absent: run __graft_entry__.build()")
+    txt = open(path).read()
+    out = []
+    for m in re.finditer(r"Compiling entry function '(\S+)' for 'sm_100a'.*?Used (\d+) registers[^\n]*", txt, re.S):
+        spill = [int(v) for v in re.findall(r"(\d+) bytes spill", m.group(0))]
+        out.append((m.group(1), int(m.group(2)), max(spill or [0])))
+    assert out, path
+    return out
+
+
+def _demangle(names):
+    if not shutil.which("c++filt"):
+        return {n: n for n in names}
+    res = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, text=True).stdout.splitlines()
+    return dict(zip(names, res))
+
+
+def test_fused_cg_kernels_fit_three_ctas_per_sm():
+    ents = _entries("cg_fused")
+    dm = _demangle([e[0] for e in ents])
+    k1 = [(dm[n], r, s) for n, r, s in ents if "cg_k1_tma<double" in dm[n] and ", 3, " in dm[n]]
+    assert k1, "the 3-CTA/SM variants of cg_k1_tma are gone"
+    for name, regs, spill in k1:
+        assert regs <= 72, (name, regs)                                # 288 threads x 72 regs x 3 CTAs fit the 64K file
+        # the single-GPU kernels (MODE 0 plain, 2 Jacobi) hold everything in registers; the row-partitioned variant
+        # (MODE 1) may park the few words its in-kernel all-reduce needs
+        assert spill == 0 if ("<double, 0, 3" in name or "<double, 2, 3" in name) else spill <= 16, (name, spill)
+    for name, regs, spill in [(dm[n], r, s) for n, r, s in ents if "cg_k2<" in dm[n]]:
+        assert spill == 0 and regs <= 64, (name, regs, spill)
+
+
+def test_staged_spmv_family_register_budget():
+    for obj, pat in (("spmv", "spmv_tma_kernel<double"), ("fused_phases", "spmv_epi_tma<double"), ("block", "spmm_tma_kernel<double")):
+        ents = _entries(obj)
+        dm = _demangle([e[0] for e in ents])
+        hit = [(dm[n], r, s) for n, r, s in ents if pat in dm[n]]
+        assert hit, pat
+        for name, regs, spill in hit:
+            assert spill <= 16, (name, spill)                          # at most the finaliser's scalars
+            assert regs <= 96, (name, regs)                            # >= 2 CTAs of 288 threads per SM
+            if "XPlain" in name or "spmm_tma_kernel<double, 8>" in name:
+                assert regs <= 72, (name, regs)                        # the single-GPU variants keep 3 CTAs per SM
+
+
+def test_block_fast_kernels_do_not_spill():
+    ents = _entries("block")
+    dm = _demangle([e[0] for e in ents])
+    fast = [(dm[n], r, s) for n, r, s in ents if "panel_fast_kernel<" in dm[n] and dm[n].rstrip(")").split(",")[5].strip().startswith("false")]
+    assert fast
+    for name, regs, spill in fast:
+        assert spill == 0, (name, regs, spill)                         # the default (non-prefetch) variants
+
+
+def test_tma_and_mbarrier_instructions_present_in_sass():
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    for obj in ("cg_fused", "spmv", "fused_phases", "block"):
+        path = os.path.join(BUILD, obj + ".o")
+        if not os.path.exists(path):
+            pytest.skip("objects absent: run __graft_entry__.build()")
+        sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+        assert "UBLKCP" in sass, obj                                   # 1-D bulk TMA copies (cp.async.bulk)
+        assert "SYNCS.PHASECHK" in sass or "SYNCS.ARRIVE" in sass, obj  # mbarrier wait / arrive
