@@ -30,3 +30,23 @@ for name in cases.NAMES:
                      x_head=[float(v) for v in x[:8]])
 json.dump(out, open(os.path.join(HERE, "oracle_histories.json"), "w"), indent=0)
 print({k: (v["niter"], v["status"]) for k, v in out.items()})
+
+
+# ---- block_gmres (oracle/krylov_oracle_block.h): n x p blocks, residual = Frobenius norm ----------------------
+import scipy.sparse as sp  # noqa: E402
+from krylov_b200 import problems as P  # noqa: E402
+
+
+def block_case(p, **kw):
+    rp, ci, va = P.kron_unsymmetric_csr(8)
+    n = len(rp) - 1
+    A = sp.csr_matrix((va, ci, rp), shape=(n, n))
+    B = A @ np.cos(np.outer(np.arange(1, n + 1), np.arange(1, p + 1)))        # deterministic full-rank block
+    X, st = O.block_gmres(A, B, **kw)
+    return dict(p=p, kw=kw, niter=st["niter"], status=st["status"], residuals=[float(v) for v in st["residuals"]],
+                xnorm=float(np.linalg.norm(X)), x_head=[float(v) for v in X[:4].ravel()])
+
+
+blk = {f"block_gmres_kron8_p{p}_{'restart' if r else 'full'}": block_case(p, memory=6, restart=r) for p in (2, 3, 8) for r in (False, True)}
+json.dump(blk, open(os.path.join(HERE, "oracle_block.json"), "w"), indent=0)
+print({k: (v["niter"], v["status"]) for k, v in blk.items()})
