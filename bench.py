@@ -145,6 +145,177 @@ def best_cpu_threads(N):
     return best, sweep
 
 
+def affinity_threads(cap=32):
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    return max(1, min(cap, avail))
+
+
+def parity_block(gpu_hist, N, iters, tol=1e-6):
+    """Residual-norm history of the GPU solve vs the CPU oracle's on the SAME benchmark-size problem (outside the
+    timed region): the oracle runs `iters` iterations of cg.jl:195-268 with OpenMP (its dots then differ from the
+    sequential order by O(eps), far below the 1e-6 bar of north_star)."""
+    from krylov_b200.problems import div_grad_csr
+    from oracle import oracle as O
+    if N not in _CPU_PROBLEM:
+        _CPU_PROBLEM[N] = div_grad_csr(N) + (np.ones(N ** 3),)
+    rp, ci, va, b = _CPU_PROBLEM[N]
+    threads = affinity_threads()
+    t, _, _, hist = O.cg_timed(rp, ci, va, b, iters, threads, history=True)
+    g = np.asarray(gpu_hist, dtype=np.float64)
+    k = min(len(g), len(hist))
+    rel = np.abs(g[:k] - hist[:k]) / np.maximum(np.abs(hist[:k]), 1e-300)
+    dev = float(rel.max()) if k else float("inf")
+    return dict(against="oracle (CPU restatement of cg.jl:195-268), same matrix and b", iters_compared=k - 1,
+                niter_equal=bool(len(g) == len(hist)), max_rel_dev=dev, tol=tol, ok=bool(len(g) == len(hist) and dev <= tol),
+                oracle_threads=threads, oracle_seconds=round(t, 2))
+
+
+def golden_parity(gpu_hist, name, tol=1e-6):
+    """cfg5 (n ~ 1e8) is too large for an in-run oracle solve: compare with the committed oracle history
+    (tests/golden/<name>.json, generated by tests/golden/gen_bench_golden.py)."""
+    path = os.path.join(ROOT, "tests", "golden", name + ".json")
+    if not os.path.exists(path):
+        return dict(against=path, ok=None, note="golden file missing")
+    gold = np.asarray(json.load(open(path))["residuals"], dtype=np.float64)
+    g = np.asarray(gpu_hist, dtype=np.float64)
+    k = min(len(g), len(gold))
+    rel = np.abs(g[:k] - gold[:k]) / np.maximum(np.abs(gold[:k]), 1e-300)
+    dev = float(rel.max()) if k else float("inf")
+    return dict(against=f"tests/golden/{name}.json (oracle history)", iters_compared=k - 1, max_rel_dev=dev, tol=tol,
+                ok=bool(k > 1 and dev <= tol))
+
+
+def device_random_csr(torch, dev, n, per_row=20, seed=1234, shift=3.0):
+    """BASELINE config 4 matrix (problems.random_csr: numpy default_rng(seed), indices first, then values,
+    duplicates summed, +shift on the diagonal) ASSEMBLED on the GPU: the host only draws the random numbers.
+    tests/test_gpu_formats.py checks it entry by entry against the SciPy assembly."""
+    rng = np.random.default_rng(seed)
+    cols = rng.integers(0, n, size=(n, per_row), dtype=np.int64)
+    vals = rng.uniform(-1.0, 1.0, size=(n, per_row)).astype(np.float32)
+    c = torch.from_numpy(cols.reshape(-1)).to(dev)
+    v = torch.from_numpy(vals.reshape(-1)).to(dev)
+    del cols, vals
+    r = torch.arange(n, device=dev, dtype=torch.int64).repeat_interleave(per_row)
+    d = torch.arange(n, device=dev, dtype=torch.int64)
+    key = torch.cat([r * n + c, d * n + d])
+    val = torch.cat([v, torch.full((n,), shift, dtype=torch.float32, device=dev)])
+    del r, c, v
+    key, order = torch.sort(key, stable=True)
+    val = val[order]
+    del order
+    ukey, inv = torch.unique_consecutive(key, return_inverse=True)
+    out = torch.zeros(ukey.numel(), dtype=torch.float32, device=dev)
+    out.index_add_(0, inv, val)
+    rows = ukey // n
+    ci = (ukey - rows * n).to(torch.int32)
+    counts = torch.bincount(rows, minlength=n)
+    rp = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    rp[1:] = torch.cumsum(counts, 0)
+    return rp.to(torch.int32), ci, out
+
+
+def extra_records(kb, torch, dev, peak):
+    """BASELINE configs 3 and 4 on the same GPU (it/s + fraction of their own algorithmic-byte roofline,
+    SURVEY.md 8d).  Not the headline metric: reported under "extra" on the N = 1 line."""
+    from krylov_b200 import problems as P
+    out = []
+
+    def timed(ws, b, reps, **kw):
+        st = torch.cuda.ExternalStream(kb.lib().krylov_b200_stream(ws._h), device=dev)
+        for _ in range(2):
+            ws.solve(None, b, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        l0 = ws.launches
+        e0.record(st)
+        for _ in range(reps):
+            ws.solve(None, b, **kw)
+        e1.record(st)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps, ws.stats.niter, (ws.launches - l0) / reps
+
+    # cfg3: gmres!(memory = 30, restart) on kron_unsymmetric(215), b = A*ones; 2 full cycles per solve
+    N = 215
+    rp, ci, va = P.kron_unsymmetric_csr(N, xp=torch, device=dev)
+    n, nnz = N ** 3, int(va.numel())
+    b = P.csr_matvec_ones(rp, ci, va)
+    torch.cuda.synchronize()
+    ws = kb.GmresWorkspace(n, n, np.float64, memory=30, device="cuda")
+    ws.set_operator((rp, ci, va))
+    sec, niter, launches = timed(ws, b, 3, atol=0.0, rtol=0.0, itmax=60, restart=True)
+    ws.free()
+    B = nnz * 12 + (n + 1) * 4 + 2 * n * 8 + 64 * n * 8
+    its = niter / sec
+    out.append(dict(solver="gmres(30)", config="cfg3: kron_unsymmetric(215) Float64, restart, 60 inner iterations per solve",
+                    value=its, unit="it/s", launches_per_iteration=launches / niter,
+                    roofline=dict(bound="hbm", bytes_per_iteration=B, achieved=B * its / 1e9, peak=peak, unit="GB/s",
+                                  frac=B * its / 1e9 / peak, note="B_spmv + 64 n v (cycle average of the MGS sweep)")))
+    del rp, ci, va, b
+    torch.cuda.empty_cache()
+    # cfg4: bicgstab! Float32 on the random CSR (n = 5e6, 20 draws/row + diagonal), b = A*ones; 50 iterations
+    n = 5_000_000
+    t0 = time.perf_counter()
+    rp, ci, va = device_random_csr(torch, dev, n)
+    nnz = int(va.numel())
+    b = P.csr_matvec_ones(rp, ci, va)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+    ws = kb.BicgstabWorkspace(n, n, np.float32, device="cuda")
+    ws.set_operator((rp, ci, va))
+    sec, niter, launches = timed(ws, b, 3, atol=0.0, rtol=0.0, itmax=50)
+    ws.free()
+    B = 2 * (nnz * 8 + (n + 1) * 4) + 20 * n * 4
+    its = niter / sec
+    out.append(dict(solver="bicgstab", config=f"cfg4: random CSR n={n} nnz={nnz} Float32, 50 iterations per solve",
+                    value=its, unit="it/s", launches_per_iteration=launches / niter, matrix_generate_s=round(gen_s, 2),
+                    roofline=dict(bound="hbm", bytes_per_iteration=B, achieved=B * its / 1e9, peak=peak, unit="GB/s",
+                                  frac=B * its / 1e9 / peak,
+                                  note="2 x matrix + 20 n v; the x gather of a RANDOM matrix is L2-sector bound "
+                                       "(profiles/README.md)")))
+    del rp, ci, va, b
+    torch.cuda.empty_cache()
+    return out
+
+
+def cfg5_single(kb, torch, dev, steps, peak):
+    """BASELINE config 5 (get_div_grad(464): n = 99 897 344) on ONE GPU -- the denominator of north_star's
+    ">= 6x at 8 GPUs"; the multi-GPU runs carry the same key (krylov_b200/dist.py)."""
+    N, iters = WORKLOADS["poisson464"]
+    n, nnz = N ** 3, 7 * N ** 3 - 6 * N ** 2
+    rp, ci, va = build_problem(N, torch, dev)
+    b = torch.ones(n, dtype=torch.float64, device=dev)
+    ws = kb.CgWorkspace(n, n, np.float64, device="cuda")
+    ws.set_operator((rp, ci, va))
+    del rp, ci, va
+    torch.cuda.empty_cache()
+    kw = dict(atol=0.0, rtol=0.0, itmax=iters)
+    stream = torch.cuda.ExternalStream(kb.lib().krylov_b200_stream(ws._h), device=dev)
+    for _ in range(3):
+        ws.solve(None, b, **kw)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps):
+        ws.solve(None, b, **kw)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    ws.solve(None, b, history=True, **kw)
+    hist = list(ws.stats.residuals)
+    ws.free()
+    del b
+    torch.cuda.empty_cache()
+    v = steps * iters / (ms * 1e-3)
+    B = algorithmic_bytes_cg(n, nnz)
+    return dict(workload=f"cg! on get_div_grad({N},{N},{N}) (n = {n}, nnz = {nnz}) on 1 GPU, {iters} iterations per step, "
+                         f"{steps} steps", value=v, unit="it/s", n_gpus=1, ms_per_step=ms / steps, frac=B * v / 1e9 / peak,
+                bytes_per_iteration=B, parity=golden_parity(hist, "bench_cg_poisson464"),
+                speedup_note="north_star target: value at 8 GPUs >= 6 x this value (same key on the N=8 line)")
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path.  Julia is not in this image, so the timed code is the
     oracle port (oracle/krylov_oracle.c), threaded over all host cores it can use."""
@@ -179,7 +350,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("KB200_WORKLOAD", "poisson215"), choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg and the parity block")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg3 / cfg4 extra records")
+    ap.add_argument("--no-cfg5", dest="no_cfg5", action="store_true", help="skip the cfg5 (n ~ 1e8) record")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -191,7 +364,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from krylov_b200 import dist
-        return dist.bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler)
+        return dist.bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler, parity_block, golden_parity)
     if kb.device_count() < 1:
         raise SystemExit("bench.py needs a B200: libkrylov_b200 has no CPU path")
     torch.cuda.set_device(local)
@@ -232,14 +405,19 @@ def main():
     B = algorithmic_bytes_cg(n, nnz)
     peak, peak_src = hbm_peak()
     achieved = B * its / (ms * 1e-3) / 1e9
-    # per-kernel breakdown: launches 8..39 of each fused kernel bracketed by CUDA events inside the library
+    # phase breakdown of the persistent kernel (cg_persist): phase A = SpMV + p update + <p,Ap> (+ x update),
+    # phase B = r update + <r,r>; each measured inside the kernel (%globaltimer), its closing grid barrier included
     ws.solve(None, b, time_kernels=True, **solve_kw)
     k1_ms, k2_ms, timed = ws.kernel_times
-    B_k1 = nnz * 12 + (n + 1) * 4 + 6 * n * 8      # matrix + read r,p,x + write p,Ap,x  (x update rides in K1)
+    B_k1 = nnz * 12 + (n + 1) * 4 + 6 * n * 8      # matrix + read r,p,x + write p,Ap,x  (x update rides in phase A)
     B_k2 = 3 * n * 8                               # read r,Ap + write r
-    kernels = dict(cg_k1_tma=dict(ms=k1_ms, bytes=B_k1, GBs=B_k1 / (k1_ms * 1e-3) / 1e9 if k1_ms else None),
-                   cg_k2=dict(ms=k2_ms, bytes=B_k2, GBs=B_k2 / (k2_ms * 1e-3) / 1e9 if k2_ms else None),
-                   timed_iterations=timed, share_k1=k1_ms / (k1_ms + k2_ms) if k1_ms else None)
+    kernels = dict(phase_a=dict(ms=k1_ms, bytes=B_k1, GBs=B_k1 / (k1_ms * 1e-3) / 1e9 if k1_ms else None),
+                   phase_b=dict(ms=k2_ms, bytes=B_k2, GBs=B_k2 / (k2_ms * 1e-3) / 1e9 if k2_ms else None),
+                   timed_iterations=timed, share_a=k1_ms / (k1_ms + k2_ms) if k1_ms else None,
+                   kernel="cg_persist (one cooperative launch per 16 iterations)")
+    # history of the same solve for the parity block (not timed)
+    ws.solve(None, b, history=True, **solve_kw)
+    gpu_hist = list(ws.stats.residuals)
 
     # ---- end-to-end arm: C ABI with pinned host buffers ---------------------
     wsh = kb.CgWorkspace(n, n, np.float64, device="host")
@@ -271,23 +449,44 @@ def main():
     line = dict(metric="CG iterations/s", value=value, unit="it/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
                 data="synthetic",
-                config=dict(workload=f"cg! fused (2 launches/iter) on get_div_grad({N},{N},{N}) Float64 int32-CSR, b=ones, "
+                config=dict(workload=f"cg! fused (persistent cooperative kernel) on get_div_grad({N},{N},{N}) Float64 int32-CSR, b=ones, "
                                      f"atol=rtol=0, itmax={iters} per step", n=n, nnz=nnz, iters_per_step=iters,
                             l2="inputs larger than L2 (matrix 0.87 GB vs 126 MB): no flush needed",
                             matrix_upload_s=round(upload_s, 3), matrix_generate_s=round(gen_s, 3)),
                 roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                              traffic_source="static: ncu --set full capture of this command, profiles/ncu_traffic.json",
                               peak_source=peak_src, bytes_per_iteration=B,
                               note="unit = one fused CG iteration (cg_k1 + cg_k2); B_cg from SURVEY.md 8(d)",
                               kernels=kernels),
                 clocks=clocks, e2e=e2e, gpu_launches=int(launches))
+    ws.free(); wsh.free()
+    del rp, ci, va
+    torch.cuda.empty_cache()
+    if not args.no_extra and args.workload == "poisson215":
+        try:
+            line["extra"] = extra_records(kb, torch, dev, peak)
+        except Exception as ex:
+            line["extra"] = [dict(error=f"{type(ex).__name__}: {ex}")]
+    if not args.no_cfg5 and args.workload == "poisson215":
+        try:
+            line["cfg5"] = cfg5_single(kb, torch, dev, max(2, args.steps // 2), peak)
+        except Exception as ex:
+            line["cfg5"] = dict(error=f"{type(ex).__name__}: {ex}")
+    parity_ok = True
     if not args.no_cpu:
         try:
             leg, _, _ = cpu_leg(N, iters, 1, budget_s=15.0)
             line["cpu_baseline"] = leg
         except Exception as ex:  # the CPU leg must never cost the GPU number
             line["cpu_baseline"] = dict(value=None, unit="it/s", cores=1, kind="port", sample=f"failed: {ex}")
+        try:
+            line["parity"] = golden_parity(gpu_hist, "bench_cg_poisson464") if N > 300 else parity_block(gpu_hist, N, iters)
+            parity_ok = line["parity"].get("ok") is not False and (line.get("cfg5", {}).get("parity") or {}).get("ok") is not False
+        except Exception as ex:
+            line["parity"] = dict(ok=None, note=f"failed: {type(ex).__name__}: {ex}")
     print(json.dumps(line))
-    ws.free(); wsh.free()
+    if not parity_ok:
+        raise SystemExit("parity FAILED: GPU residual history deviates from the oracle by more than 1e-6 (see the line above)")
 
 
 if __name__ == "__main__":

@@ -155,11 +155,12 @@ typedef struct {
   int ldiv;           /* 1: preconditioners are applied with ldiv! (kwarg `ldiv`)   */
   double etol;        /* MINRES; NaN -> sqrt(eps)                                   */
   double conlim;      /* MINRES; NaN -> 1/sqrt(eps)                                 */
-  int fused;          /* 1 (default): fused kernels when eligible; 0: primitives    */
+  int fused;          /* 1 (default): fused kernels when eligible (CG: one persistent cooperative launch per
+                       * batch of iterations); 2: fused CG as two launches per iteration; 0: primitives */
   int batch;          /* fused CG: iterations enqueued per host poll; 0 -> default  */
   int (*callback)(void *ws, void *user); /* kwarg `callback`; nonzero return = stop */
   void *callback_user;
-  int time_kernels;   /* fused CG: event-time launches 8..39 of each kernel (see krylov_b200_get_kernel_times) */
+  int time_kernels;   /* fused CG: time the two phases of the iteration (see krylov_b200_get_kernel_times) */
   int check_curvature; /* CG-Lanczos: kwarg `check_curvature` (src/cg_lanczos.jl:94)                            */
   double cr_gamma;     /* CR: kwarg `γ` (src/cr.jl:112); NaN -> sqrt(eps)                                        */
 } KrylovB200Options;
@@ -193,8 +194,16 @@ int krylov_b200_get_vector(void *ws, const char *name, void **dev_ptr);
 int krylov_b200_get_kernel_times(void *ws, double *out3);
 /* Kernels launched so far through this workspace's stream. */
 long long krylov_b200_launch_count(void *ws);
-/* The CUDA stream (cudaStream_t) all of this workspace's work is ordered on. */
+/* The CUDA stream (cudaStream_t) all of this workspace's work is ordered on.  It is a private NON-BLOCKING stream:
+ * nothing orders it against the caller's streams implicitly.  STREAM CONTRACT for device-pointer inputs (KRYLOV_CUDA
+ * workspaces: b, c, x0; location = 1 arrays of krylov_b200_set_operator_csr / set_preconditioner_diag): the data
+ * must be complete when the call is made, OR the producer must be ordered before this stream with
+ * krylov_b200_wait_stream (or cudaStreamWaitEvent on krylov_b200_stream(ws)).  Outputs need no care: every solve
+ * returns after synchronising its stream. */
 void *krylov_b200_stream(void *ws);
+/* Make the workspace's stream wait for everything enqueued so far on `producer_stream` (a cudaStream_t; NULL = the
+ * legacy default stream): records an event there and waits for it on krylov_b200_stream(ws).  Returns 0 / -1. */
+int krylov_b200_wait_stream(void *ws, void *producer_stream);
 
 /* ---- row-partitioned solves: one process per GPU, one workspace per process ----
  * The workspace is created with n = number of LOCAL rows; its CSR operator has

@@ -230,6 +230,45 @@ template <class T> void k_dot2(Ctx& c, int n, const T* a, const T* b, const T* u
   *r2 = reinterpret_cast<T*>(c.hscal)[1];
 }
 
+// ---------------------------------------------------------------------------
+// Row-partitioned solves: host-visible pieces of the communicator
+// ---------------------------------------------------------------------------
+__global__ void dist_sum_kernel(DistComm* dc, double v, double* out) {
+  const double r = dist_allreduce_sum_warp<double>(dc, v);
+  if (threadIdx.x == 0) *out = r;
+}
+
+// Sum of one host scalar over all ranks (every rank must call it the same number of times).
+double k_dist_sum(Ctx& c, double v) {
+  if (!c.dcomm) return v;
+  dist_sum_kernel<<<1, 32, 0, c.stream>>>(c.dcomm, v, reinterpret_cast<double*>(c.dscal) + 15);
+  KB_CUDA(cudaGetLastError());
+  c.launches++;
+  return read_slot<double>(c, 15);
+}
+
+// Every rank of a row-partitioned solve must take the SAME exit decision: a rank that stops on its own callback
+// result or wall clock leaves its peers spinning in the next reduction.  Flags are OR-ed over the ranks.
+void dist_agree_on_exit(Ctx& c, bool& user_exit, bool& overtimed) {
+  if (!c.dcomm) return;
+  const double s = k_dist_sum(c, (user_exit ? 1.0 : 0.0) + (overtimed ? 1024.0 : 0.0));
+  if (!(s == s)) return;                        // dead communicator: dist_check_alive raises
+  const long long code = (long long)s;
+  user_exit = (code % 1024) > 0;
+  overtimed = (code / 1024) > 0;
+}
+
+// A reduction that timed out kills the communicator (dist.cuh); every later reduction returns NaN at once.
+// The drivers call this before and after each solve and raise instead of handing NaNs to the caller.
+void dist_check_alive(Ctx& c) {
+  if (!c.dcomm) return;
+  int err = 0;
+  KB_CUDA(cudaMemcpyAsync(&err, &c.dcomm->error, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  c.sync();
+  if (err) throw std::runtime_error("cross-GPU reduction timed out: a peer rank stopped participating; the communicator of this "
+                                    "workspace is dead (free the workspace on every rank and create it again)");
+}
+
 #define INST(T)                                                                        \
   template T k_dot<T>(Ctx&, int, const T*, const T*);                                  \
   template T k_nrm2<T>(Ctx&, int, const T*);                                           \

@@ -166,6 +166,7 @@ SolveOpts map_opts(const Handle* h, const KrylovOptions* o) {
   s.etol = std::isnan(h->ext.etol) ? -1 : h->ext.etol;
   s.conlim = std::isnan(h->ext.conlim) ? -1 : h->ext.conlim;
   s.fused = h->ext.fused;
+  s.persist = h->ext.fused != 2;       // fused == 2: fused CG keeps the two-launch kernels (A/B measurements, tests)
   s.batch = h->ext.batch;
   s.callback = h->ext.callback;
   s.callback_user = h->ext.callback_user;
@@ -181,7 +182,14 @@ int do_solve(Handle* h, KrylovMatvec fA, KrylovMatvec fM, KrylovMatvec fN, const
   SolveOpts so = map_opts(h, opts);
   LinOp<T> A;
   if (fA) A = make_cb_op<T>(h, ws, fA, ud);
-  else if (h->csr) { A.kind = LinOp<T>::CSR; A.csr = &csr_of<T>(*h->csr); A.n = ws->n; }
+  else if (h->csr) {
+    A.kind = LinOp<T>::CSR; A.csr = &csr_of<T>(*h->csr); A.n = ws->n;
+    // columns: n local ones plus, row-partitioned, the halo entries -- anything beyond is an out-of-bounds gather
+    const long long ncols = (long long)ws->n + (ws->dist.world > 1 ? ws->dist.halo.nhalo : 0);
+    if (A.csr->n != ws->n || A.csr->max_col >= ncols)
+      throw std::runtime_error("CSR operator: size or column index inconsistent with the workspace (n = " + std::to_string(ws->n) +
+                               ", operator rows = " + std::to_string(A.csr->n) + ", largest column = " + std::to_string(A.csr->max_col) + ")");
+  }
   else throw std::runtime_error("no operator: pass matvec_A or attach one with krylov_b200_set_operator_csr");
   if (A.kind == LinOp<T>::CSR && A.csr->n != ws->n) throw std::runtime_error("(workspace.m, workspace.n) is inconsistent with size(A)");
   LinOp<T> M = make_cb_op<T>(h, ws, fM, ud), N = make_cb_op<T>(h, ws, fN, ud);
@@ -189,6 +197,7 @@ int do_solve(Handle* h, KrylovMatvec fA, KrylovMatvec fM, KrylovMatvec fN, const
   if (!fN && h->Ndiag) { N.kind = LinOp<T>::DIAG; N.diag = (const T*)h->Ndiag; }
   if (!b) throw std::runtime_error("b is NULL");
   const T* bd = stage_in<T>(h, ws, b, ws->bbuf);
+  dist_check_alive(ws->ctx);             // row-partitioned: refuse to start on a dead communicator
   switch (h->solver) {
     case S_CG: cg_solve<T>(*ws, A, bd, M, so); break;
     case S_MINRES: minres_solve<T>(*ws, A, bd, M, so); break;
@@ -211,6 +220,7 @@ int do_solve(Handle* h, KrylovMatvec fA, KrylovMatvec fM, KrylovMatvec fN, const
       break;
     }
   }
+  dist_check_alive(ws->ctx);             // a reduction timed out during the solve: raise instead of returning NaNs
   return 0;
 }
 
@@ -348,6 +358,28 @@ int krylov_warm_start2(void* ws, const void* x0, const void* y0, int nx, int ny)
   return -2;
 }
 
+// One destroy routine for both handle kinds: sets the handle's device, drops the operator and the preconditioner
+// diagonals, frees the pinned callback staging and the workspace.
+static void destroy_any(Handle* h) {
+  if (h->block) {
+    Ctx& c = ctx_of(h);
+    KB_CUDA(cudaSetDevice(c.device));
+    if (c.stream) cudaStreamSynchronize(c.stream);
+    h->csr.reset();
+    dev_free(h->Mdiag); dev_free(h->Ndiag);
+    if (h->hx) cudaFreeHost(h->hx);
+    if (h->hy) cudaFreeHost(h->hy);
+    if (h->dtype == KRYLOV_FLOAT64) block_ws_destroy<double>(BW<double>(h)); else block_ws_destroy<float>(BW<float>(h));
+    delete h;
+  } else if (h->dtype == KRYLOV_FLOAT64) {
+    destroy_handle<double>(h);
+  } else {
+    destroy_handle<float>(h);
+  }
+}
+
+// Frees a single-RHS workspace; a block handle passed here is forwarded to the block destroy path (the reference
+// keeps one key store for both kinds, c_stores.jl:1652-1655).  Unknown handle -> 1 (double free is safe).
 int krylov_workspace_free(void* ws) {
   Handle* h = nullptr;
   {
@@ -358,7 +390,7 @@ int krylov_workspace_free(void* ws) {
     g_handles.erase(it);
   }
   try {
-    if (h->dtype == KRYLOV_FLOAT64) destroy_handle<double>(h); else destroy_handle<float>(h);
+    destroy_any(h);
   } catch (const std::exception& e) { fail("krylov_workspace_free", e); }
   return 0;
 }
@@ -490,10 +522,7 @@ int krylov_block_workspace_free(void* ws) {
       std::lock_guard<std::mutex> lk(g_mu);
       g_handles.erase(ws);
     }
-    h->csr.reset();
-    dev_free(h->Mdiag); dev_free(h->Ndiag);
-    if (h->dtype == KRYLOV_FLOAT64) block_ws_destroy<double>(BW<double>(h)); else block_ws_destroy<float>(BW<float>(h));
-    delete h;
+    destroy_any(h);
     return 0;
   } catch (const std::exception& e) { return fail("krylov_block_workspace_free", e); }
 }
@@ -588,6 +617,7 @@ int krylov_b200_get_stats(void* ws, KrylovB200Stats* out) {
 int krylov_b200_get_history(void* ws, int which, double* out, int cap) {
   Handle* h = lookup_any(ws);
   if (!h) return fail("krylov_b200_get_history", "unknown workspace handle");
+  if (!out || cap < 0) return fail("krylov_b200_get_history", "bad arguments (out is NULL or cap < 0)");
   const Stats& s = stats_any(h);
   const std::vector<double>& v = which == 0 ? s.residuals : which == 1 ? s.Aresiduals : s.Acond;
   int k = (int)v.size() < cap ? (int)v.size() : cap;
@@ -623,12 +653,27 @@ void* krylov_b200_stream(void* ws) {
   return (void*)ctx_of(h).stream;
 }
 
+int krylov_b200_wait_stream(void* ws, void* producer_stream) {
+  try {
+    Handle* h = lookup_any(ws);
+    if (!h) return fail("krylov_b200_wait_stream", "unknown workspace handle");
+    Ctx& c = ctx_of(h);
+    KB_CUDA(cudaSetDevice(c.device));
+    cudaEvent_t ev;
+    KB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e1 = cudaEventRecord(ev, (cudaStream_t)producer_stream);
+    cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(c.stream, ev, 0) : e1;
+    cudaEventDestroy(ev);            // released once the wait has been satisfied
+    if (e2 != cudaSuccess) throw std::runtime_error(cudaGetErrorString(e2));
+    return 0;
+  } catch (const std::exception& e) { return fail("krylov_b200_wait_stream", e); }
+}
+
 // ------------------------------ row-partitioned solves --------------------
 }  // extern "C" (templates below need C++ linkage)
 namespace {
 constexpr int kIpcHandles = 6;   // r, p, p2, mailbox, halo_buf, xhalo
-constexpr size_t kMailDoubles = 2 * kMaxRanks;
-constexpr size_t kMailBytes = kMailDoubles * sizeof(double) + kMailDoubles * sizeof(unsigned long long);
+constexpr size_t kMailBytes = kMailWords * sizeof(unsigned long long);
 
 template <class T> int dist_init_t(Handle* h, int rank, int world, int nhalo, const int* halo_rank, const int* halo_off) {
   Workspace<T>* ws = W<T>(h);
@@ -683,6 +728,15 @@ template <class T> int dist_import_t(Handle* h, const void* all) {
   DistComm hc;
   memset(&hc, 0, sizeof(hc));
   hc.rank = D.rank; hc.world = D.world;
+  {
+    // spin budget of one cross-GPU reduction; a peer that stays away longer is treated as dead (dist.cuh)
+    const char* es = getenv("KB200_DIST_TIMEOUT_S");
+    double secs = es ? atof(es) : 30.0;
+    if (!(secs > 0)) secs = 30.0;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ws->ctx.device);
+    hc.timeout_cycles = (long long)(secs * 1e3 * (khz > 0 ? khz : 1965000));
+  }
   for (int k = 0; k < D.world; k++) {
     void* ptr[kIpcHandles];
     if (k == D.rank) {
@@ -696,8 +750,7 @@ template <class T> int dist_import_t(Handle* h, const void* all) {
     D.r_peer[k] = (T*)ptr[0]; D.bufA_peer[k] = (T*)ptr[1]; D.bufB_peer[k] = (T*)ptr[2];
     D.halo_buf_peer[k] = (T*)ptr[4];
     D.xhalo_peer[k] = (T*)ptr[5];
-    hc.mail_val[k] = (double*)ptr[3];
-    hc.mail_seq[k] = (unsigned long long*)((double*)ptr[3] + kMailDoubles);
+    hc.mail[k] = (unsigned long long*)ptr[3];
   }
   D.swapped = false;
   // plan of the general x-halo exchange (k_halo_exchange)

@@ -20,7 +20,7 @@
 // its K2, which starts after the pAp all-reduce that needs MY K1's partial
 // (published after all my halo reads); a peer's p buffer read here (p_k) is
 // rewritten only in its K1 two iterations later.
-#include "kb_internal.h"
+#include "solver_common.h"
 #include "spmv_tiles.cuh"
 
 namespace kb {
@@ -238,6 +238,280 @@ __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __r
   }
 }
 
+// ===========================================================================
+// Persistent cooperative variant: ONE launch runs a whole batch of iterations.
+//
+// Same arithmetic as cg_k1_tma + cg_k2 (phase A = K1 with the x update riding along, phase B = K2), but the two
+// kernel boundaries of an iteration become two grid-wide barriers inside a co-resident grid:
+//   * no launch gap / ramp-down / ramp-up between the phases;
+//   * the TMA producer warp runs AHEAD of the barrier: as soon as the consumers release the last ring slots of
+//     phase A it streams the first tiles of the NEXT iteration's phase A (the matrix does not change), so after
+//     the beta barrier the consumers find their first tiles already in shared memory;
+//   * each barrier carries its reduction: CTAs publish their partial, the last one to arrive re-reduces all
+//     partials in index order (deterministic), runs the scalar recurrence (cg_k1_finalize / cg_k2_finalize) and,
+//     row-partitioned, the cross-GPU all-reduce with a full warp, then releases the others.
+// Row-partitioned (MODE = kDist): the halo is STAGED instead of being pulled nonzero by nonzero.  At the start of
+// phase A every CTA's producer warp fetches its share of the halo list from the owners' r and p buffers with
+// coalesced system-scope loads (all in flight at once: one NVLink round trip), forms p_halo = r + beta p and
+// stores it into the local halo buffer; tiles with halo columns are ordered LAST in every CTA's tile sequence
+// (tile_order) and wait for the staging counter, so the exchange hides behind the interior tiles.
+//
+// Memory model: vectors written in one phase are read in the next through plain (coherent) loads after the
+// barrier's acquire; nothing that changes during the launch is read through the non-coherent path (__ldg).
+// ===========================================================================
+struct GridBar { unsigned count, gen, halo_ready, timed_iters; unsigned long long ns_a, ns_b; };
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double ld_sys(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Grid-wide barrier that also sums one value per thread over the whole grid.  `fin(total)` runs in warp 0 of the
+// LAST CTA to arrive (total valid in every lane of that warp) before anyone is released.  Returns false (in every
+// thread) if the wait timed out: the caller must leave the kernel.
+template <class T, class Fin>
+__device__ __forceinline__ bool grid_reduce_barrier(GridBar* gb, T v, T* part, T* sm, unsigned* sflag, Fin fin) {
+  const T mine = block_sum(v, sm);
+  if (threadIdx.x == 0) {
+    const unsigned g = *(volatile unsigned*)&gb->gen;      // read BEFORE arriving
+    __stcg(&part[blockIdx.x], mine);
+    __threadfence();
+    const unsigned t = atomicAdd(&gb->count, 1u);
+    sflag[0] = (t == gridDim.x - 1);
+    sflag[1] = g;
+  }
+  __syncthreads();
+  const bool last = sflag[0] != 0;
+  const unsigned g = sflag[1];
+  bool ok = true;
+  if (last) {
+    __threadfence();
+    T acc = T(0);
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) acc += __ldcg(&part[i]);
+    const T tot = block_sum(acc, sm);       // valid in every lane of warp 0
+    if (threadIdx.x < 32) {
+      fin(tot);
+      __syncwarp();
+      if (threadIdx.x == 0) {
+        gb->count = 0u;
+        __threadfence();
+        st_release_gpu_u32(&gb->gen, g + 1u);
+      }
+    }
+  } else if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (ld_acquire_gpu_u32(&gb->gen) == g) {
+      if (clock64() - t0 > 120000000000LL) { sflag[0] = 2; break; }     // ~1 minute: the grid is wedged
+    }
+  }
+  __syncthreads();
+  if (sflag[0] == 2) ok = false;
+  __syncthreads();           // sflag is rewritten by the next barrier
+  return ok;
+}
+
+template <class T>
+struct CgPeerTab {          // device-resident table of the peers' buffers (row-partitioned solves)
+  const T* r[kMaxRanks];
+  const T* p[2][kMaxRanks];  // in the order of CgPersistArgs::P
+};
+
+template <class T>
+struct CgPersistArgs {
+  T* r; T* P0; T* P1; T* Ap; T* x;     // P0 / P1: direction buffers; iteration k reads P[k & 1], writes the other
+  const T* mdiag;            // kJacobi
+  HaloMap halo;              // kDist ...
+  const CgPeerTab<T>* tab;
+  T* phalo;                  // local halo buffer: p_halo = r + beta p of the halo columns, rebuilt every iteration
+  const int* tile_order;     // interior tiles first, tiles with halo columns last (bit 31 set)
+  int max_iters;
+  int timed;                 // accumulate phase durations (CTA 0, %globaltimer) into the GridBar block
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <class T, int MODE, int MINB>
+__global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPersistArgs<T> a, CgState<T>* st, T* part,
+                                                                GridBar* gb, DistComm* dc) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ T sm[32];
+  __shared__ unsigned sflag[2];
+  volatile CgState<T>* vst = st;
+  if (vst->done) return;                       // uniform: st only changes inside the barriers below
+  TilePipe<T> P;
+  P.init(A, smem);
+  const int G = gridDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cnt = (A.ntiles - (int)blockIdx.x + G - 1) / G;         // grid <= ntiles: cnt >= 1
+  auto tile_at = [&](int j) -> int {
+    const int q = blockIdx.x + j * G;
+    return MODE == kDist ? __ldg(&a.tile_order[q]) : q;
+  };
+  const unsigned pre = (unsigned)min(P.S, cnt);
+  const uint64_t pol = l2_evict_first_policy();
+  unsigned ppos = 0, cpos = 0;
+  int passes = 0;
+  const int n = A.n;
+  for (int k = 0; k < a.max_iters; k++) {
+    const int iter = vst->iter;
+    const T beta = vst->beta, alpha_prev = vst->alpha;
+    const bool xup = iter > 0;                 // x += alpha_{k-1} p_{k-1} rides in phase A (cg.jl:239)
+    T* p_old = (iter & 1) ? a.P1 : a.P0;
+    T* p_new = (iter & 1) ? a.P0 : a.P1;
+    T dacc = T(0);
+    const bool timing = a.timed && blockIdx.x == 0 && tid == 0;
+    unsigned long long t0 = 0, t1 = 0;
+    if (timing) t0 = globaltimer_ns();
+    // ------------------------------ phase A (= K1) ------------------------------
+    if (warp == kConsumerWarps) {
+      if (MODE == kDist) {
+        // halo staging: this CTA's share of the halo list, all loads in flight at once
+        const int nh = a.halo.nhalo;
+        const int per = (nh + G - 1) / G;
+        const int h0 = (int)blockIdx.x * per, h1 = min(nh, h0 + per);
+        const int pb = iter & 1;
+        constexpr int U = 8;
+        for (int hb = h0 + lane; hb < h1; hb += 32 * U) {
+          T rv[U], pv[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const int h = hb + 32 * u;
+            if (h < h1) {
+              const int rk = __ldg(&a.halo.src_rank[h]), off = __ldg(&a.halo.src_off[h]);
+              rv[u] = ld_sys(a.tab->r[rk] + off);
+              pv[u] = ld_sys(a.tab->p[pb][rk] + off);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const int h = hb + 32 * u;
+            if (h < h1) __stcg(&a.phalo[h], add_rn(rv[u], mul_rn(beta, pv[u])));
+          }
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(&gb->halo_ready, 1u);
+      }
+      if (lane == 0) {
+        const unsigned target = (unsigned)(k + 1) * (unsigned)cnt + (k + 1 < a.max_iters ? pre : 0u);
+        tile_issue_until<T>(A, P, ppos, target, cnt, tile_at, pol);
+      }
+    } else {
+      const T* r = a.r;
+      const T* mdiag = a.mdiag;
+      const T* phalo = a.phalo;
+      const int nloc = a.halo.nloc;
+      const T* phalo_m = phalo - nloc;
+      auto gather = [&](int j) -> T {          // p_j = z_j + beta p_j (cg.jl:259 applied on the fly)
+        if (MODE == kDist) {
+          // halo column: the staged value p_halo[j - nloc] (already r + beta p); branch-free so that the batch of
+          // gathers stays straight-line: select the base pointer, clamp the p index, select a zero
+          const bool loc = j < nloc;
+          const T* base = loc ? r : phalo_m;
+          const T zv = base[j];
+          const T pv = p_old[loc ? j : 0];
+          return add_rn(zv, mul_rn(beta, loc ? pv : T(0)));
+        }
+        T z = r[j];
+        if (MODE == kJacobi) z = mul_rn(__ldg(&mdiag[j]), z);
+        return add_rn(z, mul_rn(beta, p_old[j]));
+      };
+      auto row_begin = [&](int row) {
+        RowPre<T> q;
+        q.po = p_old[row];
+        T z = r[row];
+        if (MODE == kJacobi) z = mul_rn(__ldg(&mdiag[row]), z);
+        q.pn = add_rn(z, mul_rn(beta, q.po));
+        q.xr = xup ? a.x[row] : T(0);
+        return q;
+      };
+      auto row_done = [&](int row, T acc, RowPre<T> q) {
+        p_new[row] = q.pn;
+        a.Ap[row] = acc;
+        if (xup) a.x[row] = add_rn(q.xr, mul_rn(alpha_prev, q.po));
+        dacc += q.pn * acc;
+      };
+      auto pre_tile = [&]() {
+        if (MODE == kDist) {
+          if (lane == 0) { while (ld_acquire_gpu_u32(&gb->halo_ready) < (unsigned)G) { } }
+          __syncwarp();
+        }
+      };
+      tile_consume_pass<T>(A, P, cpos, cnt, tile_at, gather, row_begin, row_done, pre_tile);
+    }
+    passes = k + 1;
+    bool ok = grid_reduce_barrier<T>(gb, dacc, part, sm, sflag, [&](T tot) {
+      if (MODE == kDist) {
+        tot = (T)dist_allreduce_sum_warp<T>(dc, (double)tot);
+        if (*(volatile int*)&dc->error) { if (lane == 0) { st->comm_error = 1; st->done = 1; } return; }
+      }
+      if (lane == 0) cg_k1_finalize(st, tot);
+    });
+    if (!ok || vst->done) break;
+    if (timing) t1 = globaltimer_ns();
+    // ------------------------------ phase B (= K2) ------------------------------
+    {
+      const T alpha = vst->alpha, nalpha = -alpha;
+      T* r = a.r;
+      const T* Ap = a.Ap;
+      const T* mdiag = a.mdiag;
+      T acc = T(0);
+      const int stride = G * kTileThreads;
+      int i = (int)blockIdx.x * kTileThreads + tid;
+      for (; i + 3 * stride < n; i += 4 * stride) {
+        T rv[4], av[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { rv[u] = r[i + u * stride]; av[u] = Ap[i + u * stride]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int j = i + u * stride;
+          const T rn = add_rn(rv[u], mul_rn(nalpha, av[u]));
+          r[j] = rn;
+          acc += rn * (MODE == kJacobi ? mul_rn(__ldg(&mdiag[j]), rn) : rn);
+        }
+      }
+      for (; i < n; i += stride) {
+        const T rn = add_rn(r[i], mul_rn(nalpha, Ap[i]));
+        r[i] = rn;
+        acc += rn * (MODE == kJacobi ? mul_rn(__ldg(&mdiag[i]), rn) : rn);
+      }
+      ok = grid_reduce_barrier<T>(gb, acc, part, sm, sflag, [&](T tot) {
+        if (MODE == kDist) {
+          tot = (T)dist_allreduce_sum_warp<T>(dc, (double)tot);
+          if (*(volatile int*)&dc->error) { if (lane == 0) { st->comm_error = 1; st->done = 1; } return; }
+        }
+        if (lane == 0) {
+          cg_k2_finalize(st, tot);
+          gb->halo_ready = 0u;                 // every consumer is past phase A: re-arm the staging counter
+        }
+      });
+      if (timing) {
+        const unsigned long long t2 = globaltimer_ns();
+        gb->ns_a += t1 - t0; gb->ns_b += t2 - t1; gb->timed_iters += 1;
+      }
+      if (!ok || vst->done) break;
+    }
+  }
+  if (warp == kConsumerWarps && lane == 0) tile_drain<T>(P, (unsigned)passes * (unsigned)cnt, ppos);
+}
+
 // Prologue of a row-partitioned solve in push mode: send the boundary entries of r_0 to the neighbours' halo
 // buffers.  The all-reduce of the prologue's <r,z> (launched next on the same stream) orders it before any K1.
 template <class T>
@@ -260,6 +534,61 @@ template <class T> void cg_dist_push_r(Workspace<T>& ws) {
 }
 
 // ---------------------------------------------------------------------------
+// Everything the fused loops need besides the solver's vectors is allocated when the workspace is created
+// (ws_create) -- the in-place call allocates nothing (test/test_allocations.jl:54-57).
+constexpr size_t kOffGridBar = 1024, kOffPeerTab = 2048;     // layout of the 4 KB device / pinned blocks
+
+template <class T> void cg_fused_prepare(Workspace<T>& ws) {
+  static_assert(sizeof(CgState<T>) <= kOffGridBar && sizeof(CgPeerTab<T>) <= kFusedBlockBytes - kOffPeerTab, "block layout");
+  if (!ws.fused_state) {
+    KB_CUDA(cudaMalloc(&ws.fused_state, kFusedBlockBytes));
+    KB_CUDA(cudaMemset(ws.fused_state, 0, kFusedBlockBytes));
+    KB_CUDA(cudaHostAlloc(&ws.fused_host, kFusedBlockBytes, cudaHostAllocDefault));
+  }
+  if (!ws.p2) ws.p2 = dev_alloc<T>((size_t)ws.n);
+  for (int i = 0; i < 2; i++)
+    if (!ws.fused_ev[i]) KB_CUDA(cudaEventCreateWithFlags(&ws.fused_ev[i], cudaEventDisableTiming));
+}
+
+// Row-partitioned persistent CG: order of the row tiles -- tiles without halo columns first, tiles that gather
+// halo entries last (bit 31 set), so that every CTA reaches its halo tiles at the END of phase A, long after the
+// halo staging of that iteration has finished.
+template <class T>
+__global__ void tile_halo_flags_kernel(Csr<T> A, int nloc, int* flags) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int t = warp; t < A.ntiles; t += nw) {
+    const int k0 = A.rowptr[t * kTileRows], k1 = A.rowptr[min(t * kTileRows + kTileRows, A.n)];
+    bool any = false;
+    for (int k = k0 + lane; k < k1; k += 32) any |= A.colind[k] >= nloc;
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) flags[t] = any ? 1 : 0;
+  }
+}
+
+template <class T> void cg_dist_tile_order(Workspace<T>& ws, const Csr<T>& A) {
+  if (ws.dist.tile_order && ws.dist.tile_order_for == (const void*)A.rowptr && ws.dist.tile_order_n == A.ntiles) return;
+  Ctx& c = ws.ctx;
+  if (ws.dist.tile_order) { cudaFree(ws.dist.tile_order); ws.dist.tile_order = nullptr; }
+  const int nt = A.ntiles;
+  KB_CUDA(cudaMalloc((void**)&ws.dist.tile_order, sizeof(int) * (size_t)(nt > 0 ? nt : 1)));
+  if (nt > 0) {
+    tile_halo_flags_kernel<T><<<sm_count() * 4, 256, 0, c.stream>>>(A, ws.n, ws.dist.tile_order);
+    KB_CUDA(cudaGetLastError());
+    std::vector<int> fl(nt), ord;
+    KB_CUDA(cudaMemcpyAsync(fl.data(), ws.dist.tile_order, sizeof(int) * nt, cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    ord.reserve(nt);
+    for (int t = 0; t < nt; t++) if (!fl[t]) ord.push_back(t);
+    for (int t = 0; t < nt; t++) if (fl[t]) ord.push_back((int)((unsigned)t | 0x80000000u));
+    KB_CUDA(cudaMemcpyAsync(ws.dist.tile_order, ord.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, c.stream));
+    c.sync();
+  }
+  ws.dist.tile_order_for = (const void*)A.rowptr;
+  ws.dist.tile_order_n = nt;
+}
+
+// ---------------------------------------------------------------------------
 template <class T> bool cg_fused_eligible(const LinOp<T>& A, const LinOp<T>& M, const SolveOpts& o) {
   // M = I, or a Diagonal M applied with mul! (the Jacobi case of SURVEY.md 8f-1), folded into the two kernels
   const bool m_ok = M.is_identity() || (M.kind == LinOp<T>::DIAG && !o.ldiv);
@@ -274,21 +603,19 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   const int n = ws.n;
   typedef CgState<T> St;
   const bool dist = ws.dist.world > 1;
-  if (!ws.fused_state) {
-    KB_CUDA(cudaMalloc(&ws.fused_state, sizeof(St)));
-    KB_CUDA(cudaHostAlloc(&ws.fused_host, 2 * sizeof(St), cudaHostAllocDefault));
-  }
-  if (!ws.p2) ws.p2 = dev_alloc<T>(n);
+  cg_fused_prepare<T>(ws);                      // no-op: done at workspace creation
   St* dst = (St*)ws.fused_state;
-  St* hst = (St*)ws.fused_host;
+  St* hst = (St*)ws.fused_host;                 // two read-back slots, kOffGridBar apart
+  auto hslot = [&](int i) -> St* { return (St*)((char*)hst + (size_t)i * kOffGridBar); };
 
   St init;
   memset(&init, 0, sizeof(init));
   init.gamma = gamma0; init.pNorm2 = gamma0; init.beta = T(0); init.eps_tol = eps_tol;
   init.rNorm = sqrt(gamma0); init.itmax = itmax; init.linesearch = o.linesearch ? 1 : 0;
-  hst[0] = init;
-  KB_CUDA(cudaMemcpyAsync(dst, &hst[0], sizeof(St), cudaMemcpyHostToDevice, c.stream));
-  c.sync();   // hst[0] is reused below as a read-back slot
+  *hslot(0) = init;
+  KB_CUDA(cudaMemcpyAsync(dst, hslot(0), sizeof(St), cudaMemcpyHostToDevice, c.stream));
+  KB_CUDA(cudaMemsetAsync((char*)ws.fused_state + kOffGridBar, 0, sizeof(GridBar), c.stream));
+  c.sync();   // slot 0 is reused below as a read-back slot
 
   const bool jac = ws.mdiag_fused != nullptr;
   const bool single_step = (o.callback != nullptr) || (o.timemax < 1e300) || o.verbose > 0;
@@ -368,9 +695,48 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   if (batch > kHist / 2) batch = kHist / 2;
   if (single_step) batch = 1;
 
-  cudaEvent_t ev[2];
-  KB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-  KB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  // Persistent cooperative variant (one launch per batch of iterations): whenever the tile plan is staged and x
+  // need not be current after every iteration.  KB200_PERSIST=0 keeps the two-launch kernels (A/B measurements).
+  const char* epers = getenv("KB200_PERSIST");
+  const bool persist = A.tma_ok && xup && !(epers && atoi(epers) == 0) && o.persist != 0;
+  typedef void (*KpFn)(Csr<T>, CgPersistArgs<T>, CgState<T>*, T*, GridBar*, DistComm*);
+  KpFn kp = nullptr;
+  int pgrid = 0;
+  CgPersistArgs<T> pa;
+  memset(&pa, 0, sizeof(pa));
+  GridBar* gbar = (GridBar*)((char*)ws.fused_state + kOffGridBar);
+  if (persist) {
+    kp = dist ? cg_persist<T, kDist, 3> : (jac ? cg_persist<T, kJacobi, 3> : cg_persist<T, kPlain, 3>);
+    ensure_dyn_smem((const void*)kp, 220 * 1024);
+    int occ = 0;
+    KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kp, kTileThreads, A.smem_bytes));
+    if (occ < 1) throw std::runtime_error("cg_persist does not fit on an SM with the planned shared-memory ring");
+    pgrid = std::min(std::min(occ, A.ctas_per_sm) * sm_count(), std::max(1, A.ntiles));
+    pa.r = ws.r; pa.P0 = ws.p; pa.P1 = ws.p2; pa.Ap = ws.Ap; pa.x = ws.x;
+    pa.mdiag = md;
+    pa.max_iters = batch;
+    pa.timed = o.time_kernels ? 1 : 0;
+    if (dist) {
+      cg_dist_tile_order<T>(ws, A);
+      CgPeerTab<T>* htab = (CgPeerTab<T>*)((char*)ws.fused_host + kOffPeerTab);
+      memset(htab, 0, sizeof(*htab));
+      for (int b = 0; b < 2; b++) {
+        const bool wantB = (b == 1) != ws.dist.swapped;
+        for (int k = 0; k < ws.dist.world; k++) {
+          htab->r[k] = ws.dist.r_peer[k];
+          htab->p[b][k] = wantB ? ws.dist.bufB_peer[k] : ws.dist.bufA_peer[k];
+        }
+      }
+      CgPeerTab<T>* dtab = (CgPeerTab<T>*)((char*)ws.fused_state + kOffPeerTab);
+      KB_CUDA(cudaMemcpyAsync(dtab, htab, sizeof(*htab), cudaMemcpyHostToDevice, c.stream));
+      pa.halo = ws.dist.halo;
+      pa.tab = dtab;
+      pa.phalo = ws.dist.halo_buf;
+      pa.tile_order = ws.dist.tile_order;
+    }
+  }
+
+  cudaEvent_t* ev = ws.fused_ev;
   int enq = 0;
   // optional per-kernel timing (bench.py roofline breakdown): events around launches 8..39
   constexpr int kTimedFirst = 8, kTimedCount = 32;
@@ -380,7 +746,16 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
     for (auto& e : tev) KB_CUDA(cudaEventCreate(&e));
   }
   auto enqueue = [&](int slot) {
-    for (int b = 0; b < batch; b++, enq++) {
+    if (persist) {
+      DistComm* dcm = dist ? c.dcomm : nullptr;
+      Csr<T> Acopy = A;
+      T* partp = part;
+      void* args[] = {(void*)&Acopy, (void*)&pa, (void*)&dst, (void*)&partp, (void*)&gbar, (void*)&dcm};
+      KB_CUDA(cudaLaunchCooperativeKernel((const void*)kp, dim3(pgrid), dim3(kTileThreads), args, A.smem_bytes, c.stream));
+      c.launches += 1;
+      enq += batch;
+    }
+    for (int b = 0; !persist && b < batch; b++, enq++) {
       T* p_old = P[enq & 1];
       T* p_new = P[(enq + 1) & 1];
       const CgPeers<T>& pe = peersP[enq & 1];
@@ -396,7 +771,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
       c.launches += 2;
     }
     KB_CUDA(cudaGetLastError());
-    KB_CUDA(cudaMemcpyAsync(&hst[slot], dst, sizeof(St), cudaMemcpyDeviceToHost, c.stream));
+    KB_CUDA(cudaMemcpyAsync(hslot(slot), dst, sizeof(St), cudaMemcpyDeviceToHost, c.stream));
     KB_CUDA(cudaEventRecord(ev[slot], c.stream));
   };
 
@@ -406,7 +781,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   for (;;) {
     if (!single_step) enqueue(cur ^ 1);           // keep the GPU busy while the host inspects `cur`
     KB_CUDA(cudaEventSynchronize(ev[cur]));
-    last = hst[cur];
+    last = *hslot(cur);
     for (int k = seen + 1; k <= last.iter; k++) {
       if (o.history) ws.stats.residuals.push_back((double)last.hist[k % kHist]);
     }
@@ -421,6 +796,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
         user_exit = o.callback(&ws, o.callback_user) != 0;
       }
       overtimed = (now_seconds() - start_time) > o.timemax;
+      agree_exit(ws, o, user_exit, overtimed);      // row-partitioned: same decision on every rank
       if (user_exit || overtimed) break;
       enqueue(cur);
     } else {
@@ -428,9 +804,15 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
     }
   }
   c.sync();   // drain speculative no-op launches
-  cudaEventDestroy(ev[0]);
-  cudaEventDestroy(ev[1]);
-  if (o.time_kernels) {
+  if (o.time_kernels && persist) {
+    // phase durations measured inside the kernel (%globaltimer of CTA 0, barriers included)
+    GridBar hb;
+    KB_CUDA(cudaMemcpy(&hb, gbar, sizeof(hb), cudaMemcpyDeviceToHost));
+    ws.timed_pairs = (int)hb.timed_iters;
+    ws.k1_ms = hb.timed_iters ? 1e-6 * (double)hb.ns_a / hb.timed_iters : 0;
+    ws.k2_ms = hb.timed_iters ? 1e-6 * (double)hb.ns_b / hb.timed_iters : 0;
+    for (auto& e : tev) cudaEventDestroy(e);
+  } else if (o.time_kernels) {
     const int pairs = std::min(kTimedCount, std::max(0, std::min(enq, last.iter) - kTimedFirst));
     double s1 = 0, s2 = 0;
     for (int i = 0; i < pairs; i++) {
@@ -471,6 +853,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
 
 #define INST(T)                                                                                              \
   template bool cg_fused_eligible<T>(const LinOp<T>&, const LinOp<T>&, const SolveOpts&);                    \
+  template void cg_fused_prepare<T>(Workspace<T>&);                                                          \
   template void cg_dist_push_r<T>(Workspace<T>&);                                                            \
   template void cg_fused_loop<T>(Workspace<T>&, const Csr<T>&, const SolveOpts&, T, T, int, double, bool&, bool&, \
                                  bool&, bool&, bool&, bool&, int&);

@@ -26,12 +26,16 @@ constexpr int kMaxRanks = 8;
 
 struct DistComm {
   int rank, world;
-  int error;                                   // set on spin timeout
+  int error;                                   // sticky: set on spin timeout -- the communicator is DEAD from then on
   int pad;
   unsigned long long seq;                      // reductions completed so far (device-resident, stream-ordered)
-  double* mail_val[kMaxRanks];                 // [dst rank] -> that rank's value mailbox  [2][kMaxRanks]
-  unsigned long long* mail_seq[kMaxRanks];     // [dst rank] -> that rank's flag mailbox   [2][kMaxRanks]
+  long long timeout_cycles;                    // spin budget of one reduction (KB200_DIST_TIMEOUT_S, default 30 s)
+  // [dst rank] -> that rank's mailbox: u64 words [2 parities][kMaxRanks sources][2 halves].  A word carries
+  // 32 bits of the value in its low half and the low 32 bits of the reduction's sequence number in its high
+  // half (the LL idea of NCCL): value and flag travel in ONE 8-byte store, so no fence separates them.
+  unsigned long long* mail[kMaxRanks];
 };
+constexpr int kMailWords = 2 * kMaxRanks * 2;
 
 // Halo description of a row block: column indices >= nloc refer to entries
 // owned by other ranks; entry h lives at offset src_off[h] of rank src_rank[h].
@@ -100,33 +104,99 @@ __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // Sum `local` over all ranks.  Called by ONE thread per rank (the thread that
 // finalises the local grid reduction), the same number of times on every rank.
 // Slot parity alternates per reduction: a rank can only be one reduction ahead
 // of any peer (it needs the peer's value to finish), so two slots suffice.
+// The leading system fence publishes everything this rank wrote before the
+// reduction (the peers read halo entries of those vectors afterwards); the
+// trailing one orders the peers' data behind the flags just observed.
+// After a timeout the communicator is dead: every later reduction returns NaN
+// at once (no stale mailbox entry is ever produced) and the host raises.
+template <class ACC = double>
 __device__ __forceinline__ double dist_allreduce_sum(DistComm* c, double local) {
+  if (c->error) return nan("");
   const unsigned long long q = c->seq + 1;
-  const int base = (int)(q & 1) * kMaxRanks;
-  for (int d = 0; d < c->world; d++) st_relaxed_sys(c->mail_val[d] + base + c->rank, local);
+  const unsigned long long tag = (q & 0xffffffffull) << 32;
+  const int base = ((int)(q & 1) * kMaxRanks + c->rank) * 2;
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(local);
+  const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
   __threadfence_system();
-  for (int d = 0; d < c->world; d++) st_relaxed_sys(c->mail_seq[d] + base + c->rank, q);
-  double sum = 0.0;
-  const unsigned long long* myseq = c->mail_seq[c->rank] + base;
-  const double* myval = c->mail_val[c->rank] + base;
+  for (int d = 0; d < c->world; d++) {
+    st_relaxed_sys(c->mail[d] + base, w0);
+    st_relaxed_sys(c->mail[d] + base + 1, w1);
+  }
+  ACC sum = ACC(0);          // "reduce in T" (SURVEY.md 8e): Float32 solves add the ranks' partials in Float32
+  const unsigned long long* mine = c->mail[c->rank] + (int)(q & 1) * kMaxRanks * 2;
   const long long t0 = clock64();
   for (int s = 0; s < c->world; s++) {
-    while (ld_acquire_sys(myseq + s) != q) {
-      if (clock64() - t0 > 20000000000LL) { c->error = 1; return nan(""); }   // ~10 s: a peer died
+    unsigned long long a, b;
+    for (;;) {
+      a = ld_relaxed_sys_u64(mine + 2 * s); b = ld_relaxed_sys_u64(mine + 2 * s + 1);
+      if ((a >> 32) == (tag >> 32) && (b >> 32) == (tag >> 32)) break;
+      if (clock64() - t0 > c->timeout_cycles) { c->error = 1; return nan(""); }
     }
-    sum += ld_relaxed_sys(myval + s);
+    sum += (ACC)__longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
   }
+  __threadfence_system();
   c->seq = q;
-  return sum;
+  return (double)sum;
 }
 
+// The same reduction (same mailbox protocol, interoperable call by call) executed by a FULL WARP: lane d sends to
+// peer d and polls source d, so the 8 stores and the 8 polls of an 8-GPU box proceed in parallel instead of one
+// after the other.  `local` is taken from lane 0; every lane returns the sum (added in rank order).
+template <class ACC = double>
+__device__ __forceinline__ double dist_allreduce_sum_warp(DistComm* c, double local) {
+  const int lane = threadIdx.x & 31;
+  local = __shfl_sync(0xffffffffu, local, 0);
+  if (*(volatile int*)&c->error) return nan("");
+  const unsigned long long q = *(volatile unsigned long long*)&c->seq + 1;
+  const unsigned long long tag = (q & 0xffffffffull) << 32;
+  const int world = c->world;
+  const int base = ((int)(q & 1) * kMaxRanks + c->rank) * 2;
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(local);
+  __threadfence_system();
+  if (lane < world) {
+    st_relaxed_sys(c->mail[lane] + base, tag | (bits & 0xffffffffull));
+    st_relaxed_sys(c->mail[lane] + base + 1, tag | (bits >> 32));
+  }
+  double v = 0.0;
+  bool dead = false;
+  if (lane < world) {
+    const unsigned long long* src = c->mail[c->rank] + ((int)(q & 1) * kMaxRanks + lane) * 2;
+    const long long t0 = clock64();
+    const long long budget = c->timeout_cycles;
+    unsigned long long a, b;
+    for (;;) {
+      a = ld_relaxed_sys_u64(src); b = ld_relaxed_sys_u64(src + 1);
+      if ((a >> 32) == (tag >> 32) && (b >> 32) == (tag >> 32)) break;
+      if (clock64() - t0 > budget) { dead = true; break; }
+    }
+    v = __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+  }
+  __threadfence_system();
+  if (__any_sync(0xffffffffu, dead)) {
+    if (lane == 0) c->error = 1;
+    return nan("");
+  }
+  ACC sum = ACC(0);
+  for (int s = 0; s < world; s++) sum += (ACC)__shfl_sync(0xffffffffu, v, s);
+  __syncwarp();
+  if (lane == 0) c->seq = q;
+  return (double)sum;
+}
+
+// Partials travel as doubles (exact for Float32) and are added in T, in rank order, identically on every rank.
 template <class T>
 __device__ __forceinline__ T dist_reduce(DistComm* c, T local) {
-  return c ? (T)dist_allreduce_sum(c, (double)local) : local;
+  return c ? (T)dist_allreduce_sum<T>(c, (double)local) : local;
 }
 
 }  // namespace kb

@@ -20,7 +20,7 @@ namespace kb {
 // generic launchers
 // ---------------------------------------------------------------------------
 template <class T, int K, class Epi, class Fin, class G>
-__global__ void __launch_bounds__(kTileThreads) spmv_epi_tma(Csr<T> A, G xg, Epi epi, Fin fin, T* part,
+__global__ void __launch_bounds__(kTileThreads, 3) spmv_epi_tma(Csr<T> A, G xg, Epi epi, Fin fin, T* part,
                                                              unsigned* ticket, DistComm* dc) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ T sm[32];
@@ -129,9 +129,9 @@ static void launch_stream(Ctx& c, int n, Body body, Fin fin, int ticket) {
 
 template <class S> static S* state_buf(void*& dev, void*& host) {
   if (!dev) {
-    KB_CUDA(cudaMalloc(&dev, 1024));
-    KB_CUDA(cudaMemset(dev, 0, 1024));
-    KB_CUDA(cudaHostAlloc(&host, 2048, cudaHostAllocDefault));
+    KB_CUDA(cudaMalloc(&dev, kFusedBlockBytes));
+    KB_CUDA(cudaMemset(dev, 0, kFusedBlockBytes));
+    KB_CUDA(cudaHostAlloc(&host, kFusedBlockBytes, cudaHostAllocDefault));
   }
   static_assert(sizeof(S) <= 1024, "state block too large");
   return (S*)dev;

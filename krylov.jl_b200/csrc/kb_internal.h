@@ -63,6 +63,10 @@ template <class T> void k_scalcopy(Ctx& c, int n, T* y, T s, const T* x);       
 template <class T> void k_divcopy(Ctx& c, int n, T* y, const T* x, T s);              // y = x / s
 template <class T> void k_fill(Ctx& c, int n, T* x, T v);
 template <class T> void k_diagmul(Ctx& c, int n, T* y, const T* d, const T* x, bool ldiv);  // y = d.*x or x./d
+// row-partitioned solves (no-ops on a single GPU)
+double k_dist_sum(Ctx& c, double v);                                   // sum of a host scalar over all ranks
+void dist_agree_on_exit(Ctx& c, bool& user_exit, bool& overtimed);     // OR the exit flags over the ranks
+void dist_check_alive(Ctx& c);                                         // throws once a reduction has timed out
 
 // ---------------------------------------------------------------------------
 // CSR operator resident in HBM (int32 indices, 0-based, columns ascending).
@@ -80,6 +84,7 @@ struct Csr {
   int ntiles = 0;
   int tile_cap = 0;         // max nnz of any kTileRows-row tile
   int max_row = 0;          // longest row
+  int max_col = -1;         // largest column index (validated against the number of columns when a solve starts)
   bool tma_ok = false;      // tile fits the shared-memory stage budget
   int stages = 0;           // pipeline depth chosen for tile_cap
   size_t smem_bytes = 0;    // dynamic smem of the staged kernels
@@ -140,6 +145,7 @@ struct SolveOpts {
   int fused = 1;                    // 0 => force the generic primitive path
   int batch = 0;                    // fused CG: iterations enqueued per host poll (0 => default)
   int time_kernels = 0;             // fused CG: bracket the first launches of K1/K2 with CUDA events
+  int persist = 1;                  // fused CG: 0 => keep the two-launch kernels instead of the persistent one
 };
 
 struct Stats {
@@ -186,6 +192,7 @@ struct Workspace {
   int timed_pairs = 0;
   void* fused_state = nullptr;         // device scalar block of the fused paths
   void* fused_host = nullptr;          // pinned mirror (2 slots)
+  cudaEvent_t fused_ev[2] = {nullptr, nullptr};   // fused CG: one event per read-back slot
   T* bbuf = nullptr;                   // device copies of host b / c for the C ABI
   T* cbuf = nullptr;
   // row-partitioned (multi-GPU) state; world == 1 means single GPU
@@ -208,6 +215,9 @@ struct Workspace {
     int* send_row = nullptr; int* send_peer = nullptr; int* send_slot = nullptr;
     long long nglobal = 0;                      // global number of rows (default itmax = 2 n)
     int npush = 0;                              // > 0: push mode (contiguous send ranges), else pull mode
+    int* tile_order = nullptr;                  // persistent CG: interior tiles first, halo tiles last (device)
+    const void* tile_order_for = nullptr;       // ... built for this operator
+    int tile_order_n = 0;
     PushRange push[kMaxPushRanges];
   } dist;
 };
@@ -235,6 +245,8 @@ template <class T> void cr_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b
 // (caller falls back to the generic primitive path, still on the GPU).
 template <class T> bool cg_fused_eligible(const LinOp<T>& A, const LinOp<T>& M, const SolveOpts& o);
 template <class T> void cg_dist_push_r(Workspace<T>& ws);
+template <class T> void cg_fused_prepare(Workspace<T>& ws);   // device/pinned scalar blocks, p2, events (ws_create)
+constexpr size_t kFusedBlockBytes = 4096;
 template <class T> void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamma0, T eps_tol, int itmax,
                                       double start_time, bool& solved, bool& tired, bool& zero_curvature,
                                       bool& inconsistent, bool& user_exit, bool& overtimed, int& iter);

@@ -92,6 +92,7 @@ void cgs_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c_in, c
     tired = iter >= itmax;
     breakdown = (alpha == 0 || std::isnan(alpha));
     overtimed = (now_seconds() - start_time) > o.timemax;
+    agree_exit(ws, o, user_exit, overtimed);      // row-partitioned: same decision on every rank
     if (kdisplay(iter, o.verbose)) printf("%5d  %7.1e  %.2fs\n", iter, (double)rNorm, now_seconds() - start_time);
   }
   if (o.verbose > 0) printf("\n");
@@ -191,6 +192,7 @@ void cg_lanczos_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const Lin
     solved = (rNorm <= eps_tol) || resid_decrease_mach;
     tired = iter >= itmax;
     overtimed = (now_seconds() - start_time) > o.timemax;
+    agree_exit(ws, o, user_exit, overtimed);      // row-partitioned: same decision on every rank
   }
   if (o.verbose > 0) printf("\n");
   if (tired) status = "maximum number of iterations exceeded";
@@ -368,6 +370,7 @@ static void arnoldi_family_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b
       solved = resid_decrease_lim || resid_decrease_mach;
       inner_tired = restart ? inner_iter >= std::min(mem, inner_itmax) : inner_iter >= inner_itmax;
       overtimed = (now_seconds() - start_time) > o.timemax;
+      agree_exit(ws, o, user_exit, overtimed);      // row-partitioned: same decision on every rank
       if (kdisplay(iter + inner_iter, o.verbose))
         printf("%5d  %5d  %7.1e  %7.1e  %.2fs\n", npass, iter + inner_iter, (double)rNorm, (double)Hbis, now_seconds() - start_time);
       if (!(solved || inner_tired || breakdown || user_exit || overtimed)) {
@@ -400,6 +403,7 @@ static void arnoldi_family_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b
     iter = iter + inner_iter;
     tired = iter >= itmax;
     overtimed = (now_seconds() - start_time) > o.timemax;
+    agree_exit(ws, o, user_exit, overtimed);      // row-partitioned: same decision on every rank
   }
   if (o.verbose > 0) printf("\n");
   if (tired) status = "maximum number of iterations exceeded";
@@ -558,6 +562,7 @@ static void truncated_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, con
     solved = (rNorm <= eps_tol) || resid_decrease_mach;
     tired = iter >= itmax;
     overtimed = (now_seconds() - start_time) > o.timemax;
+    agree_exit(ws, o, user_exit, overtimed);      // row-partitioned: same decision on every rank
     if (kdisplay(iter, o.verbose)) printf("%5d  %7.1e  %.2fs\n", iter, (double)rNorm, now_seconds() - start_time);
   }
   if (o.verbose > 0) printf("\n");
@@ -774,6 +779,7 @@ void cr_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
     solved = resid_decrease || npcurv || on_boundary;
     tired = iter >= itmax;
     overtimed = (now_seconds() - start_time) > o.timemax;
+    agree_exit(ws, o, user_exit, overtimed);      // row-partitioned: same decision on every rank
     if (solved || tired || user_exit || overtimed) continue;
     const T rhobar = rho;
     rho = k_dot<T>(c, n, r, Ar);

@@ -17,11 +17,19 @@ template <class T> static inline void allocate_if(bool cond, Workspace<T>& ws, T
   ws.stats.allocation_timer += now_seconds() - t0;
 }
 
+// Row-partitioned solves: exit decisions taken from a per-rank clock or callback are OR-ed over the ranks (one extra
+// tiny launch per iteration, only when a callback or a finite timemax is in play).
+template <class T> static inline void agree_exit(Workspace<T>& ws, const SolveOpts& o, bool& user_exit, bool& overtimed) {
+  if (ws.dist.world > 1 && (o.callback != nullptr || o.timemax < 1e300)) dist_agree_on_exit(ws.ctx, user_exit, overtimed);
+}
+
 static inline bool kdisplay(int iter, int verbose) { return verbose > 0 && iter % verbose == 0; }
 
 // default itmax = 2n of the GLOBAL system (row-partitioned workspaces hold a slice)
 template <class T> static inline int default_itmax(const Workspace<T>& ws, int itmax) {
-  return itmax == 0 ? 2 * (int)(ws.dist.world > 1 ? ws.dist.nglobal : ws.n) : itmax;
+  if (itmax != 0) return itmax;
+  const long long two_n = 2LL * (ws.dist.world > 1 ? ws.dist.nglobal : (long long)ws.n);
+  return two_n > 2147483647LL ? 2147483647 : (int)two_n;
 }
 
 // sym_givens, real case (src/krylov_utils.jl:21-51)

@@ -25,7 +25,7 @@ template <class T> Workspace<T>* ws_create(SolverKind kind, int m, int n, int me
     auto A = [&]() { return dev_alloc<T>((size_t)n); };
     ws->x = A();
     switch (kind) {
-      case S_CG: ws->r = A(); ws->p = A(); ws->Ap = A(); break;
+      case S_CG: ws->r = A(); ws->p = A(); ws->Ap = A(); cg_fused_prepare<T>(*ws); break;
       case S_BICGSTAB: ws->r = A(); ws->p = A(); ws->v = A(); ws->s = A(); ws->qd = A(); break;
       case S_MINRES:
         ws->r1 = A(); ws->r2 = A(); ws->w1 = A(); ws->w2 = A(); ws->y = A();
@@ -82,6 +82,8 @@ template <class T> void ws_destroy(Workspace<T>* ws) {
   for (T* p : ws->Z) dev_free(p);
   if (ws->fused_state) cudaFree(ws->fused_state);
   if (ws->fused_host) cudaFreeHost(ws->fused_host);
+  for (auto& e : ws->fused_ev) if (e) cudaEventDestroy(e);
+  if (ws->dist.tile_order) cudaFree(ws->dist.tile_order);
   for (void* p : ws->dist.opened) cudaIpcCloseMemHandle(p);
   if (ws->dist.mailbox) cudaFree(ws->dist.mailbox);
   dev_free(ws->dist.halo_buf);
@@ -155,7 +157,7 @@ void cg_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
     return;
   }
   int iter = 0;
-  int itmax = o.itmax == 0 ? 2 * (int)(ws.dist.world > 1 ? ws.dist.nglobal : n) : o.itmax;
+  int itmax = default_itmax(ws, o.itmax);
   T pAp = 0, pNorm2 = gamma;
   const T eps_tol = tol_of<T>(o.atol) + tol_of<T>(o.rtol) * rNorm;     // cg.jl:181
   if (o.verbose > 0) printf("%5s  %7s  %8s  %8s  %8s  %5s\n", "k", "‖r‖", "pAp", "α", "σ", "timer");
@@ -223,6 +225,7 @@ void cg_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
       tired = iter >= itmax;
       if (o.callback) { c.sync(); stats.niter = iter; user_exit = o.callback(&ws, o.callback_user) != 0; }
       overtimed = (now_seconds() - start_time) > o.timemax;
+      agree_exit(ws, o, user_exit, overtimed);      // row-partitioned: same decision on every rank
       if (kdisplay(iter, o.verbose)) printf("%5d  %7.1e", iter, (double)rNorm);
     }
   }
@@ -307,7 +310,7 @@ void bicgstab_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c_
   };
   if (rNorm == 0) { finish_early(true, "x is a zero-residual solution"); return; }
   int iter = 0;
-  const int itmax = o.itmax == 0 ? 2 * (int)(ws.dist.world > 1 ? ws.dist.nglobal : n) : o.itmax;
+  const int itmax = default_itmax(ws, o.itmax);
   const T eps_tol = tol_of<T>(o.atol) + tol_of<T>(o.rtol) * rNorm;
   if (o.verbose > 0) printf("%5s  %7s  %8s  %8s  %5s\n", "k", "‖rₖ‖", "|αₖ|", "|ωₖ|", "timer");
   if (kdisplay(iter, o.verbose)) printf("%5d  %7.1e  %8.1e  %8.1e  %.2fs\n", iter, (double)rNorm, 1.0, 1.0, now_seconds() - start_time);
@@ -352,6 +355,7 @@ void bicgstab_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c_
     tired = iter >= itmax;
     breakdown = (alpha == 0 || std::isnan(alpha));
     overtimed = (now_seconds() - start_time) > o.timemax;
+    agree_exit(ws, o, user_exit, overtimed);      // row-partitioned: same decision on every rank
     if (kdisplay(iter, o.verbose))
       printf("%5d  %7.1e  %8.1e  %8.1e  %.2fs\n", iter, (double)rNorm, (double)std::fabs(alpha), (double)std::fabs(omega), now_seconds() - start_time);
   }
@@ -417,7 +421,7 @@ void gmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>
   }
   const int mem = (int)c.size();                              // gmres.jl:181
   int npass = 0, iter = 0, inner_iter = 0;
-  const int itmax = o.itmax == 0 ? 2 * (int)(ws.dist.world > 1 ? ws.dist.nglobal : n) : o.itmax;
+  const int itmax = default_itmax(ws, o.itmax);
   int inner_itmax = itmax;
   if (o.verbose > 0) printf("%5s  %5s  %7s  %7s  %5s\n", "pass", "k", "‖rₖ‖", "hₖ₊₁.ₖ", "timer");
   if (kdisplay(iter, o.verbose)) printf("%5d  %5d  %7.1e  %7s  %.2fs\n", npass, iter, (double)rNorm, "✗ ✗ ✗ ✗", now_seconds() - start_time);
@@ -505,6 +509,7 @@ void gmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>
       solved = resid_decrease_lim || resid_decrease_mach;
       inner_tired = restart ? inner_iter >= std::min(mem, inner_itmax) : inner_iter >= inner_itmax;
       overtimed = (now_seconds() - start_time) > o.timemax;
+      agree_exit(ws, o, user_exit, overtimed);      // row-partitioned: same decision on every rank
       if (kdisplay(iter + inner_iter, o.verbose))
         printf("%5d  %5d  %7.1e  %7.1e  %.2fs\n", npass, iter + inner_iter, (double)rNorm, (double)Hbis, now_seconds() - start_time);
       if (!(solved || inner_tired || breakdown || user_exit || overtimed)) {   // gmres.jl:318-327
@@ -536,6 +541,7 @@ void gmres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>
     iter = iter + inner_iter;
     tired = iter >= itmax;
     overtimed = (now_seconds() - start_time) > o.timemax;
+    agree_exit(ws, o, user_exit, overtimed);      // row-partitioned: same decision on every rank
   }
   if (o.verbose > 0) printf("\n");
   if (tired) status = "maximum number of iterations exceeded";
@@ -616,7 +622,7 @@ void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T
   const int window = (int)err_vec.size();
   std::fill(err_vec.begin(), err_vec.end(), T(0));
   int iter = 0;
-  const int itmax = o.itmax == 0 ? 2 * (int)(ws.dist.world > 1 ? ws.dist.nglobal : n) : o.itmax;
+  const int itmax = default_itmax(ws, o.itmax);
   if (o.verbose > 0)
     printf("%5s  %7s  %7s  %7s  %8s  %8s  %7s  %7s  %7s  %7s  %5s\n", "k", "‖r‖", "‖Aᴴr‖", "β", "cos", "sin", "‖A‖", "κ(A)", "test1", "test2", "timer");
   const T eps_tol = atol + tol_of<T>(o.rtol) * beta1;        // minres.jl:269
@@ -762,6 +768,7 @@ void minres_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T
     ill_cond = ill_cond_mach || ill_cond_lim;
     solved = solved_mach || solved_lim || zero_resid || fwd_err || resid_decrease;
     overtimed = (now_seconds() - start_time) > o.timemax;
+    agree_exit(ws, o, user_exit, overtimed);      // row-partitioned: same decision on every rank
   }
   if (o.verbose > 0) printf("\n");
   if (tired) status = "maximum number of iterations exceeded";

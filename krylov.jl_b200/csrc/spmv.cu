@@ -83,7 +83,7 @@ void csr_upload(Ctx& c, Csr<T>& A, int n, long long nnz, const void* rowptr, con
   if (tmp_rp) cudaFree(tmp_rp);
   if (tmp_ci) cudaFree(tmp_ci);
   if (hbad) { csr_free(A); throw std::runtime_error("CSR operator: index outside int32 range after rebasing"); }
-  csr_plan(c, A);
+  try { csr_plan(c, A); } catch (...) { csr_free(A); throw; }
 }
 
 template <class T> void csr_free(Csr<T>& A) {
@@ -95,39 +95,57 @@ template <class T> void csr_free(Csr<T>& A) {
 // Staging plan: largest tile (nnz of kTileRows consecutive rows) and longest
 // row decide whether the TMA ring fits, how deep it is, and the grid.
 // ---------------------------------------------------------------------------
-__global__ void plan_kernel(int n, int ntiles, const int* __restrict__ rowptr, int* out /* [0]=tile_cap [1]=max_row [2]=unsorted */,
-                            const int* __restrict__ colind) {
+__global__ void plan_kernel(int n, int ntiles, const int* __restrict__ rowptr,
+                            int* out /* [0]=tile_cap [1]=max_row [2]=unsorted [3]=rowptr not monotone [4]=max col [5]=negative col */,
+                            const int* __restrict__ colind, long long nnz) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int stride = gridDim.x * blockDim.x;
-  int cap = 0, mr = 0, uns = 0;
+  int cap = 0, mr = 0, uns = 0, bad = 0, mc = -1, neg = 0;
+  for (int i = t; i < n; i += stride) {
+    const int kb = rowptr[i], ke = rowptr[i + 1];
+    // validation (a malformed matrix must be an error, not an out-of-bounds read in the SpMV): row pointers
+    // non-decreasing and inside [0, nnz] -- only then are the column indices of the row looked at
+    if (kb > ke || kb < 0 || (long long)ke > nnz) { bad = 1; continue; }
+    mr = max(mr, ke - kb);
+    for (int k = kb; k < ke; k++) { const int cj = colind[k]; mc = max(mc, cj); neg |= cj < 0; }
+    // halo columns (index >= n, row-partitioned operators) keep their global position in the row: skip them
+    for (int k = kb + 1; k < ke; k++) uns |= (colind[k] <= colind[k - 1]) && colind[k] < n && colind[k - 1] < n;
+  }
+  if (bad) atomicExch(&out[3], 1);
+  __syncthreads();
   for (int i = t; i < ntiles; i += stride) {
     const int r0 = i * kTileRows, r1 = min(r0 + kTileRows, n);
     cap = max(cap, rowptr[r1] - rowptr[r0]);
   }
-  for (int i = t; i < n; i += stride) {
-    const int kb = rowptr[i], ke = rowptr[i + 1];
-    mr = max(mr, ke - kb);
-    // halo columns (index >= n, row-partitioned operators) keep their global position in the row: skip them
-    for (int k = kb + 1; k < ke; k++) uns |= (colind[k] <= colind[k - 1]) && colind[k] < n && colind[k - 1] < n;
-  }
   atomicMax(&out[0], cap);
   atomicMax(&out[1], mr);
+  atomicMax(&out[4], mc);
   if (uns) atomicExch(&out[2], 1);
+  if (neg) atomicExch(&out[5], 1);
 }
 
 template <class T> void csr_plan(Ctx& c, Csr<T>& A) {
   A.ntiles = (A.n + kTileRows - 1) / kTileRows;
   int* dout = nullptr;
-  KB_CUDA(cudaMalloc((void**)&dout, 3 * sizeof(int)));
-  KB_CUDA(cudaMemsetAsync(dout, 0, 3 * sizeof(int), c.stream));
+  KB_CUDA(cudaMalloc((void**)&dout, 6 * sizeof(int)));
+  KB_CUDA(cudaMemsetAsync(dout, 0, 6 * sizeof(int), c.stream));
+  int h[6] = {0, 0, 0, 0, -1, 0};
+  int ends[2] = {0, (int)A.nnz};
   if (A.n > 0) {
-    plan_kernel<<<sm_count() * 4, 256, 0, c.stream>>>(A.n, A.ntiles, A.rowptr, dout, A.colind);
+    KB_CUDA(cudaMemcpyAsync(dout + 4, &h[4], sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    plan_kernel<<<sm_count() * 4, 256, 0, c.stream>>>(A.n, A.ntiles, A.rowptr, dout, A.colind, A.nnz);
     KB_CUDA(cudaGetLastError());
+    KB_CUDA(cudaMemcpyAsync(&ends[0], A.rowptr, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    KB_CUDA(cudaMemcpyAsync(&ends[1], A.rowptr + A.n, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   }
-  int h[3] = {0, 0, 0};
   KB_CUDA(cudaMemcpyAsync(h, dout, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
   c.sync();
   cudaFree(dout);
+  // the reference would throw a BoundsError on such input; here it must not reach the kernels
+  if (ends[0] != 0 || (long long)ends[1] != A.nnz || h[3])
+    throw std::runtime_error("CSR operator: row pointers must start at 0 (after rebasing), be non-decreasing and end at nnz");
+  if (h[5]) throw std::runtime_error("CSR operator: negative column index (after rebasing)");
+  A.max_col = h[4];
   if (h[2]) fprintf(stderr, "[krylov_b200] warning: CSR column indices are not strictly ascending within rows; "
                             "results remain correct but are no longer bit-comparable to SparseArrays' order\n");
   A.tile_cap = h[0];
@@ -188,7 +206,7 @@ __global__ void __launch_bounds__(kBlock) spmv_rows_kernel(Csr<T> A, G xg, T* __
 }
 
 template <class T, bool DOT, class G>
-__global__ void __launch_bounds__(kTileThreads) spmv_tma_kernel(Csr<T> A, G xg, T* __restrict__ y, T* part,
+__global__ void __launch_bounds__(kTileThreads, 3) spmv_tma_kernel(Csr<T> A, G xg, T* __restrict__ y, T* part,
                                                                 unsigned* ticket, T* out) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ T sm[32];

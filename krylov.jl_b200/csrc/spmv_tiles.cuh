@@ -24,6 +24,9 @@ namespace kb {
 constexpr int kConsumerWarps = kTileRows / 32;            // 8
 constexpr int kTileThreads = kTileRows + 32;              // + 1 producer warp
 constexpr int kGatherDepth = 8;                           // gathers in flight per thread
+#ifndef KB_CLAMP_GATHER
+#define KB_CLAMP_GATHER 1                                 // 0: guarded gathers of round 1 (A/B builds)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -192,6 +195,22 @@ __device__ __forceinline__ void spmv_tiles_run(const Csr<T>& A, unsigned char* s
         T acc = T(0);
         for (int k = kb; k < ke; k += kGatherDepth) {
           T xv[kGatherDepth], av[kGatherDepth];
+#if KB_CLAMP_GATHER
+          // clamped indices + selected sums: straight-line code, every gather of the batch is issued before the
+          // first use (guarded loads compile to load -> use -> load chains: 2-3 loads in flight instead of 8)
+#pragma unroll
+          for (int u = 0; u < kGatherDepth; u++) {
+            const int kk = min(k + u, ke - 1);
+            av[u] = vrow[kk];
+            xv[u] = gather(crow[kk]);
+          }
+          asm volatile("" ::: "memory");      // keep the loads above the sums (the optimiser would sink them)
+#pragma unroll
+          for (int u = 0; u < kGatherDepth; u++) {
+            const T nx = add_rn(acc, mul_rn(av[u], xv[u]));
+            acc = (k + u < ke) ? nx : acc;
+          }
+#else
 #pragma unroll
           for (int u = 0; u < kGatherDepth; u++) {
             if (k + u < ke) { av[u] = vrow[k + u]; xv[u] = gather(crow[k + u]); }
@@ -200,12 +219,129 @@ __device__ __forceinline__ void spmv_tiles_run(const Csr<T>& A, unsigned char* s
           for (int u = 0; u < kGatherDepth; u++) {
             if (k + u < ke) acc = add_rn(acc, mul_rn(av[u], xv[u]));
           }
+#endif
         }
         row_done(row, acc, pre);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
     }
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// The same pipeline split into pieces for PERSISTENT kernels (cg_fused.cu: cg_persist) that run the tile pass
+// many times inside one launch.  Ring positions are running counters (slot = pos % S, phase = (pos / S) & 1) that
+// survive from one pass to the next, so the producer may already stream the first tiles of the NEXT pass (the
+// matrix does not change between iterations) while the consumers sit in a grid-wide barrier.
+// `tile_at(j)` maps the j-th tile of this CTA's sequence to a tile id; bit 31 set marks a tile whose gathers
+// need data that `pre_tile()` must wait for (row-partitioned solves: halo columns).
+// ---------------------------------------------------------------------------
+template <class T>
+struct TilePipe {
+  TileLayout<T> L;
+  int S;
+  uint64_t* full;
+  uint64_t* empty;
+  unsigned char* ring;
+  __device__ __forceinline__ void init(const Csr<T>& A, unsigned char* smem) {   // every thread of the CTA
+    L = TileLayout<T>{A.tile_cap};
+    S = A.stages;
+    full = reinterpret_cast<uint64_t*>(smem);
+    empty = full + S;
+    ring = smem + 128;
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+};
+
+// Producer (one elected lane): issue ring positions [pos, target).  Position q carries tile tile_at(q % cnt).
+template <class T, class TileAt>
+__device__ __forceinline__ void tile_issue_until(const Csr<T>& A, const TilePipe<T>& P, unsigned& pos, unsigned target, int cnt,
+                                                 TileAt tile_at, uint64_t pol) {
+  constexpr int VA = 16 / sizeof(T);
+  if (pos >= target) return;
+  int t = tile_at((int)(pos % (unsigned)cnt)) & 0x7fffffff;
+  int k0 = __ldg(&A.rowptr[t * kTileRows]), k1 = __ldg(&A.rowptr[min(t * kTileRows + kTileRows, A.n)]);
+  for (; pos < target; pos++) {
+    int tn = 0, nk0 = 0, nk1 = 0;
+    if (pos + 1 < target) {        // next tile's nnz range: fetch before blocking on the ring slot
+      tn = tile_at((int)((pos + 1) % (unsigned)cnt)) & 0x7fffffff;
+      nk0 = __ldg(&A.rowptr[tn * kTileRows]); nk1 = __ldg(&A.rowptr[min(tn * kTileRows + kTileRows, A.n)]);
+    }
+    const int s = (int)(pos % (unsigned)P.S);
+    mbar_wait(&P.empty[s], ((pos / (unsigned)P.S) & 1) ^ 1);
+    unsigned char* st = P.ring + (size_t)s * P.L.stage_bytes();
+    const int k0v = k0 & ~(VA - 1), k1v = (k1 + VA - 1) & ~(VA - 1);
+    const int k0c = k0 & ~3, k1c = (k1 + 3) & ~3;
+    const unsigned rp_b = (kTileRows + 4) * sizeof(int);
+    const unsigned v_b = (unsigned)(k1v - k0v) * sizeof(T);
+    const unsigned c_b = (unsigned)(k1c - k0c) * sizeof(int);
+    mbar_expect_tx(&P.full[s], rp_b + v_b + c_b);
+    tma_load_1d(st, A.rowptr + t * kTileRows, rp_b, &P.full[s], pol);
+    if (v_b) tma_load_1d(st + P.L.rp_bytes(), A.val + k0v, v_b, &P.full[s], pol);
+    if (c_b) tma_load_1d(st + P.L.rp_bytes() + P.L.val_bytes(), A.colind + k0c, c_b, &P.full[s], pol);
+    t = tn; k0 = nk0; k1 = nk1;
+  }
+}
+
+// Producer at kernel exit: positions [consumed, pos) were issued but never consumed -- wait for their copies to
+// land (a CTA must not retire with bulk copies in flight into its shared memory).
+template <class T>
+__device__ __forceinline__ void tile_drain(const TilePipe<T>& P, unsigned consumed, unsigned pos) {
+  for (unsigned q = consumed; q < pos; q++) mbar_wait(&P.full[q % (unsigned)P.S], (q / (unsigned)P.S) & 1);
+}
+
+// Consumers (threads 0 .. kTileRows-1): one pass over this CTA's cnt tiles.
+template <class T, class TileAt, class Gather, class RowBegin, class RowDone, class PreTile>
+__device__ __forceinline__ void tile_consume_pass(const Csr<T>& A, const TilePipe<T>& P, unsigned& cpos, int cnt, TileAt tile_at,
+                                                  Gather gather, RowBegin row_begin, RowDone row_done, PreTile pre_tile) {
+  constexpr int VA = 16 / sizeof(T);
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int j = 0; j < cnt; j++, cpos++) {
+    const int traw = tile_at(j);
+    const int t = traw & 0x7fffffff;
+    const int row = t * kTileRows + tid;
+    auto pre = row_begin(row < A.n ? row : 0);
+    if (traw < 0) pre_tile();
+    const int s = (int)(cpos % (unsigned)P.S);
+    mbar_wait(&P.full[s], (cpos / (unsigned)P.S) & 1);
+    const unsigned char* st = P.ring + (size_t)s * P.L.stage_bytes();
+    const int* rp = reinterpret_cast<const int*>(st);
+    const T* vs = reinterpret_cast<const T*>(st + P.L.rp_bytes());
+    const int* cs = reinterpret_cast<const int*>(st + P.L.rp_bytes() + P.L.val_bytes());
+    if (row < A.n) {
+      const int k0 = rp[0];
+      const T* vrow = vs - (k0 & ~(VA - 1));
+      const int* crow = cs - (k0 & ~3);
+      const int kb = rp[tid], ke = rp[tid + 1];
+      T acc = T(0);
+      // The gathers here are plain (coherent) loads, which the compiler will not speculate: guarded loads would
+      // be chained load -> use -> load.  Clamp the index instead (every address is valid) and select the sum, so
+      // the batch is straight-line code and all gathers of a row are issued together.
+      for (int k = kb; k < ke; k += kGatherDepth) {
+        T xv[kGatherDepth], av[kGatherDepth];
+#pragma unroll
+        for (int u = 0; u < kGatherDepth; u++) {
+          const int kk = min(k + u, ke - 1);
+          av[u] = vrow[kk];
+          xv[u] = gather(crow[kk]);
+        }
+        asm volatile("" ::: "memory");        // keep the loads above the sums (the optimiser would sink them)
+#pragma unroll
+        for (int u = 0; u < kGatherDepth; u++) {
+          const T nx = add_rn(acc, mul_rn(av[u], xv[u]));
+          acc = (k + u < ke) ? nx : acc;
+        }
+      }
+      row_done(row, acc, pre);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&P.empty[s]);
   }
 }
 

@@ -227,6 +227,17 @@ class KrylovWorkspace:
         except Exception:
             pass
 
+    def _order_after(self, *arrays):
+        """Stream contract of device inputs (include/krylov_b200.h): torch tensors are produced on torch's current
+        stream, the library works on its own non-blocking stream -- make the latter wait for the former."""
+        for a in arrays:
+            if a is not None and _is_torch(a) and a.is_cuda:
+                import torch
+                s = torch.cuda.current_stream(a.device)
+                if lib().krylov_b200_wait_stream(self._h, C.c_void_p(s.cuda_stream)) != 0:
+                    raise B200Error(_lib.last_error())
+                return
+
     # -- operator -----------------------------------------------------------
     def set_operator(self, A):
         """Upload A as the device-resident CSR operator (krylov_b200_set_operator_csr)."""
@@ -267,6 +278,7 @@ class KrylovWorkspace:
         p_rp, k1 = _ptr(rp)
         p_ci, k2 = _ptr(ci)
         p_va, k3 = _ptr(va)
+        self._order_after(va)
         rc = lib().krylov_b200_set_operator_csr(self._h, n, nnz, p_rp, p_ci, p_va, int(base), int(ib), loc)
         if rc != 0:
             raise B200Error(_lib.last_error())
@@ -284,6 +296,7 @@ class KrylovWorkspace:
         if not _is_torch(d):
             d = np.ascontiguousarray(d, dtype=self.dtype)
         p, keep = _ptr(d)
+        self._order_after(d)
         if lib().krylov_b200_set_preconditioner_diag(self._h, which, p, 1 if _is_torch(d) else 0) != 0:
             raise B200Error(_lib.last_error())
 
@@ -375,6 +388,7 @@ class KrylovWorkspace:
         if c is not None and not _is_torch(c):
             c = np.ascontiguousarray(c, dtype=self.dtype)
         pc, kc = _ptr(c)
+        self._order_after(kb, kc)
         null = _lib.MATVEC()
         rc = lib().krylov_solve(self._h, fA or null, null, fM or null, fN or null, pb, pc, None, C.byref(o))
         del keep
@@ -390,6 +404,7 @@ class KrylovWorkspace:
         if x0.shape[0] != self.n:
             raise B200Error(f"x0 should have size {self.n}")
         p, k = _ptr(x0)
+        self._order_after(k)
         rc = lib().krylov_warm_start(self._h, p, self.n)
         if rc != 0:
             raise B200Error(_lib.last_error())
@@ -596,6 +611,7 @@ class BlockGmresWorkspace(KrylovWorkspace):
             raise B200Error("ktypeof(B) must match the workspace storage (host array / device tensor)")
         Bc = self._colmajor(B)
         pb, kb_ = _ptr(Bc)
+        self._order_after(kb_)
         null = _lib.BLOCK_MATVEC()
         rc = lib().krylov_block_solve(self._h, fA or null, fM or null, fN or null, pb, None, C.byref(o))
         del keep
@@ -610,6 +626,7 @@ class BlockGmresWorkspace(KrylovWorkspace):
             raise B200Error(f"X0 should have size {self.n} x {self.p}")
         Xc = self._colmajor(X0)
         p, k = _ptr(Xc)
+        self._order_after(k)
         if lib().krylov_block_warm_start(self._h, p, self.n, self.p) != 0:
             raise B200Error(_lib.last_error())
         return self

@@ -92,6 +92,7 @@ SIGNATURES = {
     "krylov_b200_get_kernel_times": (_I, [_P, C.POINTER(_D)]),
     "krylov_b200_launch_count": (_LL, [_P]),
     "krylov_b200_stream": (_P, [_P]),
+    "krylov_b200_wait_stream": (C.c_int, [_P, _P]),
     "krylov_b200_dist_handle_bytes": (_I, []),
     "krylov_b200_dist_init": (_I, [_P, _I, _I, _I, _P, _P]),
     "krylov_b200_dist_set_push": (_I, [_P, _I, _P, _P]),

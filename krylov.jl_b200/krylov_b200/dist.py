@@ -211,34 +211,27 @@ def make_poisson_rank(N, rank, world, torch, device, dtype=np.float64):
 # --------------------------------------------------------------------------
 # bench entry (called by bench.py when WORLD_SIZE > 1)
 # --------------------------------------------------------------------------
-def bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler):
-    import torch
-    import torch.distributed as dist
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    _lib.lib().krylov_b200_set_device(local)
-    dist.init_process_group("nccl", device_id=dev)
-    N, iters = WORKLOADS[args.workload]
-    n, nnz = N ** 3, 7 * N ** 3 - 6 * N ** 2
+def _run_workload(N, iters, steps, warmup, rank, world, local, dev, torch, dist, sampler=None):
+    """Row-partitioned fused CG on get_div_grad(N,N,N): device-resident timing (CUDA events on the workspace
+    stream, max over ranks), end-to-end timing with host buffers, and the residual history of one extra solve."""
     csr, hr, ho, nloc = make_poisson_rank(N, rank, world, torch, dev)
     dws = DistCgWorkspace(csr, hr, ho, rank, world)
     b = torch.ones(nloc, dtype=torch.float64, device=dev)
     kw = dict(atol=0.0, rtol=0.0, itmax=iters)
     stream = torch.cuda.ExternalStream(_lib.lib().krylov_b200_stream(dws.ws._h), device=dev)
-    for _ in range(args.warmup):
+    torch.cuda.synchronize()
+    for _ in range(warmup):
         dist.barrier()
         dws.solve(b, **kw)
     assert dws.stats.niter == iters, dws.stats
-    sampler = ClockSampler(local)
-    if rank == 0:
+    if sampler is not None:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = dws.ws.launches
     dist.barrier()
     torch.cuda.synchronize()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         dws.solve(b, **kw)
     e1.record(stream)
     torch.cuda.synchronize()
@@ -248,16 +241,14 @@ def bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler):
     ms = float(ms.item())
     launches = torch.tensor([dws.ws.launches - l0], device=dev)
     dist.all_reduce(launches)
-    rn = dws.stats
     # end-to-end arm: host buffers for this rank's slice of b and x
-    from . import CgWorkspace  # noqa: F401
     bh = torch.ones(nloc, dtype=torch.float64).pin_memory()
     xh = torch.empty(nloc, dtype=torch.float64).pin_memory()
     bd = torch.empty(nloc, dtype=torch.float64, device=dev)
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         bd.copy_(bh, non_blocking=True)                         # H2D of this rank's slice of b
         torch.cuda.synchronize()
         dws.solve(bd, **kw)
@@ -266,25 +257,95 @@ def bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler):
     dist.barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler is not None else None
+    # parity material (not timed): the residual history of one more solve, identical on every rank because every
+    # rank derives alpha / beta / rNorm from the same all-reduced scalars -- checked here, then compared by rank 0
+    dws.solve(b, history=True, **kw)
+    hist = np.asarray(dws.stats.residuals, dtype=np.float64)
+    hmax = torch.tensor(hist, device=dev)
+    hmin = hmax.clone()
+    dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(hmin, op=dist.ReduceOp.MIN)
+    ranks_agree = bool(torch.equal(hmax, hmin))
+    status = dws.stats.status
+    dws.free()
+    del csr, b, bd
+    torch.cuda.empty_cache()
+    return dict(ms=ms, launches=int(launches.item()), e2e_s=float(e2e_s.item()), clocks=clocks, hist=hist,
+                ranks_agree=ranks_agree, status=status)
+
+
+def bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler, parity_block=None, golden_parity=None):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.lib().krylov_b200_set_device(local)
+    dist.init_process_group("nccl", device_id=dev)
+    N, iters = WORKLOADS[args.workload]
+    n, nnz = N ** 3, 7 * N ** 3 - 6 * N ** 2
+    sampler = ClockSampler(local) if rank == 0 else None
+    res = _run_workload(N, iters, args.steps, args.warmup, rank, world, local, dev, torch, dist, sampler)
+    # BASELINE config 5 (n ~ 1e8) rides along on the default workload so that the driver's 1/2/4/8-GPU scaling file
+    # carries it: `cfg5.value` at 8 GPUs over `cfg5.value` at 1 GPU is north_star's ">= 6x" figure.
+    cfg5 = None
+    if args.workload == "poisson215" and not getattr(args, "no_cfg5", False):
+        N5, it5 = WORKLOADS["poisson464"]
+        r5 = _run_workload(N5, it5, max(2, args.steps // 2), 3, rank, world, local, dev, torch, dist)
+        cfg5 = (N5, it5, max(2, args.steps // 2), r5)
     if rank == 0:
         its = args.steps * iters
+        ms = res["ms"]
         value = its / (ms * 1e-3)
         B = algorithmic_bytes_cg(n, nnz)
         peak, src = hbm_peak()
         achieved = B * its / (ms * 1e-3) / 1e9
+        parity = None
+        if parity_block is not None and not getattr(args, "no_cpu", False):
+            try:
+                parity = golden_parity(res["hist"], "bench_cg_poisson464") if N > 300 else parity_block(res["hist"], N, iters)
+            except Exception as ex:
+                parity = dict(ok=None, note=f"failed: {type(ex).__name__}: {ex}")
+            parity["ranks_agree"] = res["ranks_agree"]
+            if not res["ranks_agree"]:
+                parity["ok"] = False
         line = dict(metric="CG iterations/s", value=value, unit="it/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
                     data="synthetic",
-                    config=dict(workload=f"cg! fused, get_div_grad({N},{N},{N}) Float64 int32-CSR row-partitioned in z-slabs over "
-                                         f"{world} GPUs, b=ones, atol=rtol=0, itmax={iters} per step", n=n, nnz=nnz,
-                                iters_per_step=iters, parallelism=f"rows/{world}: NVLink P2P halo loads + in-kernel all-reduce",
-                                l2="per-rank matrix slab %.0f MB" % (nnz * 12 / world / 1e6), final_rnorm=rn.status),
+                    config=dict(workload=f"cg! fused (persistent cooperative kernel), get_div_grad({N},{N},{N}) Float64 int32-CSR "
+                                         f"row-partitioned in z-slabs over {world} GPUs, b=ones, atol=rtol=0, itmax={iters} per step",
+                                n=n, nnz=nnz, iters_per_step=iters,
+                                parallelism=f"rows/{world}: halo staged over NVLink P2P inside the kernel + in-kernel all-reduce",
+                                l2="per-rank matrix slab %.0f MB" % (nnz * 12 / world / 1e6), status=res["status"]),
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak * world, unit="GB/s", frac=achieved / (peak * world),
                                   traffic=None, peak_source=src + f" x {world} GPUs", bytes_per_iteration=B),
-                    clocks=clocks,
-                    e2e=dict(value=its / float(e2e_s.item()), unit="it/s", h2d_bytes_per_step=n * 8, d2h_bytes_per_step=n * 8),
-                    gpu_launches=int(launches.item()))
+                    clocks=res["clocks"],
+                    e2e=dict(value=its / res["e2e_s"], unit="it/s", h2d_bytes_per_step=n * 8, d2h_bytes_per_step=n * 8),
+                    gpu_launches=res["launches"])
+        if parity is not None:
+            line["parity"] = parity
+        if cfg5 is not None:
+            N5, it5, st5, r5 = cfg5
+            n5, nnz5 = N5 ** 3, 7 * N5 ** 3 - 6 * N5 ** 2
+            v5 = st5 * it5 / (r5["ms"] * 1e-3)
+            B5 = algorithmic_bytes_cg(n5, nnz5)
+            p5 = None
+            if golden_parity is not None:
+                p5 = golden_parity(r5["hist"], "bench_cg_poisson464")
+                p5["ranks_agree"] = r5["ranks_agree"]
+                if not r5["ranks_agree"]:
+                    p5["ok"] = False
+            line["cfg5"] = dict(workload=f"cg! on get_div_grad({N5},{N5},{N5}) (n = {n5}, nnz = {nnz5}) row-partitioned over {world} GPUs, "
+                                         f"{it5} iterations per step, {st5} steps", value=v5, unit="it/s", n_gpus=world,
+                                ms_per_step=r5["ms"] / st5, frac=B5 * v5 / 1e9 / (peak * world), bytes_per_iteration=B5,
+                                e2e=dict(value=st5 * it5 / r5["e2e_s"], unit="it/s"), parity=p5,
+                                speedup_note="north_star target: value at 8 GPUs >= 6 x value at 1 GPU (same key on the N=1 line)")
         print(json.dumps(line))
-    dws.free()
+        bad = [k for k, p in (("parity", line.get("parity")), ("cfg5.parity", (line.get("cfg5") or {}).get("parity"))) if p and p.get("ok") is False]
+    else:
+        bad = []
+    dist.barrier()
     dist.destroy_process_group()
+    if bad:
+        raise SystemExit("parity FAILED: " + ", ".join(bad))

@@ -10,6 +10,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+int oracle_dot_mode = 0;
+void oracle_set_dot_mode(int m) { oracle_dot_mode = m; }
+
 /* ---- Float64 instantiation ---- */
 #define REAL double
 #define SUF(name) name##_f64
@@ -54,7 +57,7 @@
  * ------------------------------------------------------------------------- */
 #include <omp.h>
 double oracle_cg_timed_f64(int n, const int *rowptr, const int *colind, const double *val, const double *b,
-                           int iters, int threads, double *x_out, double *rnorm_out) {
+                           int iters, int threads, double *x_out, double *rnorm_out, double *hist_out /* iters+1 or NULL */) {
   double *x = calloc(n, sizeof(double)), *r = malloc(sizeof(double) * n), *p = malloc(sizeof(double) * n),
          *Ap = malloc(sizeof(double) * n);
   if (threads < 1) threads = 1;
@@ -62,6 +65,7 @@ double oracle_cg_timed_f64(int n, const int *rowptr, const int *colind, const do
   double gamma = 0;
 #pragma omp parallel for reduction(+ : gamma) schedule(static)
   for (int i = 0; i < n; i++) { r[i] = b[i]; p[i] = b[i]; gamma += b[i] * b[i]; }
+  if (hist_out) hist_out[0] = sqrt(gamma);
   double t0 = omp_get_wtime();
   for (int it = 0; it < iters; it++) {
     double pAp = 0;
@@ -81,6 +85,7 @@ double oracle_cg_timed_f64(int n, const int *rowptr, const int *colind, const do
     }
     double beta = gamma_next / gamma;
     gamma = gamma_next;
+    if (hist_out) hist_out[it + 1] = sqrt(gamma);
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < n; i++) p[i] = r[i] + beta * p[i];
   }
@@ -91,4 +96,4 @@ double oracle_cg_timed_f64(int n, const int *rowptr, const int *colind, const do
   return t1 - t0;
 }
 
-int oracle_abi_version(void) { return 3; }
+int oracle_abi_version(void) { return 4; }

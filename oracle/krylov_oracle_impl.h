@@ -44,7 +44,16 @@ static void SUF(spmv)(const SUF(csr) *A, const REAL *x, REAL *y) {
 }
 
 /* BLAS-1 wrappers, src/krylov_utils.jl:309-347 (sequential restatement). */
+/* Test knob (oracle_set_dot_mode): 0 = the restatement's sequential sum in REAL; 1 = the same terms accumulated in
+ * double and rounded once.  Float32 parity tests run both and take the gap between the two histories as the
+ * measured sensitivity of the iteration to the rounding of its dot products (tests/test_gpu_solvers.py). */
+extern int oracle_dot_mode;
 static REAL SUF(kdot)(int n, const REAL *x, const REAL *y) {
+  if (oracle_dot_mode == 1) {
+    double s = 0.0;
+    for (int i = 0; i < n; i++) { double p = (double)x[i] * (double)y[i]; s = s + p; }
+    return (REAL)s;
+  }
   REAL s = (REAL)0;
   for (int i = 0; i < n; i++) { REAL p = x[i] * y[i]; s = s + p; }
   return s;

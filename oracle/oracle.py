@@ -112,6 +112,20 @@ def _result(st, x, res, extra=None):
     return x, out
 
 
+class dot_mode:
+    """with dot_mode(1): ...  -- the oracle's dot products accumulate in double and round once (test knob,
+    krylov_oracle_impl.h: kdot); the default 0 is the restatement's sequential sum in the working precision."""
+
+    def __init__(self, mode):
+        self.mode = int(mode)
+
+    def __enter__(self):
+        lib().oracle_set_dot_mode(self.mode)
+
+    def __exit__(self, *a):
+        lib().oracle_set_dot_mode(0)
+
+
 def cg(A, b, x0=None, M=None, dtype=np.float64, **kw):
     """cg! (src/cg.jl:120-291).  M: None or the diagonal of a Diagonal preconditioner."""
     suf, _ = _suf(dtype)
@@ -285,8 +299,9 @@ def householder(Q, compact=False, dtype=np.float64):
     return Q, R, tau
 
 
-def cg_timed(rowptr, colind, val, b, iters, threads=1):
-    """Fixed-iteration CG loop on the host (bench.py CPU legs).  Returns (seconds, x, rNorm)."""
+def cg_timed(rowptr, colind, val, b, iters, threads=1, history=False):
+    """Fixed-iteration CG loop on the host (bench.py CPU legs).  Returns (seconds, x, rNorm) and, with
+    history=True, a fourth item: the residual norms of iterations 0..iters (bench.py's parity block)."""
     L = lib()
     L.oracle_cg_timed_f64.restype = C.c_double
     n = len(rowptr) - 1
@@ -296,7 +311,11 @@ def cg_timed(rowptr, colind, val, b, iters, threads=1):
     b = np.ascontiguousarray(b, dtype=np.float64)
     x = np.zeros(n)
     rn = C.c_double()
-    t = L.oracle_cg_timed_f64(n, _p(rowptr), _p(colind), _p(val), _p(b), int(iters), int(threads), _p(x), C.byref(rn))
+    hist = np.zeros(int(iters) + 1) if history else None
+    t = L.oracle_cg_timed_f64(n, _p(rowptr), _p(colind), _p(val), _p(b), int(iters), int(threads), _p(x), C.byref(rn),
+                              _p(hist) if history else None)
+    if history:
+        return float(t), x, rn.value, hist
     return float(t), x, rn.value
 
 

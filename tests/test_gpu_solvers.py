@@ -1,8 +1,8 @@
 """GPU parity tests proper: cg!/gmres!/bicgstab!/minres! through the C ABI vs the CPU oracle.
 
 Bar (BASELINE.json north_star): identical iteration count and residual norms within 1e-6 relative
-for Float64.  Float32 histories are held to 5e-3 and the iteration count to +-1 (the oracle's
-sequential fp32 dots and the GPU's tree reductions differ by ~sqrt(n)*eps32)."""
+for Float64.  Float32 histories are held to 10x the oracle's own measured sensitivity to the rounding of
+its dot products (sequential fp32 sums vs the same sums accumulated in double: f32_dot_sensitivity)."""
 import json
 import os
 
@@ -15,6 +15,7 @@ import cases
 pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_histories.json")))
 F64_TOL = 1e-6
+F32_FLOOR = 5e-7          # 4 ulp of Float32
 
 
 def run_gpu(kb, name, **extra):
@@ -63,14 +64,34 @@ def check_against(st, x, g_res, g_niter, g_status, dt, xo=None, sens=None):
             xtol = 1e-6 if sens is None else max(1e-6, 10 * float(sens[np.isfinite(sens)].max()))
             assert np.linalg.norm(x - xo) <= xtol * np.linalg.norm(xo)
     else:
-        # Float32 (outside the 1e-6 Float64 bar of north_star): sequential fp32 dots (oracle) vs tree reductions
-        # (GPU) differ by ~sqrt(n)*eps32 per dot and fp32 BiCGSTAB histories have spikes (small omega) whose height
-        # is itself ill-conditioned (measured: median 4e-3, max 2e-2 on the random matrix).  Bar: iteration count
-        # within +-2, median relative deviation <= 2e-2, 80th percentile <= 5e-2 (isolated spikes may differ by O(1)).
-        assert abs(st.niter - g_niter) <= 2
-        k = min(len(res), len(g_res))
-        rel = np.abs(res[:k] - g_res[:k]) / (np.abs(g_res[:k]) + 1e-5 * abs(g_res[0]))
-        assert np.median(rel) <= 2e-2 and np.percentile(rel, 80) <= 5e-2, (np.median(rel), np.percentile(rel, 80))
+        # Float32 (outside the 1e-6 Float64 bar of north_star).  The tolerance is MEASURED, not hand-set: `sens` is
+        # the running-max gap between the oracle's history with sequential fp32 dots and with the same dots
+        # accumulated in double (f32_dot_sensitivity) -- i.e. how far the restated algorithm itself moves when only
+        # the rounding of its dot products changes, which is exactly what separates the GPU's tree sums from the
+        # oracle's sequential ones.  Allowance: 10x that gap, floor 4 ulp(f32); iteration count within the gap
+        # between the two oracle variants + 1.
+        assert sens is not None
+        env, dn = sens
+        assert abs(st.niter - g_niter) <= dn + 1, (st.niter, g_niter, dn)
+        k = min(len(res), len(g_res), len(env))
+        tol = np.maximum(F32_FLOOR, 10 * env[:k])
+        ok = np.abs(res[:k] - g_res[:k]) <= tol * np.abs(g_res[:k]) + 1e-6 * abs(g_res[0])
+        rel = np.abs(res[:k] - g_res[:k]) / np.maximum(np.abs(g_res[:k]), 1e-300)
+        assert np.all(ok), f"fp32 history deviates {rel[~ok].max():.3e} at iteration {np.argmax(~ok)} (allowed {tol[np.argmax(~ok)]:.3e})"
+
+
+def f32_dot_sensitivity(O, name):
+    """(running-max relative gap between the oracle's fp32 histories with sequential vs double-accumulated dots,
+    |difference of their iteration counts|)."""
+    solver, A, b, kw, dt = cases.build(name)
+    x0, s0 = getattr(O, solver)(A, b, dtype=dt, **kw)
+    with O.dot_mode(1):
+        x1, s1 = getattr(O, solver)(A, b, dtype=dt, **kw)
+    r0, r1 = np.asarray(s0["residuals"], float), np.asarray(s1["residuals"], float)
+    k = min(len(r0), len(r1))
+    env = np.full(max(len(r0), len(r1)) + 4, np.inf)
+    env[:k] = np.abs(r0[:k] - r1[:k]) / np.maximum(r0[:k], 1e-300)
+    return np.maximum.accumulate(env), abs(s0["niter"] - s1["niter"])
 
 
 @pytest.mark.parametrize("name", cases.NAMES)
@@ -79,7 +100,7 @@ def test_parity_with_golden_and_oracle(kb, O, name):
     x, st, launches = run_gpu(kb, name)
     g = GOLD[name]
     xo, so = cases.run_oracle(O, name)
-    sens = history_sensitivity(O, name)
+    sens = history_sensitivity(O, name) if dt == np.float64 else f32_dot_sensitivity(O, name)
     check_against(st, x, np.asarray(g["residuals"]), g["niter"], g["status"], dt, xo if dt == np.float64 else None, sens)
     check_against(st, x, np.asarray(so["residuals"]), so["niter"], so["status"], dt, None, sens)
     assert st.solved == so["solved"] and st.inconsistent == so["inconsistent"]
@@ -99,6 +120,17 @@ def test_fused_cg_equals_primitive_path(kb, name):
     for batch in (1, 3, 32):
         xb, sb, _ = run_gpu(kb, name, fused=True, batch=batch)
         assert sb.niter == s1.niter and np.array_equal(xb, x1) and sb.residuals == s1.residuals
+    # fused=True is the persistent cooperative kernel (one launch per batch of iterations); fused=2 keeps the
+    # two-launch kernels.  Same arithmetic except the summation tree of <r,r> (different grid): histories agree to
+    # rounding, and the persistent path needs far fewer launches.
+    x2, s2, l2 = run_gpu(kb, name, fused=2)
+    assert s2.niter == s1.niter and s2.status == s1.status
+    assert np.allclose(s1.residuals, s2.residuals, rtol=1e-10)
+    assert np.linalg.norm(x1 - x2) <= 1e-10 * np.linalg.norm(x2)
+    assert l1 < l2
+    for batch in (1, 5):
+        xb, sb, _ = run_gpu(kb, name, fused=2, batch=batch)
+        assert sb.niter == s2.niter and np.array_equal(xb, x2) and sb.residuals == s2.residuals
 
 
 def test_cg_statuses_and_flags(kb, O):
