@@ -500,6 +500,151 @@ __global__ void __launch_bounds__(kBlock, (P * P / TPR <= 32 ? 2 : 1)) panel_fas
 }
 
 
+// ---- tensor-core path for Float64, P in {8, 16, 32}: mma.sync.m8n8k4.f64 (SASS DMMA) ------------------------------
+// Same two operations as panel_fast_kernel (UPDATE: Out = beta Out + alpha In S;  GRAM: G = Next^T Out), one warp
+// per tile of 8 panel rows, no shuffles and no shared-memory tiles: every operand is loaded straight into the
+// fragment layout of the instruction, and the two products are oriented so that the OUTPUT fragment of the update
+// is, register for register, the INPUT fragment of the Gram product:
+//   update, transposed:  Out_tile^T (P x 8) = S^T (P x P) . In_tile^T (P x 8)
+//       A (8 x 4, row)  = S^T block   lane (a, b) holds S(i = kslot, j = 8 mb + a)        -- constant, staged in smem
+//       B (4 x 8, col)  = In_tile^T   lane (a, b) holds In[row a][kslot]                   -- 16-byte loads
+//       D (8 x 8)       = lane (a, b) holds Out[row 2b + e][col 8 mb + a], e = 0, 1
+//   Gram:  G (P x P) += L_tile^T (P x 8) . Out_tile (8 x P),  L = Next (or Out itself)
+//       A (8 x 4, row)  = L^T block   lane (a, b) holds L[row 2b + e][col 8 ib + a]       -- the D layout above
+//       B (4 x 8, col)  = Out block   lane (a, b) holds Out[row 2b + e][col 8 jb + a]     -- the D registers themselves
+//       the two k-steps e = 0 / 1 cover rows {0,2,4,6} / {1,3,5,7}: the reduction index may be permuted freely.
+// with a = lane >> 2, b = lane & 3 and kslot(ks, b) = 8 (ks / 2) + 2 b + (ks & 1) (again a permutation of the
+// reduction index, chosen so that one 16-byte load feeds two k-steps).  256 FMAs per instruction instead of 32:
+// the issue slots that bound the SIMT kernels at P >= 16 (profiles/r1_ncu_block_p8.txt) are freed, the kernels go
+// back to being HBM-bound.  Float32 panels keep the SIMT path.
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b, double c0, double c1) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %5};"
+               : "=d"(d0), "=d"(d1)
+               : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
+constexpr int kMmaWarps = 8;
+
+template <int P, bool UPDATE, bool GRAM>
+__global__ void __launch_bounds__(kMmaWarps * 32, (P <= 16 ? 3 : 2))
+panel_mma_kernel(int n, double alpha, const double* In, const double* __restrict__ S, double beta, double* Out, const double* Next,
+                 double* part, unsigned* ticket, double* G) {
+  constexpr int NB = P / 8;           // 8-column blocks of a panel row
+  constexpr int KS = P / 4;           // k-steps of the update
+  __shared__ double Sf[UPDATE ? KS * NB * 32 : 1];     // S^T fragments: [ks][mb][lane]
+  __shared__ double Gs[GRAM ? P * P : 1];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int a = lane >> 2, b = lane & 3;
+  if (UPDATE) {
+    for (int idx = tid; idx < KS * NB * 32; idx += kMmaWarps * 32) {
+      const int ks = idx / (NB * 32), mb = (idx / 32) % NB, l = idx % 32;
+      const int i = 8 * (ks >> 1) + 2 * (l & 3) + (ks & 1), j = 8 * mb + (l >> 2);
+      Sf[idx] = S[i + (size_t)j * P];                   // S is column-major: S(i, j)
+    }
+    __syncthreads();
+  }
+  double acc[GRAM ? NB : 1][GRAM ? NB : 1][2];
+  if (GRAM) {
+#pragma unroll
+    for (int i = 0; i < NB; i++)
+#pragma unroll
+      for (int j = 0; j < NB; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  }
+  const bool need_old = !UPDATE || beta != 0.0;
+  const int ntiles = (n + 7) >> 3;
+  for (int tile = blockIdx.x * kMmaWarps + warp; tile < ntiles; tile += gridDim.x * kMmaWarps) {
+    const int row0 = tile << 3;
+    // ---- loads (all issued before any use) ----
+    double inx[UPDATE ? NB : 1], iny[UPDATE ? NB : 1];            // In[row0 + a][8 q + 2 b], [.. + 1]
+    double old[NB][2], nx[GRAM ? NB : 1][2];
+    const int rin = row0 + a;
+    if (UPDATE) {
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        Vec2<double> v; v.x = 0.0; v.y = 0.0;
+        if (rin < n) v = ld2(In + (size_t)rin * P + 8 * q + 2 * b);
+        inx[q] = v.x; iny[q] = v.y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int r = row0 + 2 * b + e;
+      const bool ok = r < n;
+#pragma unroll
+      for (int mb = 0; mb < NB; mb++) {
+        old[mb][e] = (need_old && ok) ? Out[(size_t)r * P + 8 * mb + a] : 0.0;
+        if (GRAM) nx[mb][e] = (Next != nullptr && ok) ? Next[(size_t)r * P + 8 * mb + a] : 0.0;
+      }
+    }
+    // ---- update: D[mb] = sum_ks S^T frag x In frag ----
+    double o[NB][2];
+    if (UPDATE) {
+#pragma unroll
+      for (int mb = 0; mb < NB; mb++) {
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++)
+          dmma_884(c0, c1, Sf[(ks * NB + mb) * 32 + lane], (ks & 1) ? iny[ks >> 1] : inx[ks >> 1], c0, c1);
+        o[mb][0] = beta != 0.0 ? fma(alpha, c0, beta * old[mb][0]) : alpha * c0;
+        o[mb][1] = beta != 0.0 ? fma(alpha, c1, beta * old[mb][1]) : alpha * c1;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int r = row0 + 2 * b + e;
+        if (r < n) {
+#pragma unroll
+          for (int mb = 0; mb < NB; mb++) Out[(size_t)r * P + 8 * mb + a] = o[mb][e];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int mb = 0; mb < NB; mb++) { o[mb][0] = old[mb][0]; o[mb][1] = old[mb][1]; }
+    }
+    // ---- Gram: acc[ib][jb] += L^T frag x Out frag (rows past n contribute zeros) ----
+    if (GRAM) {
+#pragma unroll
+      for (int ib = 0; ib < NB; ib++)
+#pragma unroll
+        for (int jb = 0; jb < NB; jb++)
+#pragma unroll
+          for (int e = 0; e < 2; e++)
+            dmma_884(acc[ib][jb][0], acc[ib][jb][1], Next != nullptr ? nx[ib][e] : o[ib][e], o[jb][e], acc[ib][jb][0], acc[ib][jb][1]);
+    }
+  }
+  if (!GRAM) return;
+  // deterministic reduction: warps of the CTA in order, then the CTAs in order (last CTA finalises)
+  for (int e = tid; e < P * P; e += kMmaWarps * 32) Gs[e] = 0.0;
+  __syncthreads();
+  for (int w = 0; w < kMmaWarps; w++) {
+    if (warp == w) {
+#pragma unroll
+      for (int ib = 0; ib < NB; ib++)
+#pragma unroll
+        for (int jb = 0; jb < NB; jb++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) Gs[(8 * ib + a) + (size_t)(8 * jb + 2 * b + e) * P] += acc[ib][jb][e];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < P * P; e += kMmaWarps * 32) part[(size_t)blockIdx.x * (P * P) + e] = Gs[e];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+    if (is_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int pair = tid; pair < P * P; pair += kMmaWarps * 32) {
+    double s = 0.0;
+    for (int bk = 0; bk < (int)gridDim.x; bk++) s += __ldcg(&part[(size_t)bk * (P * P) + pair]);
+    G[pair] = s;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
@@ -548,11 +693,40 @@ template <class T> static void k_rows_diag(Ctx& c, int n, int p, const T* d, con
   rows_diag_kernel<T><<<stream_grid((long long)n * p, 1, 8), kBlock, 0, c.stream>>>((long long)n * p, p, d, in, out, ldiv ? 1 : 0);
   KB_CUDA(cudaGetLastError()); c.launches++;
 }
+// tensor-core dispatch (Float64, p = 8 / 16 / 32; KB200_BLOCK_MMA=0 keeps the SIMT kernels for A/B runs,
+// KB200_BLOCK_MMA=8 also routes p = 8 through the tensor cores)
+template <class T, bool UPDATE, bool GRAM>
+static bool launch_mma(BlockWorkspace<T>&, T, const T*, const T*, T, T*, const T*, T*, int) { return false; }
+template <bool UPDATE, bool GRAM>
+static bool launch_mma_f64(BlockWorkspace<double>& ws, double alpha, const double* In, const double* S, double beta, double* Out,
+                           const double* Next, double* G, int rows) {
+  Ctx& c = ws.ctx;
+  static const char* env = getenv("KB200_BLOCK_MMA");
+  static const int mode = env ? atoi(env) : 1;
+  if (mode == 0) return false;
+  const int p = ws.p;
+  if (!(p == 16 || p == 32 || (p == 8 && mode == 8))) return false;
+  const int ntiles = (rows + 7) / 8;
+  const int per_sm = p <= 16 ? 3 : 2;
+  const int grid = std::max(1, std::min(sm_count() * per_sm, (ntiles + kMmaWarps - 1) / kMmaWarps));
+  switch (p) {
+    case 8: panel_mma_kernel<8, UPDATE, GRAM><<<grid, kMmaWarps * 32, 0, c.stream>>>(rows, alpha, In, S, beta, Out, Next, ws.part, c.tickets + 6, G); break;
+    case 16: panel_mma_kernel<16, UPDATE, GRAM><<<grid, kMmaWarps * 32, 0, c.stream>>>(rows, alpha, In, S, beta, Out, Next, ws.part, c.tickets + 6, G); break;
+    default: panel_mma_kernel<32, UPDATE, GRAM><<<grid, kMmaWarps * 32, 0, c.stream>>>(rows, alpha, In, S, beta, Out, Next, ws.part, c.tickets + 6, G); break;
+  }
+  KB_CUDA(cudaGetLastError()); c.launches++;
+  return true;
+}
+template <> bool launch_mma<double, true, true>(BlockWorkspace<double>& ws, double al, const double* In, const double* S, double be, double* Out, const double* Nx, double* G, int rows) { return launch_mma_f64<true, true>(ws, al, In, S, be, Out, Nx, G, rows); }
+template <> bool launch_mma<double, true, false>(BlockWorkspace<double>& ws, double al, const double* In, const double* S, double be, double* Out, const double* Nx, double* G, int rows) { return launch_mma_f64<true, false>(ws, al, In, S, be, Out, Nx, G, rows); }
+template <> bool launch_mma<double, false, true>(BlockWorkspace<double>& ws, double al, const double* In, const double* S, double be, double* Out, const double* Nx, double* G, int rows) { return launch_mma_f64<false, true>(ws, al, In, S, be, Out, Nx, G, rows); }
+
 // fast-path dispatch: true when p has a register-resident specialization
 template <class T, bool UPDATE, bool GRAM>
 static bool launch_fast(BlockWorkspace<T>& ws, T alpha, const T* In, const T* S, T beta, T* Out, const T* Next, T* G, int rows) {
   Ctx& c = ws.ctx;
   if (ws.generic_kernels) return false;
+  if (launch_mma<T, UPDATE, GRAM>(ws, alpha, In, S, beta, Out, Next, G, rows)) return true;
   const int grid = ws.fast_grid;
   // KB200_FAST_TPR=alt selects the second lanes-per-row shape of P = 8 / 16 (sweeps, profiles/README.md)
   static const bool alt = getenv("KB200_FAST_TPR") != nullptr;

@@ -680,8 +680,16 @@ template <class T> int dist_init_t(Handle* h, int rank, int world, int nhalo, co
   if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) throw std::runtime_error("bad rank/world");
   KB_CUDA(cudaSetDevice(ws->ctx.device));
   if (h->solver == S_CG) {
-    if (!ws->p2) ws->p2 = dev_alloc<T>((size_t)ws->n);
-    KB_CUDA(cudaMemset(ws->p2, 0, sizeof(T) * (size_t)ws->n));
+    // r and the two direction buffers get a TAIL of nhalo entries: the persistent kernel stages the halo there and
+    // gathers column nloc + h as element nloc + h of the same array (cg_fused.cu)
+    KB_CUDA(cudaStreamSynchronize(ws->ctx.stream));
+    const size_t len = (size_t)ws->n + (size_t)(nhalo > 0 ? nhalo : 0);
+    T** bufs[3] = {&ws->r, &ws->p, &ws->p2};
+    for (T** b : bufs) {
+      dev_free(*b);
+      *b = dev_alloc<T>(len);
+      KB_CUDA(cudaMemset(*b, 0, sizeof(T) * len));
+    }
   }
   ws->dist.rank = rank; ws->dist.world = world;
   int *dr = nullptr, *dof = nullptr;

@@ -252,9 +252,10 @@ __global__ void __launch_bounds__(kBlock) cg_k2(int n, T* __restrict__ x, T* __r
 //     row-partitioned, the cross-GPU all-reduce with a full warp, then releases the others.
 // Row-partitioned (MODE = kDist): the halo is STAGED instead of being pulled nonzero by nonzero.  At the start of
 // phase A every CTA's producer warp fetches its share of the halo list from the owners' r and p buffers with
-// coalesced system-scope loads (all in flight at once: one NVLink round trip), forms p_halo = r + beta p and
-// stores it into the local halo buffer; tiles with halo columns are ordered LAST in every CTA's tile sequence
-// (tile_order) and wait for the staging counter, so the exchange hides behind the interior tiles.
+// coalesced system-scope loads (all in flight at once: one NVLink round trip) and stores the entries into the
+// TAILS of the local r and p buffers (nloc + nhalo entries each), so that the gather is the single-GPU code with
+// no halo branch at all; tiles with halo columns are ordered LAST in every CTA's tile sequence (tile_order) and
+// wait for the staging counter, so the exchange hides behind the interior tiles.
 //
 // Memory model: vectors written in one phase are read in the next through plain (coherent) loads after the
 // barrier's acquire; nothing that changes during the launch is read through the non-coherent path (__ldg).
@@ -336,8 +337,8 @@ struct CgPersistArgs {
   const T* mdiag;            // kJacobi
   HaloMap halo;              // kDist ...
   const CgPeerTab<T>* tab;
-  T* phalo;                  // local halo buffer: p_halo = r + beta p of the halo columns, rebuilt every iteration
   const int* tile_order;     // interior tiles first, tiles with halo columns last (bit 31 set)
+  int n_interior;            // number of interior tiles = first halo position of tile_order
   int max_iters;
   int timed;                 // accumulate phase durations (CTA 0, %globaltimer) into the GridBar block
 };
@@ -348,7 +349,39 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-template <class T, int MODE, int MINB>
+// Halo staging of the row-partitioned persistent kernel (one warp per CTA): this CTA's share of the halo list, all
+// loads in flight at once.  The halo entries of r and of the old direction land in the TAILS of the local vectors
+// (r and the p buffers of a row-partitioned workspace hold nloc + nhalo entries), so the gather of phase A is
+// exactly the single-GPU code: column j >= nloc is simply element j of the same array.  One entry per lane and
+// trip (U = 1; the compiler unrolls the loop itself): with 8 explicit entries in flight per lane ptxas scheduled the
+// CONSUMER warps' gather batches of the same kernel as load -> use chains (checked in SASS; the staging has a whole
+// phase A to finish, its latency is hidden behind the interior tiles anyway).
+template <class T>
+__device__ __forceinline__ void cg_stage_halo(HaloMap halo, const CgPeerTab<T>* tab, T* r, T* p_old, int pb, int G, int lane) {
+  const int nh = halo.nhalo, nloc = halo.nloc;
+  const int per = (nh + G - 1) / G;
+  const int h0 = (int)blockIdx.x * per, h1 = min(nh, h0 + per);
+  constexpr int U = 1;
+  for (int hb = h0 + lane; hb < h1; hb += 32 * U) {
+    T rv[U], pv[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int h = hb + 32 * u;
+      if (h < h1) {
+        const int rk = __ldg(&halo.src_rank[h]), off = __ldg(&halo.src_off[h]);
+        rv[u] = ld_sys(tab->r[rk] + off);
+        pv[u] = ld_sys(tab->p[pb][rk] + off);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int h = hb + 32 * u;
+      if (h < h1) { __stcg(&r[nloc + h], rv[u]); __stcg(&p_old[nloc + h], pv[u]); }
+    }
+  }
+}
+
+template <class T, int MODE, int MINB, int DEPTH>
 __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPersistArgs<T> a, CgState<T>* st, T* part,
                                                                 GridBar* gb, DistComm* dc) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -364,6 +397,8 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPer
     const int q = blockIdx.x + j * G;
     return MODE == kDist ? __ldg(&a.tile_order[q]) : q;
   };
+  // row-partitioned: positions >= n_interior of the tile order are halo tiles; this CTA owns positions b + j G
+  const int cnt_int = MODE == kDist ? max(0, min(cnt, (a.n_interior - (int)blockIdx.x + G - 1) / G)) : cnt;
   const unsigned pre = (unsigned)min(P.S, cnt);
   const uint64_t pol = l2_evict_first_policy();
   unsigned ppos = 0, cpos = 0;
@@ -382,29 +417,7 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPer
     // ------------------------------ phase A (= K1) ------------------------------
     if (warp == kConsumerWarps) {
       if (MODE == kDist) {
-        // halo staging: this CTA's share of the halo list, all loads in flight at once
-        const int nh = a.halo.nhalo;
-        const int per = (nh + G - 1) / G;
-        const int h0 = (int)blockIdx.x * per, h1 = min(nh, h0 + per);
-        const int pb = iter & 1;
-        constexpr int U = 8;
-        for (int hb = h0 + lane; hb < h1; hb += 32 * U) {
-          T rv[U], pv[U];
-#pragma unroll
-          for (int u = 0; u < U; u++) {
-            const int h = hb + 32 * u;
-            if (h < h1) {
-              const int rk = __ldg(&a.halo.src_rank[h]), off = __ldg(&a.halo.src_off[h]);
-              rv[u] = ld_sys(a.tab->r[rk] + off);
-              pv[u] = ld_sys(a.tab->p[pb][rk] + off);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < U; u++) {
-            const int h = hb + 32 * u;
-            if (h < h1) __stcg(&a.phalo[h], add_rn(rv[u], mul_rn(beta, pv[u])));
-          }
-        }
+        cg_stage_halo<T>(a.halo, a.tab, a.r, p_old, iter & 1, G, lane);
         __threadfence();
         __syncwarp();
         if (lane == 0) atomicAdd(&gb->halo_ready, 1u);
@@ -416,20 +429,8 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPer
     } else {
       const T* r = a.r;
       const T* mdiag = a.mdiag;
-      const T* phalo = a.phalo;
-      const int nloc = a.halo.nloc;
-      const T* phalo_m = phalo - nloc;
-      auto gather = [&](int j) -> T {          // p_j = z_j + beta p_j (cg.jl:259 applied on the fly)
-        if (MODE == kDist) {
-          // halo column: the staged value p_halo[j - nloc] (already r + beta p); branch-free so that the batch of
-          // gathers stays straight-line: select the base pointer, clamp the p index, select a zero
-          const bool loc = j < nloc;
-          const T* base = loc ? r : phalo_m;
-          const T zv = base[j];
-          const T pv = p_old[loc ? j : 0];
-          return add_rn(zv, mul_rn(beta, loc ? pv : T(0)));
-        }
-        T z = r[j];
+      auto gather = [&](int j) -> T {          // p_j = z_j + beta p_j (cg.jl:259 applied on the fly); row-partitioned:
+        T z = r[j];                            // j >= nloc reads the staged tail of the same arrays
         if (MODE == kJacobi) z = mul_rn(__ldg(&mdiag[j]), z);
         return add_rn(z, mul_rn(beta, p_old[j]));
       };
@@ -448,13 +449,18 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPer
         if (xup) a.x[row] = add_rn(q.xr, mul_rn(alpha_prev, q.po));
         dacc += q.pn * acc;
       };
-      auto pre_tile = [&]() {
-        if (MODE == kDist) {
+      if (MODE == kDist) {
+        // interior tiles first; the tiles with halo columns (last in this CTA's sequence) only after every CTA's
+        // producer warp has staged its share of the halo
+        tile_consume_pass<T, DEPTH>(A, P, cpos, 0, cnt_int, tile_at, gather, row_begin, row_done);
+        if (cnt_int < cnt) {
           if (lane == 0) { while (ld_acquire_gpu_u32(&gb->halo_ready) < (unsigned)G) { } }
           __syncwarp();
+          tile_consume_pass<T, DEPTH>(A, P, cpos, cnt_int, cnt, tile_at, gather, row_begin, row_done);
         }
-      };
-      tile_consume_pass<T>(A, P, cpos, cnt, tile_at, gather, row_begin, row_done, pre_tile);
+      } else {
+        tile_consume_pass<T, DEPTH>(A, P, cpos, 0, cnt, tile_at, gather, row_begin, row_done);
+      }
     }
     passes = k + 1;
     bool ok = grid_reduce_barrier<T>(gb, dacc, part, sm, sflag, [&](T tot) {
@@ -580,6 +586,7 @@ template <class T> void cg_dist_tile_order(Workspace<T>& ws, const Csr<T>& A) {
     c.sync();
     ord.reserve(nt);
     for (int t = 0; t < nt; t++) if (!fl[t]) ord.push_back(t);
+    ws.dist.tile_order_interior = (int)ord.size();
     for (int t = 0; t < nt; t++) if (fl[t]) ord.push_back((int)((unsigned)t | 0x80000000u));
     KB_CUDA(cudaMemcpyAsync(ws.dist.tile_order, ord.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, c.stream));
     c.sync();
@@ -706,7 +713,17 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   memset(&pa, 0, sizeof(pa));
   GridBar* gbar = (GridBar*)((char*)ws.fused_state + kOffGridBar);
   if (persist) {
-    kp = dist ? cg_persist<T, kDist, 3> : (jac ? cg_persist<T, kJacobi, 3> : cg_persist<T, kPlain, 3>);
+    // register budget follows the plan's CTAs per SM: 3 (72 registers, the default plan) or 2 (112 registers: all 16
+    // loads of an 8-nonzero gather batch in flight per thread; selected with KB200_CTAS_PER_SM=2 / large tiles)
+    static const char* edep = getenv("KB200_GATHER_DEPTH");
+    const int depth = edep ? atoi(edep) : 0;
+    if (A.ctas_per_sm >= 3) {
+      if (depth == 8) kp = dist ? cg_persist<T, kDist, 3, 8> : (jac ? cg_persist<T, kJacobi, 3, 8> : cg_persist<T, kPlain, 3, 8>);
+      else kp = dist ? cg_persist<T, kDist, 3, 4> : (jac ? cg_persist<T, kJacobi, 3, 4> : cg_persist<T, kPlain, 3, 4>);
+    } else {
+      if (depth == 4) kp = dist ? cg_persist<T, kDist, 2, 4> : (jac ? cg_persist<T, kJacobi, 2, 4> : cg_persist<T, kPlain, 2, 4>);
+      else kp = dist ? cg_persist<T, kDist, 2, 8> : (jac ? cg_persist<T, kJacobi, 2, 8> : cg_persist<T, kPlain, 2, 8>);
+    }
     ensure_dyn_smem((const void*)kp, 220 * 1024);
     int occ = 0;
     KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kp, kTileThreads, A.smem_bytes));
@@ -731,8 +748,8 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
       KB_CUDA(cudaMemcpyAsync(dtab, htab, sizeof(*htab), cudaMemcpyHostToDevice, c.stream));
       pa.halo = ws.dist.halo;
       pa.tab = dtab;
-      pa.phalo = ws.dist.halo_buf;
       pa.tile_order = ws.dist.tile_order;
+      pa.n_interior = ws.dist.tile_order_interior;
     }
   }
 

@@ -218,6 +218,7 @@ struct Workspace {
     int* tile_order = nullptr;                  // persistent CG: interior tiles first, halo tiles last (device)
     const void* tile_order_for = nullptr;       // ... built for this operator
     int tile_order_n = 0;
+    int tile_order_interior = 0;                // number of tiles without halo columns (they come first)
     PushRange push[kMaxPushRanges];
   } dist;
 };

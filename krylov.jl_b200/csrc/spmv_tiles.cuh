@@ -296,18 +296,17 @@ __device__ __forceinline__ void tile_drain(const TilePipe<T>& P, unsigned consum
   for (unsigned q = consumed; q < pos; q++) mbar_wait(&P.full[q % (unsigned)P.S], (q / (unsigned)P.S) & 1);
 }
 
-// Consumers (threads 0 .. kTileRows-1): one pass over this CTA's cnt tiles.
-template <class T, class TileAt, class Gather, class RowBegin, class RowDone, class PreTile>
-__device__ __forceinline__ void tile_consume_pass(const Csr<T>& A, const TilePipe<T>& P, unsigned& cpos, int cnt, TileAt tile_at,
-                                                  Gather gather, RowBegin row_begin, RowDone row_done, PreTile pre_tile) {
+// Consumers (threads 0 .. kTileRows-1): tiles j0 <= j < j1 of this CTA's sequence (a pass is one call with
+// [0, cnt), or two calls when something must happen between the interior tiles and the halo tiles).
+template <class T, int DEPTH, class TileAt, class Gather, class RowBegin, class RowDone>
+__device__ __forceinline__ void tile_consume_pass(const Csr<T>& A, const TilePipe<T>& P, unsigned& cpos, int j0, int j1, TileAt tile_at,
+                                                  Gather gather, RowBegin row_begin, RowDone row_done) {
   constexpr int VA = 16 / sizeof(T);
   const int tid = threadIdx.x, lane = tid & 31;
-  for (int j = 0; j < cnt; j++, cpos++) {
-    const int traw = tile_at(j);
-    const int t = traw & 0x7fffffff;
+  for (int j = j0; j < j1; j++, cpos++) {
+    const int t = tile_at(j) & 0x7fffffff;
     const int row = t * kTileRows + tid;
     auto pre = row_begin(row < A.n ? row : 0);
-    if (traw < 0) pre_tile();
     const int s = (int)(cpos % (unsigned)P.S);
     mbar_wait(&P.full[s], (cpos / (unsigned)P.S) & 1);
     const unsigned char* st = P.ring + (size_t)s * P.L.stage_bytes();
@@ -323,17 +322,18 @@ __device__ __forceinline__ void tile_consume_pass(const Csr<T>& A, const TilePip
       // The gathers here are plain (coherent) loads, which the compiler will not speculate: guarded loads would
       // be chained load -> use -> load.  Clamp the index instead (every address is valid) and select the sum, so
       // the batch is straight-line code and all gathers of a row are issued together.
-      for (int k = kb; k < ke; k += kGatherDepth) {
-        T xv[kGatherDepth], av[kGatherDepth];
+      for (int k = kb; k < ke; k += DEPTH) {
+        T xv[DEPTH], av[DEPTH];
 #pragma unroll
-        for (int u = 0; u < kGatherDepth; u++) {
-          const int kk = min(k + u, ke - 1);
-          av[u] = vrow[kk];
-          xv[u] = gather(crow[kk]);
-        }
-        asm volatile("" ::: "memory");        // keep the loads above the sums (the optimiser would sink them)
+        for (int u = 0; u < DEPTH; u++) xv[u] = gather(crow[min(k + u, ke - 1)]);
+        asm volatile("" ::: "memory");        // keep the gathers above everything else (the optimiser would sink them)
+        // the matrix values come from shared memory (short latency): fetch them only now, so that the registers
+        // of the batch hold gathered data instead -- at 72 registers per thread that is the difference between
+        // 2 and 8 global loads in flight
 #pragma unroll
-        for (int u = 0; u < kGatherDepth; u++) {
+        for (int u = 0; u < DEPTH; u++) av[u] = vrow[min(k + u, ke - 1)];
+#pragma unroll
+        for (int u = 0; u < DEPTH; u++) {
           const T nx = add_rn(acc, mul_rn(av[u], xv[u]));
           acc = (k + u < ke) ? nx : acc;
         }

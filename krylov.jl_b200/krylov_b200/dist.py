@@ -258,6 +258,8 @@ def _run_workload(N, iters, steps, warmup, rank, world, local, dev, torch, dist,
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if sampler is not None else None
+    dws.solve(b, time_kernels=True, **kw)       # phase durations measured inside the persistent kernel (rank-local)
+    k1_ms, k2_ms, timed = dws.ws.kernel_times
     # parity material (not timed): the residual history of one more solve, identical on every rank because every
     # rank derives alpha / beta / rNorm from the same all-reduced scalars -- checked here, then compared by rank 0
     dws.solve(b, history=True, **kw)
@@ -272,7 +274,9 @@ def _run_workload(N, iters, steps, warmup, rank, world, local, dev, torch, dist,
     del csr, b, bd
     torch.cuda.empty_cache()
     return dict(ms=ms, launches=int(launches.item()), e2e_s=float(e2e_s.item()), clocks=clocks, hist=hist,
-                ranks_agree=ranks_agree, status=status)
+                ranks_agree=ranks_agree, status=status,
+                phases=dict(phase_a_ms=k1_ms, phase_b_ms=k2_ms, timed_iterations=timed,
+                            note="rank 0, measured inside cg_persist (%globaltimer), grid barrier + cross-GPU all-reduce included"))
 
 
 def bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler, parity_block=None, golden_parity=None):
@@ -319,7 +323,8 @@ def bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler, pa
                                 parallelism=f"rows/{world}: halo staged over NVLink P2P inside the kernel + in-kernel all-reduce",
                                 l2="per-rank matrix slab %.0f MB" % (nnz * 12 / world / 1e6), status=res["status"]),
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak * world, unit="GB/s", frac=achieved / (peak * world),
-                                  traffic=None, peak_source=src + f" x {world} GPUs", bytes_per_iteration=B),
+                                  traffic=None, peak_source=src + f" x {world} GPUs", bytes_per_iteration=B,
+                                  kernels=res["phases"]),
                     clocks=res["clocks"],
                     e2e=dict(value=its / res["e2e_s"], unit="it/s", h2d_bytes_per_step=n * 8, d2h_bytes_per_step=n * 8),
                     gpu_launches=res["launches"])
@@ -339,7 +344,7 @@ def bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler, pa
             line["cfg5"] = dict(workload=f"cg! on get_div_grad({N5},{N5},{N5}) (n = {n5}, nnz = {nnz5}) row-partitioned over {world} GPUs, "
                                          f"{it5} iterations per step, {st5} steps", value=v5, unit="it/s", n_gpus=world,
                                 ms_per_step=r5["ms"] / st5, frac=B5 * v5 / 1e9 / (peak * world), bytes_per_iteration=B5,
-                                e2e=dict(value=st5 * it5 / r5["e2e_s"], unit="it/s"), parity=p5,
+                                e2e=dict(value=st5 * it5 / r5["e2e_s"], unit="it/s"), parity=p5, kernels=r5["phases"],
                                 speedup_note="north_star target: value at 8 GPUs >= 6 x value at 1 GPU (same key on the N=1 line)")
         print(json.dumps(line))
         bad = [k for k, p in (("parity", line.get("parity")), ("cfg5.parity", (line.get("cfg5") or {}).get("parity"))) if p and p.get("ok") is False]

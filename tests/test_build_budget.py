@@ -78,3 +78,67 @@ def test_tma_and_mbarrier_instructions_present_in_sass():
         sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
         assert "UBLKCP" in sass, obj                                   # 1-D bulk TMA copies (cp.async.bulk)
         assert "SYNCS.PHASECHK" in sass or "SYNCS.ARRIVE" in sass, obj  # mbarrier wait / arrive
+
+
+def _sass_of(obj, mangled_substr):
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    path = os.path.join(BUILD, obj + ".o")
+    if not os.path.exists(path):
+        pytest.skip("objects absent: run __graft_entry__.build()")
+    sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    out, keep = [], False
+    for line in sass.splitlines():
+        if "Function :" in line:
+            keep = mangled_substr in line
+        elif keep:
+            out.append(line)
+    assert out, mangled_substr
+    return out
+
+
+def test_persistent_cg_register_budget_and_coherent_loads():
+    """cg_persist: 72 registers (3 CTAs of 288 threads per SM) without spills, and -- because the vectors change
+    between the phases of ONE launch -- no vector is read through the non-coherent path (LDG...CONSTANT may only
+    appear for the matrix structure / tile order, which are 32-bit loads)."""
+    ents = _entries("cg_fused")
+    dm = _demangle([e[0] for e in ents])
+    hit = [(dm[n], r, s) for n, r, s in ents if "cg_persist<double" in dm[n] and ", 3, " in dm[n]]
+    assert len(hit) >= 3
+    for name, regs, spill in hit:
+        assert regs <= 72 and spill == 0, (name, regs, spill)
+    for mode in (0, 1):
+        body = _sass_of("cg_fused", f"cg_persistIdLi{mode}ELi3ELi8")
+        assert not any("LDG.E.64.CONSTANT" in l for l in body), "a Float64 vector is read through the read-only path"
+
+
+def test_gather_batches_keep_loads_in_flight():
+    """The x gathers of a row must be ISSUED together (clamped indices, spmv_tiles.cuh): in the SASS of the hot
+    kernels the longest run of 64-bit global loads with no FP64 instruction in between is at least 6 (round 1's
+    guarded gathers compiled to load -> use chains with 2 in flight)."""
+    def longest_run(body):
+        best = cur = 0
+        for l in body:
+            if "LDG.E.64" in l and "STRONG" not in l:
+                cur += 1
+                best = max(best, cur)
+            elif "DMUL" in l or "DADD" in l or "DFMA" in l:
+                cur = 0
+        return best
+    assert longest_run(_sass_of("cg_fused", "cg_persistIdLi0ELi3ELi8")) >= 6
+    assert longest_run(_sass_of("cg_fused", "cg_persistIdLi1ELi3ELi8")) >= 6       # row-partitioned variant
+    assert longest_run(_sass_of("cg_fused", "cg_k1_tmaIdLi0ELi3ELb1")) >= 6
+    assert longest_run(_sass_of("spmv", "spmv_tma_kernelIdLb0ENS_6XPlain")) >= 6
+
+
+def test_block_panel_kernels_use_fp64_tensor_cores():
+    """SURVEY 8f-2 / north_star: the tall-skinny panel products of block_gmres! run on the tensor cores --
+    mma.sync.m8n8k4.f64 = SASS DMMA in every panel_mma_kernel instantiation (p = 8, 16, 32)."""
+    for p in (8, 16, 32):
+        body = _sass_of("block", f"panel_mma_kernelILi{p}ELb1ELb1")
+        n = sum("DMMA" in l for l in body)
+        assert n >= (p // 8) * (p // 4) + 2 * (p // 8) ** 2, (p, n)
+    ents = _entries("block")
+    dm = _demangle([e[0] for e in ents])
+    for name, regs, spill in [(dm[n], r, s) for n, r, s in ents if "panel_mma_kernel<" in dm[n]]:
+        assert regs <= 128 and spill <= 32, (name, regs, spill)

@@ -91,8 +91,12 @@ def test_cfg4_bicgstab_f32_random5e6_history_matches_oracle(kb, O):
     ok = dev <= tol * r0[:k] + 1e-6 * r0[0]
     assert np.all(ok), (f"iteration {np.argmax(~ok)}: deviation {(dev / r0[:k])[np.argmax(~ok)]:.3e}, "
                         f"allowed {tol[np.argmax(~ok)]:.3e}")
-    # the early iterations are well conditioned: there the GPU must agree to ~1e-5 regardless of the envelope
-    assert (dev[:4] / r0[:4]).max() <= 1e-4
+    # (a sequential Float32 sum of 5e6 squares is itself off by ~2e-3 -- the envelope starts there, at iteration 0.)
+    # Against the double-accumulated variant of the oracle the GPU's tree sums must be much closer: same envelope
+    # allowance, and in the first iterations (before the recurrence amplifies anything) within 1e-4.
+    devA = np.abs(res[:k] - r1[:k]) / np.maximum(r1[:k], 1e-300)
+    assert np.all(devA <= tol + 1e-6), devA.max()
+    assert devA[:3].max() <= 1e-4, devA[:3]
     ws.free()
 
 

@@ -35,26 +35,32 @@ def test_distributed_cg_matches_single_gpu_and_oracle(tmp_path, O, world):
         csr, hr, ho, nloc = D.make_poisson_rank({N}, rank, world, torch, dev)
         ws = D.DistCgWorkspace(csr, hr, ho, rank, world)
         b = torch.ones(nloc, dtype=torch.float64, device=dev)
-        for rep in range(2):                       # second solve re-uses the workspace (buffer swap bookkeeping)
-            ws.solve(b, atol=0.0, rtol=1e-8, history=True)
-        st = ws.stats
-        xs = [None] * world
-        dist.all_gather_object(xs, ws.x.cpu().numpy())
+        out = {{}}
+        # fused=True: persistent cooperative kernel (halo staged per iteration, warp-parallel all-reduce);
+        # fused=2: the two-launch kernels with the per-nonzero halo pull
+        for tag, fused in (("persist", True), ("two_launch", 2)):
+            for rep in range(2):                   # second solve re-uses the workspace (buffer swap bookkeeping)
+                ws.solve(b, atol=0.0, rtol=1e-8, history=True, fused=fused)
+            st = ws.stats
+            xs = [None] * world
+            dist.all_gather_object(xs, ws.x.cpu().numpy())
+            out[tag] = dict(niter=st.niter, residuals=st.residuals, status=st.status, x=np.concatenate(xs).tolist(),
+                            launches=ws.ws.launches)
         if rank == 0:
-            json.dump(dict(niter=st.niter, residuals=st.residuals, status=st.status, x=np.concatenate(xs).tolist()),
-                      open({str(tmp_path / 'out.json')!r}, "w"))
+            json.dump(out, open({str(tmp_path / 'out.json')!r}, "w"))
         ws.free(); dist.destroy_process_group()
     """))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                           "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    res = json.load(open(tmp_path / "out.json"))
+    both = json.load(open(tmp_path / "out.json"))
     A, b = O.sparse_laplacian(N)
     xo, so = O.cg(A, b, atol=0.0, rtol=1e-8)
-    assert res["niter"] == so["niter"] and res["status"] == so["status"]
-    assert np.allclose(res["residuals"], so["residuals"], rtol=1e-6)
-    assert np.linalg.norm(np.array(res["x"]) - xo) <= 1e-6 * np.linalg.norm(xo)
+    for tag, res in both.items():
+        assert res["niter"] == so["niter"] and res["status"] == so["status"], tag
+        assert np.allclose(res["residuals"], so["residuals"], rtol=1e-6), tag
+        assert np.linalg.norm(np.array(res["x"]) - xo) <= 1e-6 * np.linalg.norm(xo), tag
 
 
 def test_distributed_other_solvers_match_oracle(tmp_path, O):
