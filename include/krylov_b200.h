@@ -144,6 +144,13 @@ int krylov_b200_attach_csr(void *ws, void *csr);
 /* Diagonal preconditioner: which = 0 -> M, 1 -> N; d[n] holds the diagonal of
  * the operator the solver applies (P^-1 with the default ldiv=false). NULL detaches. */
 int krylov_b200_set_preconditioner_diag(void *ws, int which, const void *d, int location);
+/* Block-Jacobi preconditioner (docs/src/preconditioners.md:33,159): which = 0 -> M, 1 -> N; blocks[ceil(n/bs)][bs][bs]
+ * (row-major dense diagonal blocks, 2 <= bs <= 8, element type = workspace dtype; a last block of n % bs rows uses
+ * its leading part) of the operator the solver applies (P^-1 with the default ldiv = false; with ldiv = true the
+ * blocks are P and their inverses, formed once here, are applied).  cg! with M block-diagonal runs the persistent
+ * fused kernel (z = M r formed block by block in the r-update phase); every other solver applies it as one extra
+ * kernel per product.  A diagonal set with krylov_b200_set_preconditioner_diag takes precedence.  NULL detaches. */
+int krylov_b200_set_preconditioner_blockdiag(void *ws, int which, int bs, const void *blocks, int location);
 
 /* cg_lanczos! (src/cg_lanczos.jl) has no slot in the reference's KrylovSolverType; this value selects it in
  * krylov_workspace_create.  Options: M, check_curvature (KrylovB200Options), the common tolerances. */

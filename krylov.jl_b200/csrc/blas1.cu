@@ -145,6 +145,69 @@ template <class T> void k_diagmul(Ctx& c, int n, T* y, const T* d, const T* x, b
 }
 
 // ---------------------------------------------------------------------------
+// Block-Jacobi: y = blockdiag(B_0, B_1, ...) x with dense bs x bs blocks (row-major), bs in 2..8
+// (docs/src/preconditioners.md:33 -- the operator handed to the solver is P^-1).
+// One thread per block; the row sums run left to right, non-contracted, like every k* primitive.
+// ---------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(kBlock) blockdiag_mul_kernel(int n, int bs, const T* __restrict__ B, const T* __restrict__ x, T* __restrict__ y) {
+  const int nb = (n + bs - 1) / bs;
+  for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nb; blk += gridDim.x * blockDim.x) {
+    const int r0 = blk * bs, rows = min(bs, n - r0);
+    const T* Bk = B + (size_t)blk * bs * bs;
+    T xv[8];
+    for (int j = 0; j < rows; j++) xv[j] = x[r0 + j];
+    for (int i = 0; i < rows; i++) {
+      T acc = T(0);
+      for (int j = 0; j < rows; j++) acc = add_rn(acc, mul_rn(Bk[i * bs + j], xv[j]));
+      y[r0 + i] = acc;
+    }
+  }
+}
+template <class T> void k_blockdiag_mul(Ctx& c, int n, int bs, const T* blocks, const T* x, T* y) {
+  if (n <= 0) return;
+  blockdiag_mul_kernel<T><<<stream_grid((n + bs - 1) / bs, 1, 8), kBlock, 0, c.stream>>>(n, bs, blocks, x, y);
+  KB_CUDA(cudaGetLastError());
+  c.launches++;
+}
+
+// inverse of every diagonal block (Gauss-Jordan with partial pivoting, one thread per block): ldiv = true with a
+// block-diagonal P applies these
+template <class T>
+__global__ void __launch_bounds__(kBlock) blockdiag_invert_kernel(int n, int bs, const T* __restrict__ B, T* __restrict__ Inv, int* singular) {
+  const int nb = (n + bs - 1) / bs;
+  for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nb; blk += gridDim.x * blockDim.x) {
+    const int rows = min(bs, n - blk * bs);
+    T a[8][16];
+    for (int i = 0; i < rows; i++)
+      for (int j = 0; j < rows; j++) { a[i][j] = B[(size_t)blk * bs * bs + i * bs + j]; a[i][rows + j] = i == j ? T(1) : T(0); }
+    bool bad = false;
+    for (int col = 0; col < rows; col++) {
+      int piv = col;
+      for (int i = col + 1; i < rows; i++) if (fabs(a[i][col]) > fabs(a[piv][col])) piv = i;
+      if (a[piv][col] == T(0)) { bad = true; break; }
+      if (piv != col) for (int j = 0; j < 2 * rows; j++) { const T t = a[col][j]; a[col][j] = a[piv][j]; a[piv][j] = t; }
+      const T d = T(1) / a[col][col];
+      for (int j = 0; j < 2 * rows; j++) a[col][j] *= d;
+      for (int i = 0; i < rows; i++) {
+        if (i == col) continue;
+        const T f = a[i][col];
+        for (int j = 0; j < 2 * rows; j++) a[i][j] -= f * a[col][j];
+      }
+    }
+    if (bad) atomicExch(singular, 1);
+    for (int i = 0; i < bs; i++)
+      for (int j = 0; j < bs; j++) Inv[(size_t)blk * bs * bs + i * bs + j] = (!bad && i < rows && j < rows) ? a[i][rows + j] : T(0);
+  }
+}
+template <class T> void k_blockdiag_invert(Ctx& c, int n, int bs, const T* blocks, T* inv, int* singular) {
+  if (n <= 0) return;
+  blockdiag_invert_kernel<T><<<stream_grid((n + bs - 1) / bs, 1, 4), kBlock, 0, c.stream>>>(n, bs, blocks, inv, singular);
+  KB_CUDA(cudaGetLastError());
+  c.launches++;
+}
+
+// ---------------------------------------------------------------------------
 // Reductions
 // ---------------------------------------------------------------------------
 template <class T, int K>
@@ -281,7 +344,9 @@ void dist_check_alive(Ctx& c) {
   template void k_scalcopy<T>(Ctx&, int, T*, T, const T*);                             \
   template void k_divcopy<T>(Ctx&, int, T*, const T*, T);                              \
   template void k_fill<T>(Ctx&, int, T*, T);                                           \
-  template void k_diagmul<T>(Ctx&, int, T*, const T*, const T*, bool);
+  template void k_diagmul<T>(Ctx&, int, T*, const T*, const T*, bool);                 \
+  template void k_blockdiag_mul<T>(Ctx&, int, int, const T*, const T*, T*);            \
+  template void k_blockdiag_invert<T>(Ctx&, int, int, const T*, T*, int*);
 INST(double)
 INST(float)
 #undef INST

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kBlock) spmm_rows_kernel(Csr<T> A, int p, cons
 // P lanes share a row (see the consumer loop).  Row sums accumulate in ascending column order, non-contracted, like
 // the SpMV.
 template <class T, int P>
-__global__ void __launch_bounds__(kTileThreads) spmm_tma_kernel(Csr<T> A, const T* __restrict__ X, T* __restrict__ Y) {
+__global__ void __launch_bounds__(kTileThreads, 3) spmm_tma_kernel(Csr<T> A, const T* __restrict__ X, T* __restrict__ Y) {
   extern __shared__ __align__(128) unsigned char smem[];
   const TileLayout<T> L{A.tile_cap};
   const int S = A.stages;
@@ -105,25 +105,47 @@ __global__ void __launch_bounds__(kTileThreads) spmm_tma_kernel(Csr<T> A, const 
       const int* crow = cs - (k0 & ~3);
       constexpr int RPW = 32 / P;
       const int rsub = lane / P, c = lane % P;
+      // RU rows per trip with independent accumulators, D nonzeros of each row per batch: RU * D gathers of the
+      // panel in flight per lane (a row-at-a-time loop leaves one row's 7 gathers in flight and the warp idles on
+      // their latency 32 times per tile at P = 32).  Indices are clamped into the row and the sums selected, so the
+      // batch is straight-line code (spmv_tiles.cuh); every row still accumulates in ascending column order.
+      constexpr int RU = P >= 4 ? 4 : P, D = 4;
 #pragma unroll 1
-      for (int step = 0; step < P; step++) {
-        const int lr = warp * 32 + step * RPW + rsub;          // row inside the tile
-        const int grow = t * kTileRows + lr;
-        if (grow < A.n) {
-          const int kb = rp[lr], ke = rp[lr + 1];
-          T acc = T(0);
-          for (int k = kb; k < ke; k += kGatherDepth) {
-            T xv[kGatherDepth], av[kGatherDepth];
+      for (int step = 0; step < P; step += RU) {
+        int kb[RU], ke[RU];
+        T acc[RU];
+        int kmax = 0;
 #pragma unroll
-            for (int u = 0; u < kGatherDepth; u++) {
-              if (k + u < ke) { av[u] = vrow[k + u]; xv[u] = __ldg(&X[(size_t)crow[k + u] * P + c]); }
-            }
+        for (int u = 0; u < RU; u++) {
+          const int lr = warp * 32 + (step + u) * RPW + rsub;    // row inside the tile
+          kb[u] = rp[lr]; ke[u] = rp[lr + 1];
+          acc[u] = T(0);
+          kmax = max(kmax, ke[u] - kb[u]);
+        }
+        kmax = __reduce_max_sync(0xffffffffu, kmax);               // uniform trip count for the warp
+        for (int kk = 0; kk < kmax; kk += D) {
+          T xv[RU][D];
 #pragma unroll
-            for (int u = 0; u < kGatherDepth; u++) {
-              if (k + u < ke) acc = add_rn(acc, mul_rn(av[u], xv[u]));
+          for (int u = 0; u < RU; u++)
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+              const int idx = max(kb[u], min(kb[u] + kk + d, ke[u] - 1));      // an empty row reads a valid, ignored slot
+              xv[u][d] = __ldg(&X[(size_t)crow[idx] * P + c]);
             }
-          }
-          Y[(size_t)grow * P + c] = acc;
+          asm volatile("" ::: "memory");
+#pragma unroll
+          for (int u = 0; u < RU; u++)
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+              const int idx = max(kb[u], min(kb[u] + kk + d, ke[u] - 1));
+              const T nx = add_rn(acc[u], mul_rn(vrow[idx], xv[u][d]));
+              acc[u] = (kb[u] + kk + d < ke[u]) ? nx : acc[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+          const int grow = t * kTileRows + warp * 32 + (step + u) * RPW + rsub;
+          if (grow < A.n) Y[(size_t)grow * P + c] = acc[u];
         }
       }
     }
@@ -693,8 +715,8 @@ template <class T> static void k_rows_diag(Ctx& c, int n, int p, const T* d, con
   rows_diag_kernel<T><<<stream_grid((long long)n * p, 1, 8), kBlock, 0, c.stream>>>((long long)n * p, p, d, in, out, ldiv ? 1 : 0);
   KB_CUDA(cudaGetLastError()); c.launches++;
 }
-// tensor-core dispatch (Float64, p = 8 / 16 / 32; KB200_BLOCK_MMA=0 keeps the SIMT kernels for A/B runs,
-// KB200_BLOCK_MMA=8 also routes p = 8 through the tensor cores)
+// tensor-core dispatch (Float64, p = 8 / 16 / 32).  KB200_BLOCK_MMA=0 keeps the SIMT kernels (A/B runs, tests),
+// KB200_BLOCK_MMA=16 only p = 16 / 32 (p = 8 measured 0.72 of HBM on the tensor cores vs 0.65 on the SIMT kernel)
 template <class T, bool UPDATE, bool GRAM>
 static bool launch_mma(BlockWorkspace<T>&, T, const T*, const T*, T, T*, const T*, T*, int) { return false; }
 template <bool UPDATE, bool GRAM>
@@ -705,7 +727,7 @@ static bool launch_mma_f64(BlockWorkspace<double>& ws, double alpha, const doubl
   static const int mode = env ? atoi(env) : 1;
   if (mode == 0) return false;
   const int p = ws.p;
-  if (!(p == 16 || p == 32 || (p == 8 && mode == 8))) return false;
+  if (!(p == 16 || p == 32 || (p == 8 && mode != 16))) return false;
   const int ntiles = (rows + 7) / 8;
   const int per_sm = p <= 16 ? 3 : 2;
   const int grid = std::max(1, std::min(sm_count() * per_sm, (ntiles + kMmaWarps - 1) / kMmaWarps));
@@ -974,7 +996,10 @@ template <class T> BlockWorkspace<T>* block_ws_create(int m, int n, int p, int m
     ws->grid = panel_grid<T>(n, p);
     ws->fast_grid = std::max(1, std::min(sm_count() * 2, (int)(((long long)n + kBlock - 1) / kBlock)));
     ws->generic_kernels = getenv("KB200_BLOCK_GENERIC") != nullptr;     // tests: force the tiled any-p kernels
-    ws->part = dev_alloc<T>((size_t)std::max(ws->grid, ws->fast_grid) * pp);
+    // partial Gram matrices: one p x p block per CTA of whichever panel kernel runs (tiled, register-resident, or the
+    // tensor-core kernels with up to 3 CTAs of 8 warps per SM, one 8-row tile per warp)
+    const int mma_grid = std::max(1, std::min(sm_count() * 3, (int)((((long long)n + 7) / 8 + kMmaWarps - 1) / kMmaWarps)));
+    ws->part = dev_alloc<T>((size_t)std::max(std::max(ws->grid, ws->fast_grid), mma_grid) * pp);
     KB_CUDA(cudaMalloc(&ws->dG, sizeof(T) * pp));
     KB_CUDA(cudaMalloc(&ws->dS, sizeof(T) * pp));
     ensure_small(*ws, mem + 1);

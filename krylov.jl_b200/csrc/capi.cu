@@ -41,6 +41,9 @@ struct Handle {
   std::shared_ptr<CsrAny> csr;
   void* Mdiag = nullptr;
   void* Ndiag = nullptr;
+  void* Pblk[2] = {nullptr, nullptr};      // block-Jacobi M / N: dense diagonal blocks (device) ...
+  void* Pblk_inv[2] = {nullptr, nullptr};  // ... and their inverses (ldiv = true)
+  int Pbs[2] = {0, 0};
   KrylovB200Options ext;
   void *hx = nullptr, *hy = nullptr;   // pinned staging for host callbacks
 };
@@ -111,6 +114,7 @@ template <class T> void destroy_handle(Handle* h) {
   }
   h->csr.reset();
   dev_free(h->Mdiag); dev_free(h->Ndiag);
+  for (int w = 0; w < 2; w++) { dev_free(h->Pblk[w]); dev_free(h->Pblk_inv[w]); }
   if (h->hx) cudaFreeHost(h->hx);
   if (h->hy) cudaFreeHost(h->hy);
   ws_destroy<T>(ws);
@@ -195,6 +199,8 @@ int do_solve(Handle* h, KrylovMatvec fA, KrylovMatvec fM, KrylovMatvec fN, const
   LinOp<T> M = make_cb_op<T>(h, ws, fM, ud), N = make_cb_op<T>(h, ws, fN, ud);
   if (!fM && h->Mdiag) { M.kind = LinOp<T>::DIAG; M.diag = (const T*)h->Mdiag; }
   if (!fN && h->Ndiag) { N.kind = LinOp<T>::DIAG; N.diag = (const T*)h->Ndiag; }
+  if (!fM && !h->Mdiag && h->Pblk[0]) { M.kind = LinOp<T>::BDIAG; M.blocks = (const T*)h->Pblk[0]; M.blocks_inv = (const T*)h->Pblk_inv[0]; M.bs = h->Pbs[0]; M.n = ws->n; }
+  if (!fN && !h->Ndiag && h->Pblk[1]) { N.kind = LinOp<T>::BDIAG; N.blocks = (const T*)h->Pblk[1]; N.blocks_inv = (const T*)h->Pblk_inv[1]; N.bs = h->Pbs[1]; N.n = ws->n; }
   if (!b) throw std::runtime_error("b is NULL");
   const T* bd = stage_in<T>(h, ws, b, ws->bbuf);
   dist_check_alive(ws->ctx);             // row-partitioned: refuse to start on a dead communicator
@@ -585,6 +591,40 @@ int krylov_b200_set_preconditioner_diag(void* ws, int which, const void* d, int 
     KB_CUDA(cudaMemcpy(slot, d, esz * (size_t)n, location ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
     return 0;
   } catch (const std::exception& e) { return fail("krylov_b200_set_preconditioner_diag", e); }
+}
+
+// Block-Jacobi preconditioner (docs/src/preconditioners.md:33,159): dense bs x bs diagonal blocks,
+// row-major, ceil(n / bs) of them.  The inverses are formed once here so that ldiv = true is a product as well.
+int krylov_b200_set_preconditioner_blockdiag(void* ws, int which, int bs, const void* blocks, int location) {
+  try {
+    Handle* h = lookup(ws);
+    if (!h) return fail("krylov_b200_set_preconditioner_blockdiag", "unknown (single right-hand side) workspace handle");
+    if (which != 0 && which != 1) return fail("krylov_b200_set_preconditioner_blockdiag", "which must be 0 (M) or 1 (N)");
+    dev_free(h->Pblk[which]); dev_free(h->Pblk_inv[which]);
+    h->Pblk[which] = h->Pblk_inv[which] = nullptr; h->Pbs[which] = 0;
+    if (!blocks) return 0;
+    if (bs < 2 || bs > 8) return fail("krylov_b200_set_preconditioner_blockdiag", "block size must be in 2..8");
+    const size_t esz = h->dtype == KRYLOV_FLOAT64 ? 8 : 4;
+    const int n = n_of(h);
+    const size_t cnt = (size_t)((n + bs - 1) / bs) * bs * bs;
+    Ctx& c = ctx_of(h);
+    KB_CUDA(cudaSetDevice(c.device));
+    h->Pblk[which] = dev_alloc<char>(esz * cnt);
+    h->Pblk_inv[which] = dev_alloc<char>(esz * cnt);
+    h->Pbs[which] = bs;
+    KB_CUDA(cudaMemcpyAsync(h->Pblk[which], blocks, esz * cnt, location ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
+    int* dsing = nullptr;
+    KB_CUDA(cudaMalloc((void**)&dsing, sizeof(int)));
+    KB_CUDA(cudaMemsetAsync(dsing, 0, sizeof(int), c.stream));
+    if (h->dtype == KRYLOV_FLOAT64) k_blockdiag_invert<double>(c, n, bs, (const double*)h->Pblk[which], (double*)h->Pblk_inv[which], dsing);
+    else k_blockdiag_invert<float>(c, n, bs, (const float*)h->Pblk[which], (float*)h->Pblk_inv[which], dsing);
+    int sing = 0;
+    KB_CUDA(cudaMemcpyAsync(&sing, dsing, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    c.sync();
+    cudaFree(dsing);
+    if (sing) fprintf(stderr, "[krylov_b200] warning: a diagonal block of the block-Jacobi preconditioner is singular (its inverse, used by ldiv = true, is zero)\n");
+    return 0;
+  } catch (const std::exception& e) { return fail("krylov_b200_set_preconditioner_blockdiag", e); }
 }
 
 KrylovB200Options krylov_b200_default_options(void) {

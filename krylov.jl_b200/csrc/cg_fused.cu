@@ -92,7 +92,8 @@ __device__ __forceinline__ bool cg_global_sum(CgState<T>* st, DistComm* dc, T& v
 // MODE is a compile-time variant so that the plain path carries no dead branches inside the 8-deep gather batch
 // (a run-time `if (mdiag)` between the loads cost 11 % of K1: profiles/r1_ab.txt):
 //   0 = single GPU, M = I      1 = row-partitioned (halo columns)      2 = single GPU, Diagonal M (Jacobi)
-constexpr int kPlain = 0, kDist = 1, kJacobi = 2;
+//   3 = single GPU, block-diagonal M (block-Jacobi; z = M r is materialised block by block in phase B)
+constexpr int kPlain = 0, kDist = 1, kJacobi = 2, kBlockJac = 3;   // kBlockJac: persistent kernel only
 
 template <class T, int MODE>
 struct PVal {               // p_j = z_j + beta p_j, for local and (kDist) halo columns
@@ -335,6 +336,9 @@ template <class T>
 struct CgPersistArgs {
   T* r; T* P0; T* P1; T* Ap; T* x;     // P0 / P1: direction buffers; iteration k reads P[k & 1], writes the other
   const T* mdiag;            // kJacobi
+  T* z;                      // kBlockJac: z = M r, written in phase B, gathered in phase A in place of r
+  const T* mblocks;          //            dense bs x bs diagonal blocks of M, row-major
+  int mbs;
   HaloMap halo;              // kDist ...
   const CgPeerTab<T>* tab;
   const int* tile_order;     // interior tiles first, tiles with halo columns last (bit 31 set)
@@ -349,35 +353,55 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+// Phase B with a block-Jacobi M (cg.jl:240-242): one thread per diagonal block updates r, forms z = M_blk r on the
+// spot (the block's rows are all in this thread's registers) and accumulates <r, z>.  BS = 0: run-time block size.
+template <class T, int BS>
+__device__ __forceinline__ T cg_phase_b_block(int n, int bs_rt, T nalpha, T* r, const T* Ap, T* z, const T* __restrict__ B, int first, int stride) {
+  const int bs = BS ? BS : bs_rt;
+  const int nb = (n + bs - 1) / bs;
+  T acc = T(0);
+  for (int blk = first; blk < nb; blk += stride) {
+    const int r0 = blk * bs, rows = min(bs, n - r0);
+    T rn[BS ? BS : 8];
+#pragma unroll
+    for (int i = 0; i < (BS ? BS : 8); i++)
+      if (i < rows) { rn[i] = add_rn(r[r0 + i], mul_rn(nalpha, Ap[r0 + i])); r[r0 + i] = rn[i]; }
+    const T* Bk = B + (size_t)blk * bs * bs;
+#pragma unroll
+    for (int i = 0; i < (BS ? BS : 8); i++) {
+      if (i < rows) {
+        T zi = T(0);
+#pragma unroll
+        for (int j = 0; j < (BS ? BS : 8); j++)
+          if (j < rows) zi = add_rn(zi, mul_rn(__ldg(&Bk[i * bs + j]), rn[j]));
+        z[r0 + i] = zi;
+        acc += rn[i] * zi;
+      }
+    }
+  }
+  return acc;
+}
+
 // Halo staging of the row-partitioned persistent kernel (one warp per CTA): this CTA's share of the halo list, all
 // loads in flight at once.  The halo entries of r and of the old direction land in the TAILS of the local vectors
 // (r and the p buffers of a row-partitioned workspace hold nloc + nhalo entries), so the gather of phase A is
-// exactly the single-GPU code: column j >= nloc is simply element j of the same array.  One entry per lane and
-// trip (U = 1; the compiler unrolls the loop itself): with 8 explicit entries in flight per lane ptxas scheduled the
-// CONSUMER warps' gather batches of the same kernel as load -> use chains (checked in SASS; the staging has a whole
-// phase A to finish, its latency is hidden behind the interior tiles anyway).
+// exactly the single-GPU code: column j >= nloc is simply element j of the same array.  The CONSUMER threads do
+// it, one entry per thread and trip, before their first tile: the share of a CTA is usually <= 256 entries, i.e.
+// one NVLink round trip for the whole CTA, while the producer warp keeps the tile ring full.  (First version: the
+// producer warp staged, 7 dependent round trips per lane during which it issued no tiles -- the consumers starved
+// for ~15 us per iteration at 2 GPUs.  An explicit 8-deep unroll made ptxas schedule the gather batches of the same
+// kernel as load -> use chains, so the loop is left to the compiler.)
 template <class T>
-__device__ __forceinline__ void cg_stage_halo(HaloMap halo, const CgPeerTab<T>* tab, T* r, T* p_old, int pb, int G, int lane) {
+__device__ __forceinline__ void cg_stage_halo(HaloMap halo, const CgPeerTab<T>* tab, T* r, T* p_old, int pb, int G, int tid, int nthreads) {
   const int nh = halo.nhalo, nloc = halo.nloc;
   const int per = (nh + G - 1) / G;
   const int h0 = (int)blockIdx.x * per, h1 = min(nh, h0 + per);
-  constexpr int U = 1;
-  for (int hb = h0 + lane; hb < h1; hb += 32 * U) {
-    T rv[U], pv[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const int h = hb + 32 * u;
-      if (h < h1) {
-        const int rk = __ldg(&halo.src_rank[h]), off = __ldg(&halo.src_off[h]);
-        rv[u] = ld_sys(tab->r[rk] + off);
-        pv[u] = ld_sys(tab->p[pb][rk] + off);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const int h = hb + 32 * u;
-      if (h < h1) { __stcg(&r[nloc + h], rv[u]); __stcg(&p_old[nloc + h], pv[u]); }
-    }
+  for (int h = h0 + tid; h < h1; h += nthreads) {
+    const int rk = __ldg(&halo.src_rank[h]), off = __ldg(&halo.src_off[h]);
+    const T rv = ld_sys(tab->r[rk] + off);
+    const T pv = ld_sys(tab->p[pb][rk] + off);
+    __stcg(&r[nloc + h], rv);
+    __stcg(&p_old[nloc + h], pv);
   }
 }
 
@@ -416,18 +440,12 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPer
     if (timing) t0 = globaltimer_ns();
     // ------------------------------ phase A (= K1) ------------------------------
     if (warp == kConsumerWarps) {
-      if (MODE == kDist) {
-        cg_stage_halo<T>(a.halo, a.tab, a.r, p_old, iter & 1, G, lane);
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(&gb->halo_ready, 1u);
-      }
       if (lane == 0) {
         const unsigned target = (unsigned)(k + 1) * (unsigned)cnt + (k + 1 < a.max_iters ? pre : 0u);
         tile_issue_until<T>(A, P, ppos, target, cnt, tile_at, pol);
       }
     } else {
-      const T* r = a.r;
+      const T* r = MODE == kBlockJac ? a.z : a.r;      // block-Jacobi: gather z = M r (materialised by phase B)
       const T* mdiag = a.mdiag;
       auto gather = [&](int j) -> T {          // p_j = z_j + beta p_j (cg.jl:259 applied on the fly); row-partitioned:
         T z = r[j];                            // j >= nloc reads the staged tail of the same arrays
@@ -450,11 +468,15 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPer
         dacc += q.pn * acc;
       };
       if (MODE == kDist) {
+        cg_stage_halo<T>(a.halo, a.tab, a.r, p_old, iter & 1, G, tid, kTileRows);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(&gb->halo_ready, 1u);       // 8 consumer warps per CTA report
         // interior tiles first; the tiles with halo columns (last in this CTA's sequence) only after every CTA's
         // producer warp has staged its share of the halo
         tile_consume_pass<T, DEPTH>(A, P, cpos, 0, cnt_int, tile_at, gather, row_begin, row_done);
         if (cnt_int < cnt) {
-          if (lane == 0) { while (ld_acquire_gpu_u32(&gb->halo_ready) < (unsigned)G) { } }
+          if (lane == 0) { while (ld_acquire_gpu_u32(&gb->halo_ready) < (unsigned)(G * kConsumerWarps)) { } }
           __syncwarp();
           tile_consume_pass<T, DEPTH>(A, P, cpos, cnt_int, cnt, tile_at, gather, row_begin, row_done);
         }
@@ -481,6 +503,13 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPer
       T acc = T(0);
       const int stride = G * kTileThreads;
       int i = (int)blockIdx.x * kTileThreads + tid;
+      if (MODE == kBlockJac) {
+        if (a.mbs == 4) acc = cg_phase_b_block<T, 4>(n, 4, nalpha, r, Ap, a.z, a.mblocks, i, stride);
+        else if (a.mbs == 2) acc = cg_phase_b_block<T, 2>(n, 2, nalpha, r, Ap, a.z, a.mblocks, i, stride);
+        else if (a.mbs == 8) acc = cg_phase_b_block<T, 8>(n, 8, nalpha, r, Ap, a.z, a.mblocks, i, stride);
+        else acc = cg_phase_b_block<T, 0>(n, a.mbs, nalpha, r, Ap, a.z, a.mblocks, i, stride);
+        i = n;                                  // the element loops below are skipped
+      }
       for (; i + 3 * stride < n; i += 4 * stride) {
         T rv[4], av[4];
 #pragma unroll
@@ -599,6 +628,12 @@ template <class T> void cg_dist_tile_order(Workspace<T>& ws, const Csr<T>& A) {
 template <class T> bool cg_fused_eligible(const LinOp<T>& A, const LinOp<T>& M, const SolveOpts& o) {
   // M = I, or a Diagonal M applied with mul! (the Jacobi case of SURVEY.md 8f-1), folded into the two kernels
   const bool m_ok = M.is_identity() || (M.kind == LinOp<T>::DIAG && !o.ldiv);
+  if (o.fused && A.kind == LinOp<T>::CSR && M.kind == LinOp<T>::BDIAG && !o.ldiv && o.radius == 0) {
+    // block-Jacobi M: only the persistent kernel carries it (phase B forms z = M r block by block)
+    const char* epers = getenv("KB200_PERSIST");
+    const bool single_step = (o.callback != nullptr) || (o.timemax < 1e300) || o.verbose > 0;
+    return A.csr->tma_ok && o.persist != 0 && !single_step && !(epers && atoi(epers) == 0);
+  }
   return o.fused && A.kind == LinOp<T>::CSR && m_ok && o.radius == 0;
 }
 
@@ -706,6 +741,8 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   // need not be current after every iteration.  KB200_PERSIST=0 keeps the two-launch kernels (A/B measurements).
   const char* epers = getenv("KB200_PERSIST");
   const bool persist = A.tma_ok && xup && !(epers && atoi(epers) == 0) && o.persist != 0;
+  const bool bjac = ws.mblocks_fused != nullptr;
+  if (bjac && !persist) throw std::runtime_error("block-Jacobi M reached the fused CG loop without the persistent kernel");
   typedef void (*KpFn)(Csr<T>, CgPersistArgs<T>, CgState<T>*, T*, GridBar*, DistComm*);
   KpFn kp = nullptr;
   int pgrid = 0;
@@ -718,10 +755,13 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
     static const char* edep = getenv("KB200_GATHER_DEPTH");
     const int depth = edep ? atoi(edep) : 0;
     if (A.ctas_per_sm >= 3) {
-      if (depth == 8) kp = dist ? cg_persist<T, kDist, 3, 8> : (jac ? cg_persist<T, kJacobi, 3, 8> : cg_persist<T, kPlain, 3, 8>);
-      else kp = dist ? cg_persist<T, kDist, 3, 4> : (jac ? cg_persist<T, kJacobi, 3, 4> : cg_persist<T, kPlain, 3, 4>);
+      // measured on cfg2 (profiles/README.md, round 2): 8-deep batches 3825 it/s, 4-deep 3691 it/s
+      if (bjac) kp = cg_persist<T, kBlockJac, 2, 8>;   // the block code of phase B needs the 96-register budget (2 CTAs per SM)
+      else if (depth == 4) kp = dist ? cg_persist<T, kDist, 3, 4> : (jac ? cg_persist<T, kJacobi, 3, 4> : cg_persist<T, kPlain, 3, 4>);
+      else kp = dist ? cg_persist<T, kDist, 3, 8> : (jac ? cg_persist<T, kJacobi, 3, 8> : cg_persist<T, kPlain, 3, 8>);
     } else {
-      if (depth == 4) kp = dist ? cg_persist<T, kDist, 2, 4> : (jac ? cg_persist<T, kJacobi, 2, 4> : cg_persist<T, kPlain, 2, 4>);
+      if (bjac) kp = cg_persist<T, kBlockJac, 2, 8>;
+      else if (depth == 4) kp = dist ? cg_persist<T, kDist, 2, 4> : (jac ? cg_persist<T, kJacobi, 2, 4> : cg_persist<T, kPlain, 2, 4>);
       else kp = dist ? cg_persist<T, kDist, 2, 8> : (jac ? cg_persist<T, kJacobi, 2, 8> : cg_persist<T, kPlain, 2, 8>);
     }
     ensure_dyn_smem((const void*)kp, 220 * 1024);
@@ -731,6 +771,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
     pgrid = std::min(std::min(occ, A.ctas_per_sm) * sm_count(), std::max(1, A.ntiles));
     pa.r = ws.r; pa.P0 = ws.p; pa.P1 = ws.p2; pa.Ap = ws.Ap; pa.x = ws.x;
     pa.mdiag = md;
+    pa.z = ws.z; pa.mblocks = ws.mblocks_fused; pa.mbs = ws.mbs_fused;
     pa.max_iters = batch;
     pa.timed = o.time_kernels ? 1 : 0;
     if (dist) {

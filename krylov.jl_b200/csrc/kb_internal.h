@@ -63,6 +63,8 @@ template <class T> void k_scalcopy(Ctx& c, int n, T* y, T s, const T* x);       
 template <class T> void k_divcopy(Ctx& c, int n, T* y, const T* x, T s);              // y = x / s
 template <class T> void k_fill(Ctx& c, int n, T* x, T v);
 template <class T> void k_diagmul(Ctx& c, int n, T* y, const T* d, const T* x, bool ldiv);  // y = d.*x or x./d
+template <class T> void k_blockdiag_mul(Ctx& c, int n, int bs, const T* blocks, const T* x, T* y);   // y = blockdiag(B_k) x
+template <class T> void k_blockdiag_invert(Ctx& c, int n, int bs, const T* blocks, T* inv, int* singular);  // per-block inverse
 // row-partitioned solves (no-ops on a single GPU)
 double k_dist_sum(Ctx& c, double v);                                   // sum of a host scalar over all ranks
 void dist_agree_on_exit(Ctx& c, bool& user_exit, bool& overtimed);     // OR the exit flags over the ranks
@@ -109,9 +111,12 @@ typedef void (*MatvecFn)(const void* x, void* y, void* userdata);
 
 template <class T>
 struct LinOp {
-  enum Kind { NONE, CSR, DIAG, HOST_CB, DEV_CB } kind = NONE;
+  enum Kind { NONE, CSR, DIAG, BDIAG, HOST_CB, DEV_CB } kind = NONE;
   const Csr<T>* csr = nullptr;
   const T* diag = nullptr;       // DIAG: y = diag .* x (or x ./ diag with ldiv)
+  const T* blocks = nullptr;     // BDIAG: dense bs x bs diagonal blocks, row-major, ceil(n / bs) of them (block-Jacobi)
+  const T* blocks_inv = nullptr; //        their inverses (ldiv = true applies these)
+  int bs = 0;
   MatvecFn fn = nullptr;         // callbacks: host pointers (HOST_CB) or device pointers (DEV_CB)
   void* userdata = nullptr;
   T* hx = nullptr;               // pinned staging for HOST_CB
@@ -188,6 +193,8 @@ struct Workspace {
   int memory = 20, window = 5;
   int inner_iter = 0;
   const T* mdiag_fused = nullptr;      // diagonal of M for the fused CG kernels (set per solve; nullptr: M = I)
+  const T* mblocks_fused = nullptr;    // block-Jacobi M for the persistent CG kernel (set per solve; nullptr: none)
+  int mbs_fused = 0;
   double k1_ms = 0, k2_ms = 0;         // average event-timed duration of the fused kernels (time_kernels)
   int timed_pairs = 0;
   void* fused_state = nullptr;         // device scalar block of the fused paths

@@ -169,7 +169,9 @@ void cg_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
   // row-partitioned: the fused kernels cover M = I; everything else runs the primitive path, whose SpMV is
   // preceded by the general halo exchange and whose dots end in the in-kernel all-reduce
   if (cg_fused_eligible(A, M, o) && !(dist && !MisI) && !(solved || tired)) {
-    ws.mdiag_fused = MisI ? nullptr : M.diag;      // Diagonal M is applied inside K1/K2 (z is not materialised)
+    ws.mdiag_fused = (MisI || M.kind != LinOp<T>::DIAG) ? nullptr : M.diag;   // Diagonal M: applied inside K1/K2 (z is not materialised)
+    ws.mblocks_fused = M.kind == LinOp<T>::BDIAG ? M.blocks : nullptr;        // block-Jacobi M: z = M r materialised in phase B
+    ws.mbs_fused = M.kind == LinOp<T>::BDIAG ? M.bs : 0;
     cg_fused_loop<T>(ws, *A.csr, o, gamma, eps_tol, itmax, start_time, solved, tired, zero_curvature, inconsistent,
                      user_exit, overtimed, iter);
   } else {

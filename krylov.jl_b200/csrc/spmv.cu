@@ -305,6 +305,7 @@ template <class T> void op_apply(Ctx& c, const LinOp<T>& op, const T* x, T* y, b
       k_spmv<T>(c, *op.csr, x, y, 0);
       break;
     case LinOp<T>::DIAG: k_diagmul<T>(c, op.n, y, op.diag, x, ldiv); break;
+    case LinOp<T>::BDIAG: k_blockdiag_mul<T>(c, op.n, op.bs, ldiv ? op.blocks_inv : op.blocks, x, y); break;
     case LinOp<T>::DEV_CB:
       c.sync();                       // the callback may use its own stream
       op.fn(x, y, op.userdata);

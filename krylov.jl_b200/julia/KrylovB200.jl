@@ -4,7 +4,9 @@
 #
 # STATUS: Julia is not installed in the build image, so this file has never been executed here.
 # It is the reference-side binding a maintainer would add (see INTEGRATION.md); everything it
-# calls is exercised through the same C ABI by tests/ via ctypes.
+# calls is exercised through the same C ABI by tests/ via ctypes, and tests/test_julia_binding.py
+# parses every `ccall` below and checks symbol, argument count and argument/return types against
+# include/krylov_b200.h, and the three mirrored structs (COpts, CExt, CStats) field by field.
 #
 # Two levels, as in the reference:
 #   (1) primitive level  -- Krylov.kdot / knorm / kaxpy! / ... / kmul! overloads for B200Vector /
@@ -93,72 +95,194 @@ mutable struct B200CSR{T<:BlasT}
   handle::Ptr{Cvoid}
   m::Int
   n::Int
+  function B200CSR{T}(h::Ptr{Cvoid}, m::Integer, n::Integer) where T
+    h == C_NULL && error(unsafe_string(ccall((:krylov_b200_last_error, lib), Cstring, ())))
+    op = new{T}(h, m, n)
+    finalizer(o -> (o.handle != C_NULL && ccall((:kb200_csr_destroy, lib), Cvoid, (Ptr{Cvoid},), o.handle); o.handle = C_NULL), op)
+    op
+  end
 end
 # SparseMatrixCSC{T,Int64} is CSC, 1-based, Int64.  CSR(A) == CSC(A'): for the (symmetric) CG/MINRES
 # operators the arrays can be passed as they are; for a general A pass the CSC arrays of copy(A').
 function B200CSR(A::SparseMatrixCSC{T,Int64}; symmetric::Bool = issymmetric(A)) where T<:BlasT
   At = symmetric ? A : SparseMatrixCSC(transpose(A))
   h = ccall((:kb200_csr_create, lib), Ptr{Cvoid},
-            (Ptr{Cvoid}, Cint, Cint, Clonglong, Ptr{Int64}, Ptr{Int64}, Ptr{T}, Cint, Cint, Cint),
+            (Ptr{Cvoid}, Cint, Cint, Clonglong, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint),
             ctx(), dtype_id(T), size(A, 1), nnz(A), At.colptr, At.rowval, At.nzval, 1, 8, 0)
-  h == C_NULL && error(unsafe_string(ccall((:krylov_b200_last_error, lib), Cstring, ())))
-  op = B200CSR{T}(h, size(A)...)
-  finalizer(o -> ccall((:kb200_csr_destroy, lib), Cvoid, (Ptr{Cvoid},), o.handle), op)
+  B200CSR{T}(h, size(A)...)
 end
+# Matrix Market ingestion on the library side (benchmark/benchmarks.jl:23-33 reads SuiteSparse .mtx files)
+function B200CSR(path::AbstractString, ::Type{T} = Float64) where T<:BlasT
+  h = ccall((:kb200_csr_read_mtx, lib), Ptr{Cvoid}, (Ptr{Cvoid}, Cstring, Cint), ctx(), path, dtype_id(T))
+  h == C_NULL && error(unsafe_string(ccall((:krylov_b200_last_error, lib), Cstring, ())))
+  n = Ref{Cint}(0); nz = Ref{Clonglong}(0)
+  check(ccall((:kb200_csr_info, lib), Cint, (Ptr{Cvoid}, Ref{Cint}, Ref{Clonglong}), h, n, nz))
+  B200CSR{T}(h, n[], n[])
+end
+# A' : a new device-resident operator holding the transpose (= adjoint for the real types of this path);
+# opens the LSQR / LSMR / BiLQ / QMR family through the primitive overloads (docs/src/matrix_free.md:36-44)
+function Base.adjoint(A::B200CSR{T}) where T
+  h = ccall((:kb200_csr_transpose, lib), Ptr{Cvoid}, (Ptr{Cvoid}, Ptr{Cvoid}), ctx(), A.handle)
+  B200CSR{T}(h, A.n, A.m)
+end
+Base.transpose(A::B200CSR) = adjoint(A)
 Base.size(A::B200CSR) = (A.m, A.n)
+Base.size(A::B200CSR, i::Integer) = i == 1 ? A.m : (i == 2 ? A.n : 1)
 Base.eltype(::B200CSR{T}) where T = T
 kmul!(y::B200Vector{T}, A::B200CSR{T}, x::B200Vector{T}) where T =       # custom_workspaces.md:114-115
   (check(ccall((:kb200_spmv_csr, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint), ctx(), A.handle, x.ptr, y.ptr, 0)); y)
 LinearAlgebra.mul!(y::B200Vector, A::B200CSR, x::B200Vector) = kmul!(y, A, x)
 
+# ---- diagonal preconditioner resident in HBM (docs/src/preconditioners.md:33,159) ---------------------
+# M = B200Diagonal(d): mul!(y, M, x) is y = d .* x;  with ldiv = true the solver applies x ./ d.
+struct B200Diagonal{T<:BlasT}
+  d::B200Vector{T}
+end
+Base.size(D::B200Diagonal) = (D.d.n, D.d.n)
+Base.eltype(::B200Diagonal{T}) where T = T
+
 # ---- solver level: one C call per solve (fused kernels) ------------------------------------------------
-# The workspace keeps Krylov.jl's type (CgWorkspace{T,T,B200Vector{T}}) for its stats and public fields;
-# the device vectors of the fused solve live in a libkrylov_b200 workspace (KRYLOV_CUDA: device pointers).
+# The workspace keeps Krylov.jl's type (CgWorkspace{T,T,B200Vector{T}}) for its stats and public fields; the
+# device vectors of the fused solve live in a libkrylov_b200 workspace (KRYLOV_CUDA: device pointers) that is
+# created ONCE per Krylov.jl workspace and kept in HANDLES, so an in-place solve allocates nothing
+# (test/test_allocations.jl:54-57).
 const SOLVER_ID = Dict(:cg => 0, :cr => 1, :minres => 3, :diom => 5, :dqgmres => 6, :fom => 7, :gmres => 8, :fgmres => 9,
                        :bicgstab => 10, :cgs => 11, :cg_lanczos => 100)
 struct COpts   # KrylovOptions, interfaces/src/c_enums.jl:40-62
   atol::Cdouble; rtol::Cdouble; itmax::Cint; verbose::Cint; lambda::Cdouble; tau::Cdouble; nu::Cdouble
   timemax::Cdouble; radius::Cdouble; restart::Cint; reorthogonalization::Cint; linesearch::Cint
 end
-function fused_solve!(method::Symbol, ws, A::B200CSR{T}, b::B200Vector{T}; atol::T = √eps(T), rtol::T = √eps(T),
-                      itmax::Int = 0, timemax::Float64 = Inf, verbose::Int = 0, radius::T = zero(T),
-                      linesearch::Bool = false, λ::T = zero(T), restart::Bool = false,
-                      reorthogonalization::Bool = false, memory::Int = 0, window::Int = 0) where T
-  h = Ref{Ptr{Cvoid}}(C_NULL)
-  wo = (Cint(memory), Cint(window))
-  rc = ccall((:krylov_workspace_create, lib), Cint, (Cint, Cint, Cint, Cint, Cint, Ref{NTuple{2,Cint}}, Ref{Ptr{Cvoid}}),
-             SOLVER_ID[method], A.m, A.n, dtype_id(T), 1, wo, h)
-  rc == 0 || error("krylov_workspace_create -> $rc")
-  try
-    # attach the operator already resident in HBM; solve; copy x (device to device) into ws.x
-    check(ccall((:krylov_b200_attach_csr, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h[], A.handle))
-    o = COpts(atol, rtol, itmax, verbose, λ, NaN, NaN, isinf(timemax) ? NaN : timemax, radius, restart, reorthogonalization, linesearch)
-    check(ccall((:krylov_solve, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{COpts}),
-               h[], C_NULL, C_NULL, C_NULL, C_NULL, b.ptr, C_NULL, C_NULL, o))
-    check(ccall((:krylov_get_x, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), h[], ws.x.ptr, A.n))
-    ws.stats.niter = ccall((:krylov_niter, lib), Cint, (Ptr{Cvoid},), h[])
-    ws.stats.solved = ccall((:krylov_is_solved, lib), Cint, (Ptr{Cvoid},), h[]) == 1
-    ws.stats.timer = ccall((:krylov_elapsed_time, lib), Cdouble, (Ptr{Cvoid},), h[])
-  finally
-    ccall((:krylov_workspace_free, lib), Cint, (Ptr{Cvoid},), h[])
+struct CExt    # KrylovB200Options (include/krylov_b200.h)
+  history::Cint; ldiv::Cint; etol::Cdouble; conlim::Cdouble; fused::Cint; batch::Cint
+  callback::Ptr{Cvoid}; callback_user::Ptr{Cvoid}; time_kernels::Cint; check_curvature::Cint; cr_gamma::Cdouble
+end
+struct CStats  # KrylovB200Stats (include/krylov_b200.h)
+  niter::Cint; solved::Cint; inconsistent::Cint; indefinite::Cint; npcCount::Cint
+  nresiduals::Cint; nAresiduals::Cint; nAcond::Cint
+  allocation_timer::Cdouble; timer::Cdouble; status::NTuple{96,UInt8}; Anorm::Cdouble
+end
+
+mutable struct Handle
+  ptr::Ptr{Cvoid}
+  op::Ptr{Cvoid}          # CSR object currently attached
+end
+const HANDLES = IdDict{Any,Handle}()
+function handle_for(method::Symbol, ws, A::B200CSR{T}, memory::Int, window::Int) where T
+  h = get(HANDLES, ws, nothing)
+  if h === nothing
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    wo = Ref((Cint(memory), Cint(window)))            # KrylovWorkspaceOptions {memory, window}
+    rc = ccall((:krylov_workspace_create, lib), Cint, (Cint, Cint, Cint, Cint, Cint, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
+               SOLVER_ID[method], A.m, A.n, dtype_id(T), 1, wo, out)
+    rc == 0 || error("krylov_workspace_create -> $rc: " * unsafe_string(ccall((:krylov_b200_last_error, lib), Cstring, ())))
+    h = Handle(out[], C_NULL)
+    finalizer(x -> (x.ptr != C_NULL && ccall((:krylov_workspace_free, lib), Cint, (Ptr{Cvoid},), x.ptr); x.ptr = C_NULL), h)
+    HANDLES[ws] = h
   end
+  if h.op != A.handle      # operator resident in HBM: attach, no copy
+    check(ccall((:krylov_b200_attach_csr, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h.ptr, A.handle))
+    h.op = A.handle
+  end
+  h
+end
+
+# callback trampoline: int (*)(void *ws, void *user); `user` carries the Julia closure and the Krylov.jl workspace
+function _cb_tramp(_c_ws::Ptr{Cvoid}, user::Ptr{Cvoid})::Cint
+  f, ws = unsafe_pointer_to_objref(user)::Tuple{Any,Any}
+  r = f(ws)
+  r isa Bool || throw(TypeError(:callback, "", Bool, r))   # cg.jl:264, test_cg.jl:130
+  Cint(r)
+end
+
+set_precond!(h::Handle, which::Int, ::UniformScaling) =
+  check(ccall((:krylov_b200_set_preconditioner_diag, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint), h.ptr, which, C_NULL, 0))
+set_precond!(h::Handle, which::Int, D::B200Diagonal) =
+  check(ccall((:krylov_b200_set_preconditioner_diag, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint), h.ptr, which, D.d.ptr, 1))
+set_precond!(::Handle, ::Int, P) = error("libkrylov_b200: preconditioners must be I or a B200Diagonal (got $(typeof(P))); " *
+                                         "any other operator runs through the primitive overloads (generic Krylov.jl method)")
+
+function fill_stats!(ws, h::Handle, ::Type{T}) where T
+  cs = Ref{CStats}()
+  check(ccall((:krylov_b200_get_stats, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h.ptr, cs))
+  s = cs[]
+  st = ws.stats
+  st.niter = s.niter; st.solved = s.solved != 0; st.inconsistent = s.inconsistent != 0
+  st.timer = s.timer
+  hasproperty(st, :allocation_timer) && (st.allocation_timer = s.allocation_timer)
+  hasproperty(st, :indefinite) && (st.indefinite = s.indefinite != 0)
+  hasproperty(st, :npcCount) && (st.npcCount = s.npcCount)
+  hasproperty(st, :Anorm) && (st.Anorm = T(s.Anorm))            # LanczosStats (cg_lanczos!)
+  bytes = collect(s.status); z = findfirst(==(0x00), bytes)
+  st.status = String(bytes[1:(z === nothing ? length(bytes) : z - 1)])
+  for (which, field, cnt) in ((0, :residuals, s.nresiduals), (1, :Aresiduals, s.nAresiduals), (2, :Acond, s.nAcond))
+    hasproperty(st, field) || continue
+    buf = Vector{Cdouble}(undef, cnt)
+    got = cnt == 0 ? 0 : ccall((:krylov_b200_get_history, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint), h.ptr, which, buf, cnt)
+    v = getproperty(st, field); empty!(v); append!(v, T.(buf[1:got]))
+  end
+  st
+end
+
+# kwargs: the union of cg.jl:100-111, minres.jl:138-151, gmres.jl:96-108, bicgstab.jl:105-116 (a solver ignores the
+# ones it does not have, exactly like the C layer's option families, interfaces/src/c_stores.jl:287-398)
+function fused_solve!(method::Symbol, ws, A::B200CSR{T}, b::B200Vector{T}; c::Union{Nothing,B200Vector{T}} = nothing,
+                      M = I, N = I, ldiv::Bool = false, atol::T = √eps(T), rtol::T = √eps(T), etol::T = √eps(T),
+                      conlim::T = 1 / √eps(T), itmax::Int = 0, timemax::Float64 = Inf, verbose::Int = 0,
+                      history::Bool = false, callback = workspace -> false, iostream::IO = stdout,
+                      radius::T = zero(T), linesearch::Bool = false, λ::T = zero(T), γ::T = √eps(T),
+                      check_curvature::Bool = false, restart::Bool = false, reorthogonalization::Bool = false,
+                      memory::Int = 0, window::Int = 0) where T
+  A.m == A.n || error("System must be square")
+  length(b) == A.m || error("Inconsistent problem size")
+  h = handle_for(method, ws, A, memory, window)
+  set_precond!(h, 0, M)
+  set_precond!(h, 1, N)
+  user = Ref{Any}((callback, ws))
+  cb = @cfunction(_cb_tramp, Cint, (Ptr{Cvoid}, Ptr{Cvoid}))
+  ext = Ref(CExt(history, ldiv, etol, conlim, 1, 0, cb, Base.unsafe_convert(Ptr{Cvoid}, user), 0, check_curvature, γ))
+  o = Ref(COpts(atol, rtol, itmax, verbose, λ, NaN, NaN, isinf(timemax) ? NaN : timemax, radius, restart, reorthogonalization, linesearch))
+  GC.@preserve user ext o begin
+    check(ccall((:krylov_b200_set_options, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h.ptr, ext))
+    if ws.warm_start                      # warm_start!(ws, x0) stored x0 in ws.Δx (workspace_accessors.jl:193-200)
+      check(ccall((:krylov_warm_start, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), h.ptr, ws.Δx.ptr, A.n))
+      ws.warm_start = false
+    end
+    rc = ccall((:krylov_solve, lib), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+               h.ptr, C_NULL, C_NULL, C_NULL, C_NULL, b.ptr, c === nothing ? C_NULL : c.ptr, C_NULL, o)
+    rc == 0 || error(unsafe_string(ccall((:krylov_b200_last_error, lib), Cstring, ())))
+    # solution(ws) is ws.x itself (workspace_accessors.jl:149): device-to-device copy into the Krylov.jl vector
+    check(ccall((:krylov_get_x, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), h.ptr, ws.x.ptr, A.n))
+  end
+  fill_stats!(ws, h, T)
   ws
 end
-# NOTE for the maintainer: a production binding keeps the C handle inside the workspace (created once in the
-# CgWorkspace(kc) constructor) and attaches A with krylov_b200_share_operator, so in-place solves allocate
-# nothing (test/test_allocations.jl:54-57); the sketch above creates it per call for brevity.
-Krylov.cg!(ws::CgWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:cg, ws, A, b; kw...)
-Krylov.minres!(ws::MinresWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:minres, ws, A, b; kw...)
-Krylov.gmres!(ws::GmresWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:gmres, ws, A, b; memory = length(ws.c), kw...)
-Krylov.bicgstab!(ws::BicgstabWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:bicgstab, ws, A, b; kw...)
-# sibling solvers served by the same library (SURVEY.md 8f-3); every other method keeps running through the k*
-# overloads above, one kernel per call
-Krylov.cr!(ws::CrWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:cr, ws, A, b; kw...)
-Krylov.cgs!(ws::CgsWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:cgs, ws, A, b; kw...)
-Krylov.cg_lanczos!(ws::CgLanczosWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:cg_lanczos, ws, A, b; kw...)
-Krylov.fom!(ws::FomWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:fom, ws, A, b; memory = length(ws.l), kw...)
-Krylov.fgmres!(ws::FgmresWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:fgmres, ws, A, b; memory = length(ws.c), kw...)
-Krylov.dqgmres!(ws::DqgmresWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:dqgmres, ws, A, b; memory = length(ws.V), kw...)
-Krylov.diom!(ws::DiomWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T = fused_solve!(:diom, ws, A, b; memory = length(ws.V), kw...)
+
+# x0 as optional positional argument = warm_start! + solve (cg.jl:98, def_optargs_cg)
+function fused_solve!(method::Symbol, ws, A::B200CSR{T}, b::B200Vector{T}, x0::B200Vector{T}; kw...) where T
+  Krylov.warm_start!(ws, x0)
+  fused_solve!(method, ws, A, b; kw...)
+end
+
+for (fn, WS, sym, memexpr) in ((:cg!, :CgWorkspace, :cg, :(0)),
+                               (:gmres!, :GmresWorkspace, :gmres, :(length(ws.c))), (:bicgstab!, :BicgstabWorkspace, :bicgstab, :(0)),
+                               # sibling solvers served by the same library (SURVEY.md 8f-3); every other method keeps
+                               # running through the k* overloads above, one kernel per call
+                               (:cr!, :CrWorkspace, :cr, :(0)), (:cgs!, :CgsWorkspace, :cgs, :(0)),
+                               (:cg_lanczos!, :CgLanczosWorkspace, :cg_lanczos, :(0)), (:fom!, :FomWorkspace, :fom, :(length(ws.l))),
+                               (:fgmres!, :FgmresWorkspace, :fgmres, :(length(ws.c))), (:dqgmres!, :DqgmresWorkspace, :dqgmres, :(length(ws.V))),
+                               (:diom!, :DiomWorkspace, :diom, :(length(ws.V))))
+  @eval begin
+    Krylov.$fn(ws::Krylov.$WS{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T =
+      fused_solve!($(QuoteNode(sym)), ws, A, b; memory = $memexpr, kw...)
+    Krylov.$fn(ws::Krylov.$WS{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}, x0::B200Vector{T}; kw...) where T =
+      fused_solve!($(QuoteNode(sym)), ws, A, b, x0; memory = $memexpr, kw...)
+  end
+end
+# MINRES keeps `window` in the length of its err_vec (krylov_workspaces.jl:121-127)
+Krylov.minres!(ws::Krylov.MinresWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}; kw...) where T =
+  fused_solve!(:minres, ws, A, b; window = length(ws.err_vec), kw...)
+Krylov.minres!(ws::Krylov.MinresWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}, x0::B200Vector{T}; kw...) where T =
+  fused_solve!(:minres, ws, A, b, x0; window = length(ws.err_vec), kw...)
 
 end # module

@@ -292,7 +292,23 @@ class KrylovWorkspace:
     def _set_diag(self, which: int, d):
         if d is None:
             lib().krylov_b200_set_preconditioner_diag(self._h, which, None, 0)
+            if not isinstance(self, BlockGmresWorkspace):
+                lib().krylov_b200_set_preconditioner_blockdiag(self._h, which, 0, None, 0)
             return
+        if getattr(d, "ndim", 1) == 3:      # block-Jacobi: (nblocks, bs, bs) dense diagonal blocks
+            nb, bs, bs2 = d.shape
+            if bs != bs2 or nb != (self.n + bs - 1) // bs:
+                raise B200Error(f"block-diagonal preconditioner: expected ({(self.n + bs - 1) // bs}, {bs}, {bs}) blocks, got {tuple(d.shape)}")
+            if not _is_torch(d):
+                d = np.ascontiguousarray(d, dtype=self.dtype)
+            p, keep = _ptr(d)
+            self._order_after(d)
+            lib().krylov_b200_set_preconditioner_diag(self._h, which, None, 0)
+            if lib().krylov_b200_set_preconditioner_blockdiag(self._h, which, int(bs), p, 1 if _is_torch(d) else 0) != 0:
+                raise B200Error(_lib.last_error())
+            return
+        if not isinstance(self, BlockGmresWorkspace):
+            lib().krylov_b200_set_preconditioner_blockdiag(self._h, which, 0, None, 0)
         if not _is_torch(d):
             d = np.ascontiguousarray(d, dtype=self.dtype)
         p, keep = _ptr(d)

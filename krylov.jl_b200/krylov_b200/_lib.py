@@ -84,6 +84,7 @@ SIGNATURES = {
     "krylov_b200_share_operator": (_I, [_P, _P]),
     "krylov_b200_attach_csr": (_I, [_P, _P]),
     "krylov_b200_set_preconditioner_diag": (_I, [_P, _I, _P, _I]),
+    "krylov_b200_set_preconditioner_blockdiag": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
     "krylov_b200_default_options": (KrylovB200Options, []),
     "krylov_b200_set_options": (_I, [_P, C.POINTER(KrylovB200Options)]),
     "krylov_b200_get_stats": (_I, [_P, C.POINTER(KrylovB200Stats)]),

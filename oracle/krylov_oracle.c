@@ -12,6 +12,8 @@
 
 int oracle_dot_mode = 0;
 void oracle_set_dot_mode(int m) { oracle_dot_mode = m; }
+int oracle_precond_block = 0;
+void oracle_set_precond_block(int bs) { oracle_precond_block = bs; }
 
 /* ---- Float64 instantiation ---- */
 #define REAL double

@@ -73,8 +73,43 @@ static void SUF(kaxpby)(int n, REAL s, const REAL *x, REAL t, REAL *y) {
 }
 static void SUF(kfill)(int n, REAL *x, REAL v) { for (int i = 0; i < n; i++) x[i] = v; }
 
-/* mulorldiv!(y, P, x, ldiv) for P = Diagonal(d)  (krylov_utils.jl:307). */
+/* mulorldiv!(y, P, x, ldiv) for P = Diagonal(d)  (krylov_utils.jl:307).
+ * Test knob (oracle_set_precond_block(bs), bs >= 2): `d` then holds ceil(n/bs) dense bs x bs row-major diagonal
+ * blocks (block-Jacobi, docs/src/preconditioners.md:33): mul! is the block product, ldiv! a dense solve per block
+ * (Gaussian elimination with partial pivoting). */
+extern int oracle_precond_block;
+static void SUF(bdiagmul)(int n, int bs, REAL *y, const REAL *B, const REAL *x, int ldiv) {
+  for (int r0 = 0; r0 < n; r0 += bs) {
+    const int rows = (n - r0 < bs) ? n - r0 : bs;
+    const REAL *Bk = B + (size_t)(r0 / bs) * bs * bs;
+    if (!ldiv) {
+      for (int i = 0; i < rows; i++) {
+        REAL acc = (REAL)0;
+        for (int j = 0; j < rows; j++) { REAL p = Bk[i * bs + j] * x[r0 + j]; acc = acc + p; }
+        y[r0 + i] = acc;
+      }
+    } else {
+      REAL a[8][9];
+      for (int i = 0; i < rows; i++) { for (int j = 0; j < rows; j++) a[i][j] = Bk[i * bs + j]; a[i][rows] = x[r0 + i]; }
+      for (int c = 0; c < rows; c++) {
+        int piv = c;
+        for (int i = c + 1; i < rows; i++) if (FABS(a[i][c]) > FABS(a[piv][c])) piv = i;
+        if (piv != c) for (int j = 0; j <= rows; j++) { REAL t = a[c][j]; a[c][j] = a[piv][j]; a[piv][j] = t; }
+        for (int i = c + 1; i < rows; i++) {
+          REAL f = a[i][c] / a[c][c];
+          for (int j = c; j <= rows; j++) a[i][j] = a[i][j] - f * a[c][j];
+        }
+      }
+      for (int i = rows - 1; i >= 0; i--) {
+        REAL s = a[i][rows];
+        for (int j = i + 1; j < rows; j++) s = s - a[i][j] * y[r0 + j];
+        y[r0 + i] = s / a[i][i];
+      }
+    }
+  }
+}
 static void SUF(diagmul)(int n, REAL *y, const REAL *d, const REAL *x, int ldiv) {
+  if (oracle_precond_block >= 2) { SUF(bdiagmul)(n, oracle_precond_block, y, d, x, ldiv); return; }
   if (ldiv) for (int i = 0; i < n; i++) y[i] = x[i] / d[i];
   else      for (int i = 0; i < n; i++) y[i] = d[i] * x[i];
 }

@@ -126,6 +126,21 @@ class dot_mode:
         lib().oracle_set_dot_mode(0)
 
 
+class precond_block:
+    """with precond_block(bs): ...  -- M / N arrays handed to the solvers are read as ceil(n/bs) dense bs x bs diagonal
+    blocks (row-major, flattened) instead of a diagonal: the block-Jacobi twin of the product's
+    krylov_b200_set_preconditioner_blockdiag (test knob, krylov_oracle_impl.h: bdiagmul)."""
+
+    def __init__(self, bs):
+        self.bs = int(bs)
+
+    def __enter__(self):
+        lib().oracle_set_precond_block(self.bs)
+
+    def __exit__(self, *a):
+        lib().oracle_set_precond_block(0)
+
+
 def cg(A, b, x0=None, M=None, dtype=np.float64, **kw):
     """cg! (src/cg.jl:120-291).  M: None or the diagonal of a Diagonal preconditioner."""
     suf, _ = _suf(dtype)

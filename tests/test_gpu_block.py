@@ -30,9 +30,9 @@ def _check(st, X, so, Xo, tol=1e-6):
 @pytest.mark.parametrize("generic", [False, True, "prefetch", "simt", "mma8"])
 @pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 8, 16, 32])
 def test_block_gmres_block_sizes(kb, O, p, generic, monkeypatch):
-    """Float64 p = 16, 32 run the tensor-core panel kernels (mma.sync m8n8k4.f64; "mma8" routes p = 8 there too and
-    "simt" = KB200_BLOCK_MMA=0 keeps every p on the register-resident SIMT kernels); p = 2, 4, 8 the SIMT ones (with or
-    without software-pipelined row loads); every other p (and KB200_BLOCK_GENERIC=1) the tiled any-p kernels.
+    """Float64 p = 8, 16, 32 run the tensor-core panel kernels (mma.sync m8n8k4.f64; "simt" = KB200_BLOCK_MMA=0 keeps
+    every p on the register-resident SIMT kernels, "mma8" = KB200_BLOCK_MMA=16 only p = 8); p = 2, 4 the SIMT ones (with
+    or without software-pipelined row loads); every other p (and KB200_BLOCK_GENERIC=1) the tiled any-p kernels.
     All against the oracle."""
     if generic in ("simt", "mma8") and p not in (8, 16, 32):
         pytest.skip("variant only changes p = 8 / 16 / 32")
@@ -52,7 +52,7 @@ def test_block_gmres_block_sizes(kb, O, p, generic, monkeypatch):
             assert np.allclose(st.residuals, so["residuals"], rtol=1e-6, atol=1e-9 * so["residuals"][0])
             assert np.linalg.norm(X - Xo) <= 1e-6 * np.linalg.norm(Xo)
         """)
-        extra = {"prefetch": dict(KB200_FAST_PREFETCH="1"), "simt": dict(KB200_BLOCK_MMA="0"), "mma8": dict(KB200_BLOCK_MMA="8")}[generic]
+        extra = {"prefetch": dict(KB200_FAST_PREFETCH="1"), "simt": dict(KB200_BLOCK_MMA="0"), "mma8": dict(KB200_BLOCK_MMA="16")}[generic]
         out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **extra), capture_output=True, text=True)
         assert out.returncode == 0, out.stderr[-2000:]
         return

@@ -492,3 +492,23 @@ def test_cg_cr_on_system_zero_quad(O):
     assert not st["inconsistent"] and np.array_equal(x, b)
     x, st = O.cg(A, b)                                  # zero curvature without linesearch: inconsistent = true
     assert st["status"] == "zero curvature detected" and st["inconsistent"] and not st["indefinite"]
+
+
+def test_block_jacobi_twin_is_the_dense_block_operator(O):
+    """The oracle's block-preconditioner knob (bdiagmul) against NumPy: mul! = block product, ldiv! = block solve,
+    and CG preconditioned with the inverted diagonal blocks converges to the solution in fewer iterations."""
+    import scipy.sparse as sp
+    A, b = O.sparse_laplacian(6)
+    A = sp.csr_matrix(A + sp.diags(np.linspace(0.0, 2.0, A.shape[0])))
+    n, bs = A.shape[0], 4
+    nb = n // bs
+    D = np.stack([A[k * bs:(k + 1) * bs, k * bs:(k + 1) * bs].toarray() for k in range(nb)])
+    Dinv = np.linalg.inv(D)
+    x0, s0 = O.cg(A, b, atol=0.0, rtol=1e-10)
+    with O.precond_block(bs):
+        x1, s1 = O.cg(A, b, M=Dinv.reshape(-1), atol=0.0, rtol=1e-10)
+        x2, s2 = O.cg(A, b, M=D.reshape(-1), ldiv=True, atol=0.0, rtol=1e-10)
+    xs = sp.linalg.spsolve(sp.csc_matrix(A), b)
+    assert s1["solved"] and s2["solved"] and s1["niter"] < s0["niter"] and abs(s1["niter"] - s2["niter"]) <= 1
+    assert np.linalg.norm(x1 - xs) <= 1e-8 * np.linalg.norm(xs) and np.linalg.norm(x2 - xs) <= 1e-8 * np.linalg.norm(xs)
+    assert np.allclose(s1["residuals"][:5], s2["residuals"][:5], rtol=1e-10)
