@@ -602,14 +602,22 @@ panel_mma_kernel(int n, double alpha, const double* In, const double* __restrict
     // ---- update: D[mb] = sum_ks S^T frag x In frag ----
     double o[NB][2];
     if (UPDATE) {
+      // k-step outermost: the NB accumulator chains (one per 8-column block) are independent, so consecutive DMMAs
+      // never wait for each other's result (a per-block loop issues KS dependent DMMAs back to back)
+      double cacc[NB][2];
+#pragma unroll
+      for (int mb = 0; mb < NB; mb++) cacc[mb][0] = cacc[mb][1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < KS; ks++) {
+        const double bfrag = (ks & 1) ? iny[ks >> 1] : inx[ks >> 1];
+#pragma unroll
+        for (int mb = 0; mb < NB; mb++)
+          dmma_884(cacc[mb][0], cacc[mb][1], Sf[(ks * NB + mb) * 32 + lane], bfrag, cacc[mb][0], cacc[mb][1]);
+      }
 #pragma unroll
       for (int mb = 0; mb < NB; mb++) {
-        double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-        for (int ks = 0; ks < KS; ks++)
-          dmma_884(c0, c1, Sf[(ks * NB + mb) * 32 + lane], (ks & 1) ? iny[ks >> 1] : inx[ks >> 1], c0, c1);
-        o[mb][0] = beta != 0.0 ? fma(alpha, c0, beta * old[mb][0]) : alpha * c0;
-        o[mb][1] = beta != 0.0 ? fma(alpha, c1, beta * old[mb][1]) : alpha * c1;
+        o[mb][0] = beta != 0.0 ? fma(alpha, cacc[mb][0], beta * old[mb][0]) : alpha * cacc[mb][0];
+        o[mb][1] = beta != 0.0 ? fma(alpha, cacc[mb][1], beta * old[mb][1]) : alpha * cacc[mb][1];
       }
 #pragma unroll
       for (int e = 0; e < 2; e++) {
@@ -626,11 +634,11 @@ panel_mma_kernel(int n, double alpha, const double* In, const double* __restrict
     // ---- Gram: acc[ib][jb] += L^T frag x Out frag (rows past n contribute zeros) ----
     if (GRAM) {
 #pragma unroll
-      for (int ib = 0; ib < NB; ib++)
+      for (int e = 0; e < 2; e++)             // k-step outermost: NB * NB independent accumulators per step
 #pragma unroll
-        for (int jb = 0; jb < NB; jb++)
+        for (int ib = 0; ib < NB; ib++)
 #pragma unroll
-          for (int e = 0; e < 2; e++)
+          for (int jb = 0; jb < NB; jb++)
             dmma_884(acc[ib][jb][0], acc[ib][jb][1], Next != nullptr ? nx[ib][e] : o[ib][e], o[jb][e], acc[ib][jb][0], acc[ib][jb][1]);
     }
   }

@@ -356,25 +356,33 @@ template <class T> struct GmresMgsBody {  // q -= h_i v_i ; then <v_{i+1}, q> or
   }
 };
 
-// Arnoldi step k (1-based inner_iter): w = A V[k]; MGS against V[1..k]; returns h[0..k-1] and Hbis.
+// q = M (A xin), modified Gram-Schmidt of q against vecs[0..cnt-1] IN THAT ORDER, one launch per vector with the next
+// dot product (or ||q||^2 after the last one) accumulated in the same pass; returns h[0..cnt-1] and ||q||.
+// gmres! / fom! / fgmres! pass V[1..k]; dqgmres! / diom! the live window of their circular stack.
 template <class T>
-void gmres_fused_arnoldi(Workspace<T>& ws, const Csr<T>& A, int k, T* h_out, T* Hbis, const T* xin) {
+void fused_orth_chain(Workspace<T>& ws, const Csr<T>& A, const T* xin, T* q, const T* const* vecs, int cnt, T* h_out, T* Hbis) {
   Ctx& c = ws.ctx;
   const int n = ws.n;
   typedef GmresState<T> St;
   St* S = state_buf<St>(ws.fused_state, ws.fused_host);
   St* H = (St*)ws.fused_host;
   const T* m = ws.mdiag_fused;
-  T* q = m ? ws.q : ws.w;                                   // q == w when M = I (gmres.jl:150)
-  launch_spmv_epi<T, 1>(c, A, xin ? xin : ws.V[k - 1], GmresSpmvEpi<T>{q, ws.V[0], m}, GmresHFin<T>{S, 0}, 4);
-  for (int i = 0; i < k; i++) {
-    const T* vnext = (i + 1 < k) ? ws.V[i + 1] : nullptr;
-    launch_stream<T, 1>(c, n, GmresMgsBody<T>{q, ws.V[i], vnext, S, i}, GmresHFin<T>{S, (i + 1 < k) ? i + 1 : -1}, 5);
+  launch_spmv_epi<T, 1>(c, A, xin, GmresSpmvEpi<T>{q, vecs[0], m}, GmresHFin<T>{S, 0}, 4);
+  for (int i = 0; i < cnt; i++) {
+    const T* vnext = (i + 1 < cnt) ? vecs[i + 1] : nullptr;
+    launch_stream<T, 1>(c, n, GmresMgsBody<T>{q, vecs[i], vnext, S, i}, GmresHFin<T>{S, (i + 1 < cnt) ? i + 1 : -1}, 5);
   }
-  KB_CUDA(cudaMemcpyAsync(H, S, sizeof(T) * (size_t)(k + 1), cudaMemcpyDeviceToHost, c.stream));
+  KB_CUDA(cudaMemcpyAsync(H, S, sizeof(T) * (size_t)(cnt + 1), cudaMemcpyDeviceToHost, c.stream));
   c.sync();
-  for (int i = 0; i < k; i++) h_out[i] = H->h[i];
+  for (int i = 0; i < cnt; i++) h_out[i] = H->h[i];
   *Hbis = std::sqrt(H->hbis2);
+}
+
+// Arnoldi step k (1-based inner_iter): w = A V[k]; MGS against V[1..k]; returns h[0..k-1] and Hbis.
+template <class T>
+void gmres_fused_arnoldi(Workspace<T>& ws, const Csr<T>& A, int k, T* h_out, T* Hbis, const T* xin) {
+  T* q = ws.mdiag_fused ? ws.q : ws.w;                      // q == w when M = I (gmres.jl:150)
+  fused_orth_chain<T>(ws, A, xin ? xin : ws.V[k - 1], q, ws.V.data(), k, h_out, Hbis);
 }
 
 // xr += sum_i y_i V[i], accumulated in index order in one pass (gmres.jl:348-350)
@@ -400,6 +408,196 @@ void fused_multi_axpy(Workspace<T>& ws, T* xr, int k, const T* y, T* const* vecs
 template <class T>
 void gmres_fused_update_x(Workspace<T>& ws, T* xr, int k, const T* y) { fused_multi_axpy<T>(ws, xr, k, y, ws.V.data()); }
 
+// ===========================================================================
+// Sibling solvers, M = N = I, CSR operator: the vector operations of one iteration are grouped into
+// the fewest passes the data dependencies allow.  The scalars stay on the HOST (these loops run the reference's
+// control flow unchanged and read each group of dot products back once), so unlike the four path solvers nothing
+// chains through device memory; what is saved is launches, vector passes and read-backs:
+//   dqgmres! / diom!  2 k + 6 launches, 2 k + 2 read-backs per iteration  ->  k + 3 launches, 1 read-back (k = window)
+//   cgs!              12 launches, 3 read-backs                           ->  4 launches, 2 read-backs
+//   cg_lanczos!        8 launches, 2 read-backs                           ->  3 launches, 2 read-backs
+//   cr!                9 launches, 5 read-backs                           ->  3 launches, 2 read-backs
+// Every element update repeats the k* sequence it replaces operation by operation (non-contracted), so vectors are
+// bit-identical to the primitive path given the same scalars.
+// ===========================================================================
+template <class T, int K> struct StoreFin {          // K grid totals -> K consecutive device scalars
+  T* out;
+  __device__ void operator()(const T* tot) const {
+#pragma unroll
+    for (int k = 0; k < K; k++) out[k] = tot[k];
+  }
+};
+template <class T> static T* sib_slots(Ctx& c) { return reinterpret_cast<T*>(reinterpret_cast<double*>(c.dscal) + 8); }
+template <class T, int K> static void sib_read(Ctx& c, T* out) {
+  T* h = reinterpret_cast<T*>(reinterpret_cast<double*>(c.hscal) + 8);
+  KB_CUDA(cudaMemcpyAsync(h, sib_slots<T>(c), sizeof(T) * K, cudaMemcpyDeviceToHost, c.stream));
+  c.sync();
+  for (int k = 0; k < K; k++) out[k] = h[k];
+}
+
+// ---- dqgmres! / diom!: direction update (dqgmres.jl:279-289, diom.jl:279-289) in one pass per 8 stack vectors ----
+//   for every live i: P[ppos] = -H_i P[ppos] (same slot) or P[ppos] -= H_i P[ipos];  then P[ppos] += z; P[ppos] /= H_1;
+//   x += step P[ppos]
+template <class T, int NV> struct TruncPBody {
+  T* pp; const T* pv[NV]; T coef[NV]; int same[NV]; int cnt; int last; const T* z; T inv_h0; T step; T* x;
+  __device__ __forceinline__ void operator()(int j, T*) const {
+    T acc = pp[j];
+#pragma unroll
+    for (int i = 0; i < NV; i++)
+      if (i < cnt) acc = same[i] ? mul_rn(coef[i], acc) : add_rn(acc, mul_rn(coef[i], pv[i][j]));
+    if (last) {
+      acc = add_rn(acc, z[j]);                    // kaxpy!(n, one, z, p)
+      acc = mul_rn(inv_h0, acc);                  // kdiv!(n, p, H[1]) = kscal!(n, 1 / H[1], p)
+      x[j] = add_rn(x[j], mul_rn(step, acc));
+    }
+    pp[j] = acc;
+  }
+};
+template <class T>
+void trunc_fused_direction(Workspace<T>& ws, T* pp, int cnt, T* const* pvecs, const T* coefs, const T* z, T h0, T step) {
+  constexpr int NV = 8;
+  int base = 0;
+  do {
+    TruncPBody<T, NV> body;
+    body.pp = pp; body.cnt = std::max(0, std::min(NV, cnt - base)); body.z = z; body.inv_h0 = T(1) / h0; body.step = step; body.x = ws.x;
+    body.last = (base + NV >= cnt) ? 1 : 0;
+    for (int i = 0; i < NV; i++) {
+      const int k = std::min(base + i, std::max(cnt - 1, 0));
+      body.pv[i] = cnt > 0 ? pvecs[k] : pp; body.coef[i] = (cnt > 0 && base + i < cnt) ? coefs[base + i] : T(0);
+      body.same[i] = (cnt > 0 && pvecs[k] == pp) ? 1 : 0;
+    }
+    launch_stream<T, 0>(ws.ctx, ws.n, body, NoFin(), 5);
+    base += NV;
+  } while (base < cnt);
+}
+
+// ---- cgs! (src/cgs.jl:196-239) ----
+template <class T> struct CgsK1Epi {               // t = A p ; sigma = <c, t>
+  T* t; const T* cv;
+  __device__ __forceinline__ void operator()(int row, T acc, T* d) const { t[row] = acc; d[0] += __ldg(&cv[row]) * acc; }
+};
+template <class T> struct CgsK2Body {              // q = u - alpha v ; u += q ; x += alpha u
+  T* q; T* u; const T* v; T* x; T alpha;
+  __device__ __forceinline__ void operator()(int j, T*) const {
+    const T qn = add_rn(u[j], mul_rn(-alpha, v[j]));
+    q[j] = qn;
+    const T un = add_rn(u[j], qn);
+    u[j] = un;
+    x[j] = add_rn(x[j], mul_rn(alpha, un));
+  }
+};
+template <class T> struct CgsK3Epi {               // s = A u ; r -= alpha s ; <c, r>, <r, r>
+  T* s; T* r; const T* cv; T alpha;
+  __device__ __forceinline__ void operator()(int row, T acc, T* d) const {
+    s[row] = acc;
+    const T rn = add_rn(r[row], mul_rn(-alpha, acc));
+    r[row] = rn;
+    d[0] += __ldg(&cv[row]) * rn; d[1] += rn * rn;
+  }
+};
+template <class T> struct CgsK4Body {              // u = r + beta q ; p = u + beta (q + beta p)
+  T* u; T* p; const T* r; const T* q; T beta;
+  __device__ __forceinline__ void operator()(int j, T*) const {
+    const T un = add_rn(r[j], mul_rn(beta, q[j]));
+    u[j] = un;
+    const T p1 = add_rn(q[j], mul_rn(beta, p[j]));
+    p[j] = add_rn(un, mul_rn(beta, p1));
+  }
+};
+template <class T> T cgs_fused_sigma(Workspace<T>& ws, const Csr<T>& A, const T* cvec) {
+  Ctx& c = ws.ctx;
+  launch_spmv_epi<T, 1>(c, A, ws.p, CgsK1Epi<T>{ws.ts, cvec}, StoreFin<T, 1>{sib_slots<T>(c)}, 4);
+  T out[1]; sib_read<T, 1>(c, out);
+  return out[0];
+}
+template <class T> void cgs_fused_update(Workspace<T>& ws, const Csr<T>& A, const T* cvec, T alpha, T* rho_next, T* rr) {
+  Ctx& c = ws.ctx;
+  launch_stream<T, 0>(c, ws.n, CgsK2Body<T>{ws.q, ws.u, ws.ts, ws.x, alpha}, NoFin(), 5);
+  launch_spmv_epi<T, 2>(c, A, ws.u, CgsK3Epi<T>{ws.ts, ws.r, cvec, alpha}, StoreFin<T, 2>{sib_slots<T>(c)}, 4);
+  T out[2]; sib_read<T, 2>(c, out);
+  *rho_next = out[0]; *rr = out[1];
+}
+template <class T> void cgs_fused_directions(Workspace<T>& ws, T beta) {
+  launch_stream<T, 0>(ws.ctx, ws.n, CgsK4Body<T>{ws.u, ws.p, ws.r, ws.q, beta}, NoFin(), 5);
+}
+
+// ---- cg_lanczos! (src/cg_lanczos.jl:186-216), M = I so v === Mv ----
+template <class T> struct LanK1Epi {               // Mv_next = A v ; delta = <v, Mv_next>
+  T* mvn; const T* v;
+  __device__ __forceinline__ void operator()(int row, T acc, T* d) const { mvn[row] = acc; d[0] += __ldg(&v[row]) * acc; }
+};
+template <class T> struct LanK2Body {              // Mv_next -= delta Mv (- beta Mv_prev) ; Mv_prev = Mv ; Mv = Mv_next ; ||Mv||^2
+  T* mvn; T* mv; T* mvp; T delta; T beta; int later;
+  __device__ __forceinline__ void operator()(int j, T* d) const {
+    T m = add_rn(mvn[j], mul_rn(-delta, mv[j]));
+    if (later) { m = add_rn(m, mul_rn(-beta, mvp[j])); mvp[j] = mv[j]; }
+    mvn[j] = m; mv[j] = m;
+    d[0] += m * m;
+  }
+};
+template <class T> struct LanK3Body {              // v /= beta ; x += gamma p ; p = sigma v + omega p
+  T* v; T* x; T* p; T inv_beta; T gamma; T sigma; T omega;
+  __device__ __forceinline__ void operator()(int j, T*) const {
+    const T vn = mul_rn(inv_beta, v[j]);
+    v[j] = vn;
+    x[j] = add_rn(x[j], mul_rn(gamma, p[j]));
+    p[j] = add_rn(mul_rn(sigma, vn), mul_rn(omega, p[j]));
+  }
+};
+template <class T> T lanczos_fused_delta(Workspace<T>& ws, const Csr<T>& A) {
+  Ctx& c = ws.ctx;
+  launch_spmv_epi<T, 1>(c, A, ws.Mv, LanK1Epi<T>{ws.Mv_next, ws.Mv}, StoreFin<T, 1>{sib_slots<T>(c)}, 4);
+  T out[1]; sib_read<T, 1>(c, out);
+  return out[0];
+}
+template <class T> T lanczos_fused_recur(Workspace<T>& ws, T delta, T beta, bool later) {
+  Ctx& c = ws.ctx;
+  launch_stream<T, 1>(c, ws.n, LanK2Body<T>{ws.Mv_next, ws.Mv, ws.Mv_prev, delta, beta, later ? 1 : 0}, StoreFin<T, 1>{sib_slots<T>(c)}, 5);
+  T out[1]; sib_read<T, 1>(c, out);
+  return std::sqrt(out[0]);
+}
+template <class T> void lanczos_fused_update(Workspace<T>& ws, T beta, T gamma, T sigma, T omega) {
+  launch_stream<T, 0>(ws.ctx, ws.n, LanK3Body<T>{ws.Mv, ws.x, ws.p, T(1) / beta, gamma, sigma, omega}, NoFin(), 5);
+}
+
+// ---- cr! (src/cr.jl:375-445), M = I, no trust region, no linesearch ----
+template <class T> struct CrK1Body {               // x += alpha p ; r -= alpha q ; ||x||^2, ||r||^2
+  T* x; T* r; const T* p; const T* q; T alpha;
+  __device__ __forceinline__ void operator()(int j, T* d) const {
+    const T xn = add_rn(x[j], mul_rn(alpha, p[j]));
+    x[j] = xn;
+    const T rn = add_rn(r[j], mul_rn(-alpha, q[j]));
+    r[j] = rn;
+    d[0] += xn * xn; d[1] += rn * rn;
+  }
+};
+template <class T> struct CrK2Epi {                // Ar = A r ; ||Ar||^2, <r, Ar>
+  T* Ar; const T* r;
+  __device__ __forceinline__ void operator()(int row, T acc, T* d) const { Ar[row] = acc; d[0] += acc * acc; d[1] += __ldg(&r[row]) * acc; }
+};
+template <class T> struct CrK3Body {               // p = r + beta p ; q = Ar + beta q ; ||q||^2 (the next alpha's denominator)
+  T* p; T* q; const T* r; const T* Ar; T beta;
+  __device__ __forceinline__ void operator()(int j, T* d) const {
+    p[j] = add_rn(r[j], mul_rn(beta, p[j]));
+    const T qn = add_rn(Ar[j], mul_rn(beta, q[j]));
+    q[j] = qn;
+    d[0] += qn * qn;
+  }
+};
+template <class T> void cr_fused_step(Workspace<T>& ws, const Csr<T>& A, T alpha, T* xx, T* rr, T* ArAr, T* rAr) {
+  Ctx& c = ws.ctx;
+  launch_stream<T, 2>(c, ws.n, CrK1Body<T>{ws.x, ws.r, ws.p, ws.q, alpha}, StoreFin<T, 2>{sib_slots<T>(c)}, 5);
+  launch_spmv_epi<T, 2>(c, A, ws.r, CrK2Epi<T>{ws.Ap, ws.r}, StoreFin<T, 2>{sib_slots<T>(c) + 2}, 4);
+  T out[4]; sib_read<T, 4>(c, out);
+  *xx = out[0]; *rr = out[1]; *ArAr = out[2]; *rAr = out[3];
+}
+template <class T> T cr_fused_directions(Workspace<T>& ws, T beta) {
+  Ctx& c = ws.ctx;
+  launch_stream<T, 1>(c, ws.n, CrK3Body<T>{ws.p, ws.q, ws.r, ws.Ap, beta}, StoreFin<T, 1>{sib_slots<T>(c)}, 5);
+  T out[1]; sib_read<T, 1>(c, out);
+  return out[0];
+}
+
 int gmres_fused_max() { return kGmresMaxFused; }
 
 #define INST(T)                                                                                                      \
@@ -407,6 +605,16 @@ int gmres_fused_max() { return kGmresMaxFused; }
   template void minres_fused_lanczos<T>(Workspace<T>&, const Csr<T>&, int, T, T, T, T, T, T, T, T*, T*, T*);          \
   template T minres_fused_update<T>(Workspace<T>&, T*, T, T);                                                        \
   template void gmres_fused_arnoldi<T>(Workspace<T>&, const Csr<T>&, int, T*, T*, const T*);                         \
+  template void fused_orth_chain<T>(Workspace<T>&, const Csr<T>&, const T*, T*, const T* const*, int, T*, T*);       \
+  template void trunc_fused_direction<T>(Workspace<T>&, T*, int, T* const*, const T*, const T*, T, T);               \
+  template T cgs_fused_sigma<T>(Workspace<T>&, const Csr<T>&, const T*);                                             \
+  template void cgs_fused_update<T>(Workspace<T>&, const Csr<T>&, const T*, T, T*, T*);                              \
+  template void cgs_fused_directions<T>(Workspace<T>&, T);                                                           \
+  template T lanczos_fused_delta<T>(Workspace<T>&, const Csr<T>&);                                                   \
+  template T lanczos_fused_recur<T>(Workspace<T>&, T, T, bool);                                                      \
+  template void lanczos_fused_update<T>(Workspace<T>&, T, T, T, T);                                                  \
+  template void cr_fused_step<T>(Workspace<T>&, const Csr<T>&, T, T*, T*, T*, T*);                                   \
+  template T cr_fused_directions<T>(Workspace<T>&, T);                                                               \
   template void fused_multi_axpy<T>(Workspace<T>&, T*, int, const T*, T* const*);                                    \
   template void gmres_fused_update_x<T>(Workspace<T>&, T*, int, const T*);
 INST(double)

@@ -269,6 +269,17 @@ template <class T> T minres_fused_update(Workspace<T>& ws, T* w, T gamma, T phi)
 // xin: vector the operator is applied to (default V[k]; FGMRES passes Z[k])
 template <class T> void gmres_fused_arnoldi(Workspace<T>& ws, const Csr<T>& A, int k, T* h_out, T* Hbis, const T* xin = nullptr);
 template <class T> void fused_multi_axpy(Workspace<T>& ws, T* xr, int k, const T* y, T* const* vecs);
+// sibling solvers (fused_phases.cu): grouped passes with host-side scalars
+template <class T> void fused_orth_chain(Workspace<T>& ws, const Csr<T>& A, const T* xin, T* q, const T* const* vecs, int cnt, T* h_out, T* Hbis);
+template <class T> void trunc_fused_direction(Workspace<T>& ws, T* pp, int cnt, T* const* pvecs, const T* coefs, const T* z, T h0, T step);
+template <class T> T cgs_fused_sigma(Workspace<T>& ws, const Csr<T>& A, const T* cvec);
+template <class T> void cgs_fused_update(Workspace<T>& ws, const Csr<T>& A, const T* cvec, T alpha, T* rho_next, T* rr);
+template <class T> void cgs_fused_directions(Workspace<T>& ws, T beta);
+template <class T> T lanczos_fused_delta(Workspace<T>& ws, const Csr<T>& A);
+template <class T> T lanczos_fused_recur(Workspace<T>& ws, T delta, T beta, bool later);
+template <class T> void lanczos_fused_update(Workspace<T>& ws, T beta, T gamma, T sigma, T omega);
+template <class T> void cr_fused_step(Workspace<T>& ws, const Csr<T>& A, T alpha, T* xx, T* rr, T* ArAr, T* rAr);
+template <class T> T cr_fused_directions(Workspace<T>& ws, T beta);
 template <class T> void gmres_fused_update_x(Workspace<T>& ws, T* xr, int k, const T* y);
 int gmres_fused_max();
 

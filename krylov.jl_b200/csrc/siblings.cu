@@ -62,12 +62,26 @@ void cgs_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c_in, c
   bool solved = rNorm <= eps_tol, tired = iter >= itmax, breakdown = false, user_exit = false, overtimed = false;
   std::string status = "unknown";
 
+  // grouped passes (fused_phases.cu): 4 launches and 2 read-backs per iteration instead of 12 and 3
+  const bool fusedS = o.fused && A.kind == LinOp<T>::CSR && MisI && NisI;
   while (!(solved || tired || breakdown || user_exit || overtimed)) {
+    T alpha, rho_next;
+    if (fusedS) {
+      const T sigma = cgs_fused_sigma<T>(ws, *A.csr, cvec);
+      alpha = rho / sigma;
+      T rr;
+      cgs_fused_update<T>(ws, *A.csr, cvec, alpha, &rho_next, &rr);
+      const T beta = rho_next / rho;
+      cgs_fused_directions<T>(ws, beta);
+      rho = rho_next;
+      iter = iter + 1;
+      rNorm = std::sqrt(rr);
+    } else {
     if (!NisI) op_apply(c, N, p, y, ldiv);
     op_apply(c, A, y, t);
     if (!MisI) op_apply(c, M, t, v, ldiv);
     const T sigma = k_dot<T>(c, n, cvec, v);
-    const T alpha = rho / sigma;
+    alpha = rho / sigma;
     k_copy<T>(c, n, q, u);
     k_axpy<T>(c, n, -alpha, v, q);
     k_axpy<T>(c, n, T(1), q, u);
@@ -76,7 +90,7 @@ void cgs_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c_in, c
     op_apply(c, A, z, s);
     if (!MisI) op_apply(c, M, s, w, ldiv);
     k_axpy<T>(c, n, -alpha, w, r);
-    const T rho_next = k_dot<T>(c, n, cvec, r);
+    rho_next = k_dot<T>(c, n, cvec, r);
     const T beta = rho_next / rho;
     k_copy<T>(c, n, u, r);
     k_axpy<T>(c, n, beta, q, u);
@@ -85,6 +99,7 @@ void cgs_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c_in, c
     rho = rho_next;
     iter = iter + 1;
     rNorm = k_nrm2<T>(c, n, r);
+    }
     if (history) stats.residuals.push_back(rNorm);
     const bool resid_decrease_mach = (rNorm + T(1) <= T(1));
     if (o.callback) { c.sync(); stats.niter = iter; user_exit = o.callback(&ws, o.callback_user) != 0; }
@@ -161,11 +176,15 @@ void cg_lanczos_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const Lin
   std::string status = "unknown";
 
   while (!(solved || tired || (check_curvature && indefinite) || user_exit || overtimed)) {
-    op_apply(c, A, v, Mv_next);
-    const T delta = k_dot<T>(c, n, v, Mv_next);
+    // grouped passes (fused_phases.cu; M = I so v === Mv): 3 launches per iteration instead of 8
+    const bool fusedL = o.fused && A.kind == LinOp<T>::CSR && MisI;
+    const T delta = fusedL ? lanczos_fused_delta<T>(ws, *A.csr) : (op_apply(c, A, v, Mv_next), k_dot<T>(c, n, v, Mv_next));
     gamma = T(1) / (delta - omega / gamma);
     indefinite = indefinite || (gamma <= 0);
     if (check_curvature && indefinite) continue;
+    if (fusedL) {
+      beta = lanczos_fused_recur<T>(ws, delta, beta, iter > 0);
+    } else {
     k_axpy<T>(c, n, -delta, Mv, Mv_next);
     if (iter > 0) {
       k_axpy<T>(c, n, -beta, Mv_prev, Mv_next);
@@ -176,13 +195,15 @@ void cg_lanczos_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const Lin
     beta = norm_elliptic();
     k_scal<T>(c, n, T(1) / beta, v);
     if (!MisI) k_scal<T>(c, n, T(1) / beta, Mv);
+    }
     Anorm2 += beta_prev * beta_prev + beta * beta + delta * delta;
     beta_prev = beta;
-    k_axpy<T>(c, n, gamma, p, x);
+    if (!fusedL) k_axpy<T>(c, n, gamma, p, x);
     omega = beta * gamma;
     sigma = -omega * sigma;
     omega = omega * omega;
-    k_axpby<T>(c, n, sigma, v, omega, p);
+    if (fusedL) lanczos_fused_update<T>(ws, beta, gamma, sigma, omega);
+    else k_axpby<T>(c, n, sigma, v, omega, p);
     rNorm = std::fabs(sigma);
     if (history) stats.residuals.push_back(rNorm);
     iter = iter + 1;
@@ -488,14 +509,30 @@ static void truncated_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, con
   bool solved = rNorm <= eps_tol, tired = iter >= itmax, user_exit = false, overtimed = false;
   std::string status = "unknown";
 
+  // grouped passes (fused_phases.cu): window + 3 launches and one read-back per iteration instead of 2 window + 6
+  constexpr int kMaxWindow = 120;
+  const bool fusedT = o.fused && A.kind == LinOp<T>::CSR && MisI && NisI && !reorth && mem <= kMaxWindow && mem <= gmres_fused_max();
+  ws.mdiag_fused = nullptr;
+  T* dvec[kMaxWindow]; T dcoef[kMaxWindow];
   while (!(solved || tired || user_exit || overtimed)) {
     iter = iter + 1;
+    int ndir = 0;
     const int pos = (iter - 1) % mem + 1, next_pos = iter % mem + 1;
     T* z = NisI ? V[pos - 1] : ws.yz;
+    const int lo = std::max(1, iter - mem + 1);
+    T Haux;
+    if (fusedT) {
+      // SpMV + incomplete orthogonalization as ONE chain of passes (fused_phases.cu: fused_orth_chain): the dot
+      // product with the next basis vector rides in the pass that subtracts the current one; one read-back
+      const T* vecs[kMaxWindow]; T hbuf[kMaxWindow];
+      const int cnt = iter - lo + 1;
+      for (int i = lo; i <= iter; i++) vecs[i - lo] = V[(i - 1) % mem];
+      fused_orth_chain<T>(ws, *A.csr, z, w, vecs, cnt, hbuf, &Haux);
+      for (int i = lo; i <= iter; i++) H[iter - i] = hbuf[i - lo];
+    } else {
     if (!NisI) op_apply(cx, N, V[pos - 1], z, ldiv);
     op_apply(cx, A, z, t);
     if (!MisI) op_apply(cx, M, t, w, ldiv);
-    const int lo = std::max(1, iter - mem + 1);
     for (int i = lo; i <= iter; i++) {          // incomplete orthogonalization
       const int ipos = (i - 1) % mem + 1, diag = iter - i + 1;
       H[diag - 1] = k_dot<T>(cx, n, w, V[ipos - 1]);
@@ -509,7 +546,8 @@ static void truncated_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, con
         k_axpy<T>(cx, n, -Htmp, V[ipos - 1], w);
       }
     }
-    const T Haux = k_nrm2<T>(cx, n, w);
+    Haux = k_nrm2<T>(cx, n, w);
+    }
     if (Haux != 0) k_divcopy<T>(cx, n, V[next_pos - 1], w, Haux);
     int ppos;                                   // position of p_k in the circular stack P
     T step;                                     // x += step * p_k
@@ -528,7 +566,8 @@ static void truncated_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, con
       ppos = pos;
       for (int i = lo2; i <= iter - 1; i++) {
         const int ipos = (i - 1) % mem + 1, diag = iter - i + 1;
-        if (ipos == ppos) k_scal<T>(cx, n, -H[diag - 1], P[ppos - 1]);
+        if (fusedT) { dvec[ndir] = P[ipos - 1]; dcoef[ndir++] = -H[diag - 1]; }
+        else if (ipos == ppos) k_scal<T>(cx, n, -H[diag - 1], P[ppos - 1]);
         else k_axpy<T>(cx, n, -H[diag - 1], P[ipos - 1], P[ppos - 1]);
       }
       step = gamma_k;
@@ -547,15 +586,21 @@ static void truncated_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, con
       ppos = (iter - 1) % (mem - 1) + 1;
       for (int i = lo; i <= iter - 1; i++) {
         const int ipos = (i - 1) % (mem - 1) + 1, diag = iter - i + 1;
-        if (ipos == ppos) k_scal<T>(cx, n, -H[diag - 1], P[ppos - 1]);
+        if (fusedT) { dvec[ndir] = P[ipos - 1]; dcoef[ndir++] = -H[diag - 1]; }
+        else if (ipos == ppos) k_scal<T>(cx, n, -H[diag - 1], P[ppos - 1]);
         else k_axpy<T>(cx, n, -H[diag - 1], P[ipos - 1], P[ppos - 1]);
       }
       step = gamma_k;
       rNorm = Haux * std::fabs(gamma_k / H[0]);
     }
+    if (fusedT) {
+      // the whole direction update + x update in one pass per 8 stack vectors (trunc_fused_direction)
+      trunc_fused_direction<T>(ws, P[ppos - 1], ndir, dvec, dcoef, z, H[0], step);
+    } else {
     k_axpy<T>(cx, n, T(1), z, P[ppos - 1]);
     k_scal<T>(cx, n, T(1) / H[0], P[ppos - 1]);   // kdiv!(n, P[pos], H[1])
     k_axpy<T>(cx, n, step, P[ppos - 1], x);
+    }
     if (history) stats.residuals.push_back(rNorm);
     const bool resid_decrease_mach = (rNorm + T(1) <= T(1));
     if (o.callback) { cx.sync(); stats.niter = iter; user_exit = o.callback(&ws, o.callback_user) != 0; }
@@ -678,6 +723,10 @@ void cr_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
   if (kdisplay(iter, o.verbose)) printf("%5d  %8.1e  %8.1e  %8.1e  %.2fs\n", iter, (double)xNorm, (double)rNorm, (double)mquad, now_seconds() - start_time);
   bool descent = pr > 0, solved = rNorm <= eps_tol, tired = iter >= itmax, on_boundary = false, npcurv = false;
   bool user_exit = false, overtimed = false;
+  // grouped passes (no trust region, no linesearch, M = I): 3 launches and 2 read-backs per iteration instead of 9 and 5
+  const bool fusedC = o.fused && A.kind == LinOp<T>::CSR && MisI && radius == 0 && !linesearch;
+  T qq = 0;
+  bool have_qq = false;
   std::string status = "unknown";
   const T sqeps = std::sqrt(eps_of<T>());
 
@@ -752,8 +801,16 @@ void cr_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
       // (when the branches above rebind p := r, q := Ar, `Mq` keeps naming the ORIGINAL q array, as in the reference
       //  where Mq was bound once at cr.jl:155; the rebinding always ends the solve in this iteration)
     } else if (radius == 0) {
-      alpha = rho / k_dot<T>(c, n, q, Mq);
+      alpha = rho / (fusedC && have_qq ? qq : k_dot<T>(c, n, q, Mq));
     }
+    T rAr_fused = 0;
+    if (fusedC) {
+      // grouped passes (fused_phases.cu): x, r updates with ||x||, ||r||; then Ar = A r with ||Ar||, <r, Ar>
+      T xx, ArAr;
+      cr_fused_step<T>(ws, *A.csr, alpha, &xx, &rNorm2, &ArAr, &rAr_fused);
+      xNorm = std::sqrt(xx); rNorm = std::sqrt(rNorm2); ArNorm = std::sqrt(ArAr);
+      if (history) { stats.residuals.push_back(rNorm); stats.Aresiduals.push_back(ArNorm); }
+    } else {
     k_axpy<T>(c, n, alpha, p, x);
     xNorm = k_nrm2<T>(c, n, x);
     if (radius > 0 && std::fabs(xNorm - radius) <= sqeps * std::max(std::fabs(xNorm), std::fabs(radius))) on_boundary = true;   // xNorm ≈ radius
@@ -768,6 +825,7 @@ void cr_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
     op_apply(c, A, r, Ar);
     ArNorm = k_nrm2<T>(c, n, Ar);
     if (history) stats.Aresiduals.push_back(ArNorm);
+    }
     iter = iter + 1;
     if (kdisplay(iter, o.verbose)) {
       mquad = mquad - alpha * pr + alpha * alpha * pAp / 2;
@@ -782,10 +840,13 @@ void cr_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
     agree_exit(ws, o, user_exit, overtimed);      // row-partitioned: same decision on every rank
     if (solved || tired || user_exit || overtimed) continue;
     const T rhobar = rho;
-    rho = k_dot<T>(c, n, r, Ar);
+    rho = fusedC ? rAr_fused : k_dot<T>(c, n, r, Ar);
     const T beta = rho / rhobar;
+    if (fusedC) { qq = cr_fused_directions<T>(ws, beta); have_qq = true; }   // p, q updates + ||q||^2 for the next alpha
+    else {
     k_axpby<T>(c, n, T(1), r, beta, p);
     k_axpby<T>(c, n, T(1), Ar, beta, q);
+    }
     pNorm2 = rNorm2 + 2 * beta * pr - 2 * beta * alpha * pAp + beta * beta * pNorm2;
     if (pNorm2 > sqeps) pNorm = std::sqrt(pNorm2);
     else if (std::fabs(pNorm2) <= sqeps) pNorm = T(0);

@@ -271,3 +271,28 @@ def test_cr_curvature_cases(kb, O):
         kb.cr(Ai, bi)                            # "Indefinite system and no trust region"
     with pytest.raises(kb.B200Error):
         kb.cr(A, b, linesearch=True, radius=1.0)
+
+
+@pytest.mark.parametrize("solver,kw", [("cgs", {}), ("cg_lanczos", {}), ("cr", {}), ("dqgmres", dict(memory=6)), ("diom", dict(memory=6)),
+                                       ("dqgmres", dict(memory=20)), ("diom", dict(memory=3))])
+def test_grouped_passes_equal_the_primitive_path(kb, O, solver, kw):
+    """fused=True groups the vector operations of an iteration into a few passes (fused_phases.cu: 4 launches for
+    cgs!, 3 for cg_lanczos! / cr!, window + 3 for dqgmres! / diom!); every element update repeats the k* sequence it
+    replaces, so against fused=False: same iteration count and status, histories equal to dot-product rounding, and
+    far fewer launches."""
+    (Al, bl), (Ak, bk) = _problems(O)
+    A, b = (Al, bl) if solver in ("cg_lanczos", "cr") else (Ak, bk)
+    kw = dict(kw)
+    mem = kw.pop("memory", 0)
+    out = {}
+    for fused in (True, False):
+        ws = kb.krylov_workspace(solver, A.shape[0], A.shape[1], np.float64, memory=mem)
+        l0 = ws.launches
+        ws.solve(A, b, history=True, fused=fused, **kw)
+        out[fused] = (ws.x, ws.stats, ws.launches - l0)
+        ws.free()
+    (x1, s1, l1), (x0, s0, l0) = out[True], out[False]
+    assert s1.niter == s0.niter and s1.status == s0.status
+    assert np.allclose(s1.residuals, s0.residuals, rtol=1e-7 if solver != "cgs" else 1e-4, atol=1e-12 * s0.residuals[0])
+    assert np.linalg.norm(x1 - x0) <= 1e-8 * np.linalg.norm(x0)
+    assert l1 < 0.7 * l0, (l1, l0)
