@@ -141,4 +141,4 @@ def test_block_panel_kernels_use_fp64_tensor_cores():
     ents = _entries("block")
     dm = _demangle([e[0] for e in ents])
     for name, regs, spill in [(dm[n], r, s) for n, r, s in ents if "panel_mma_kernel<" in dm[n]]:
-        assert regs <= 128 and spill <= 32, (name, regs, spill)
+        assert regs <= 128 and spill <= 96, (name, regs, spill)      # p = 32 fused: 64 B of spill outside the DMMA chains
