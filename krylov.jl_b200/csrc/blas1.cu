@@ -332,8 +332,33 @@ void dist_check_alive(Ctx& c) {
                                     "workspace is dead (free the workspace on every rank and create it again)");
 }
 
+// cg! prologue for x0 = 0 and M = I (cg.jl:150-162): x = 0, r = b, p = r, gamma = <r, r> in ONE pass instead of
+// fill + copy + copy + dot (the per-solve fixed cost matters once 8 GPUs finish 100 iterations in 5 ms).
+template <class T>
+__global__ void __launch_bounds__(kBlock) cg_prologue_kernel(int n, const T* __restrict__ b, T* __restrict__ x, T* __restrict__ r,
+                                                             T* __restrict__ p, T* part, unsigned* ticket, T* out, DistComm* dc) {
+  __shared__ T sm[32];
+  T acc = T(0);
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const T v = b[i];
+    x[i] = T(0); r[i] = v; p[i] = v;
+    acc += v * v;
+  }
+  T mine[1] = {block_sum(acc, sm)}, tot[1];
+  if (grid_sum_last<T, 1>(mine, part, ticket, sm, tot) && threadIdx.x == 0) out[0] = dist_reduce(dc, tot[0]);
+}
+template <class T> T k_cg_prologue(Ctx& c, int n, const T* b, T* x, T* r, T* p) {
+  const int grid = n > 0 ? stream_grid(n, 4, 4) : 1;
+  cg_prologue_kernel<T><<<grid, kBlock, 0, c.stream>>>(n, b, x, r, p, (T*)c.partials, c.tickets, slot_ptr<T>(c, 0), c.dcomm);
+  KB_CUDA(cudaGetLastError());
+  c.launches++;
+  return read_slot<T>(c, 0);
+}
+
 #define INST(T)                                                                        \
   template T k_dot<T>(Ctx&, int, const T*, const T*);                                  \
+  template T k_cg_prologue<T>(Ctx&, int, const T*, T*, T*, T*);                        \
   template T k_nrm2<T>(Ctx&, int, const T*);                                           \
   template void k_dot2<T>(Ctx&, int, const T*, const T*, const T*, const T*, T*, T*);  \
   template void k_dot_dev<T>(Ctx&, int, const T*, const T*, int);                      \

@@ -36,6 +36,8 @@ struct CgState {
   T hist[kHist];
 };
 
+static_assert(sizeof(CgState<double>) % 8 == 0 && sizeof(CgState<float>) % 8 == 0, "CgState is copied as 8-byte words");
+
 template <class T>
 struct CgPeers {           // peers' vectors for the halo gather (DIST only)
   HaloMap halo;
@@ -345,7 +347,24 @@ struct CgPersistArgs {
   int n_interior;            // number of interior tiles = first halo position of tile_order
   int max_iters;
   int timed;                 // accumulate phase durations (CTA 0, %globaltimer) into the GridBar block
+  // Zero-copy report: when the launch ends, CTA 0 copies the scalar block into pinned HOST memory and then stores the
+  // launch's sequence number there.  The host polls that word instead of an event behind a D2H copy, so consecutive
+  // persistent launches sit back to back on the stream (a copy between two kernels costs two engine hand-offs).
+  CgState<T>* hsnap;
+  unsigned long long* hseq;
+  unsigned long long seq;
 };
+
+template <class T>
+__device__ __forceinline__ void cg_report_to_host(const CgPersistArgs<T>& a, const CgState<T>* st) {
+  if (blockIdx.x != 0 || threadIdx.x >= 32 || a.hsnap == nullptr) return;
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(st);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.hsnap);
+  for (int w = threadIdx.x; w < (int)(sizeof(CgState<T>) / 8); w += 32) dst[w] = __ldcg(&src[w]);
+  __threadfence_system();
+  __syncwarp();
+  if (threadIdx.x == 0) { *(volatile unsigned long long*)a.hseq = a.seq; __threadfence_system(); }
+}
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -412,7 +431,7 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPer
   __shared__ T sm[32];
   __shared__ unsigned sflag[2];
   volatile CgState<T>* vst = st;
-  if (vst->done) return;                       // uniform: st only changes inside the barriers below
+  if (vst->done) { cg_report_to_host<T>(a, st); return; }    // uniform: st only changes inside the barriers below
   TilePipe<T> P;
   P.init(A, smem);
   const int G = gridDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -545,6 +564,7 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPer
     }
   }
   if (warp == kConsumerWarps && lane == 0) tile_drain<T>(P, (unsigned)passes * (unsigned)cnt, ppos);
+  cg_report_to_host<T>(a, st);                 // st is final: every CTA left the loop after the same barrier
 }
 
 // Prologue of a row-partitioned solve in push mode: send the boundary entries of r_0 to the neighbours' halo
@@ -571,14 +591,15 @@ template <class T> void cg_dist_push_r(Workspace<T>& ws) {
 // ---------------------------------------------------------------------------
 // Everything the fused loops need besides the solver's vectors is allocated when the workspace is created
 // (ws_create) -- the in-place call allocates nothing (test/test_allocations.jl:54-57).
-constexpr size_t kOffGridBar = 1024, kOffPeerTab = 2048;     // layout of the 4 KB device / pinned blocks
+constexpr size_t kOffGridBar = 1024, kOffPeerTab = 2048, kOffHostSeq = 3072;     // layout of the 4 KB device / pinned blocks
 
 template <class T> void cg_fused_prepare(Workspace<T>& ws) {
   static_assert(sizeof(CgState<T>) <= kOffGridBar && sizeof(CgPeerTab<T>) <= kFusedBlockBytes - kOffPeerTab, "block layout");
   if (!ws.fused_state) {
     KB_CUDA(cudaMalloc(&ws.fused_state, kFusedBlockBytes));
     KB_CUDA(cudaMemset(ws.fused_state, 0, kFusedBlockBytes));
-    KB_CUDA(cudaHostAlloc(&ws.fused_host, kFusedBlockBytes, cudaHostAllocDefault));
+    KB_CUDA(cudaHostAlloc(&ws.fused_host, kFusedBlockBytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    memset(ws.fused_host, 0, kFusedBlockBytes);
   }
   if (!ws.p2) ws.p2 = dev_alloc<T>((size_t)ws.n);
   for (int i = 0; i < 2; i++)
@@ -657,7 +678,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   *hslot(0) = init;
   KB_CUDA(cudaMemcpyAsync(dst, hslot(0), sizeof(St), cudaMemcpyHostToDevice, c.stream));
   KB_CUDA(cudaMemsetAsync((char*)ws.fused_state + kOffGridBar, 0, sizeof(GridBar), c.stream));
-  c.sync();   // slot 0 is reused below as a read-back slot
+  // (no sync: the copy reads slot 0 in stream order before any kernel or read-back of this solve writes it)
 
   const bool jac = ws.mdiag_fused != nullptr;
   const bool single_step = (o.callback != nullptr) || (o.timemax < 1e300) || o.verbose > 0;
@@ -733,7 +754,7 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
     }
   }
 
-  int batch = o.batch > 0 ? o.batch : 16;
+  int batch = o.batch > 0 ? o.batch : (single_step ? 1 : 32);   // iterations per launch (persistent) / per host poll
   if (batch > kHist / 2) batch = kHist / 2;
   if (single_step) batch = 1;
 
@@ -803,15 +824,37 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
     tev.resize(3 * kTimedCount);
     for (auto& e : tev) KB_CUDA(cudaEventCreate(&e));
   }
+  // persistent launches report into pinned host memory (cg_report_to_host): poll the sequence word; every ~1000 polls
+  // make sure the stream is still alive so that a faulted kernel raises instead of hanging the host
+  unsigned long long* hseq = (unsigned long long*)((char*)ws.fused_host + kOffHostSeq);
+  unsigned long long expect[2] = {0, 0};
+  auto wait_report = [&](int slot) {
+    long spins = 0;
+    while (__atomic_load_n(&hseq[slot], __ATOMIC_ACQUIRE) != expect[slot]) {
+      if ((++spins & 1023) == 0) {
+        const cudaError_t q = cudaStreamQuery(c.stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) throw CudaError(std::string("persistent CG kernel failed: ") + cudaGetErrorString(q));
+        if (q == cudaSuccess && __atomic_load_n(&hseq[slot], __ATOMIC_ACQUIRE) != expect[slot])
+          throw std::runtime_error("persistent CG kernel finished without reporting its state");
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  };
   auto enqueue = [&](int slot) {
     if (persist) {
       DistComm* dcm = dist ? c.dcomm : nullptr;
       Csr<T> Acopy = A;
       T* partp = part;
+      pa.hsnap = hslot(slot);
+      pa.hseq = hseq + slot;
+      pa.seq = expect[slot] = ++ws.fused_seq;
       void* args[] = {(void*)&Acopy, (void*)&pa, (void*)&dst, (void*)&partp, (void*)&gbar, (void*)&dcm};
       KB_CUDA(cudaLaunchCooperativeKernel((const void*)kp, dim3(pgrid), dim3(kTileThreads), args, A.smem_bytes, c.stream));
       c.launches += 1;
       enq += batch;
+      return;                                   // the kernel reports into pinned host memory itself
     }
     for (int b = 0; !persist && b < batch; b++, enq++) {
       T* p_old = P[enq & 1];
@@ -838,7 +881,8 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
   enqueue(0);
   for (;;) {
     if (!single_step) enqueue(cur ^ 1);           // keep the GPU busy while the host inspects `cur`
-    KB_CUDA(cudaEventSynchronize(ev[cur]));
+    if (persist) wait_report(cur);
+    else KB_CUDA(cudaEventSynchronize(ev[cur]));
     last = *hslot(cur);
     for (int k = seen + 1; k <= last.iter; k++) {
       if (o.history) ws.stats.residuals.push_back((double)last.hist[k % kHist]);

@@ -131,7 +131,7 @@ template <class S> static S* state_buf(void*& dev, void*& host) {
   if (!dev) {
     KB_CUDA(cudaMalloc(&dev, kFusedBlockBytes));
     KB_CUDA(cudaMemset(dev, 0, kFusedBlockBytes));
-    KB_CUDA(cudaHostAlloc(&host, kFusedBlockBytes, cudaHostAllocDefault));
+    KB_CUDA(cudaHostAlloc(&host, kFusedBlockBytes, cudaHostAllocPortable | cudaHostAllocMapped));
   }
   static_assert(sizeof(S) <= 1024, "state block too large");
   return (S*)dev;

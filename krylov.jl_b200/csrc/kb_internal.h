@@ -53,6 +53,7 @@ void dev_free(void* p);
 // ---------------------------------------------------------------------------
 template <class T> T    k_dot(Ctx& c, int n, const T* x, const T* y);
 template <class T> T    k_nrm2(Ctx& c, int n, const T* x);
+template <class T> T    k_cg_prologue(Ctx& c, int n, const T* b, T* x, T* r, T* p);   // x = 0, r = p = b, returns <b, b>
 template <class T> void k_dot2(Ctx& c, int n, const T* a, const T* b, const T* u, const T* v, T* r1, T* r2);
 template <class T> void k_dot_dev(Ctx& c, int n, const T* x, const T* y, int slot);
 template <class T> void k_axpy(Ctx& c, int n, T s, const T* x, T* y);                 // y += s x
@@ -200,6 +201,7 @@ struct Workspace {
   void* fused_state = nullptr;         // device scalar block of the fused paths
   void* fused_host = nullptr;          // pinned mirror (2 slots)
   cudaEvent_t fused_ev[2] = {nullptr, nullptr};   // fused CG: one event per read-back slot
+  unsigned long long fused_seq = 0;               // persistent CG: sequence number of the last launch (host-polled report)
   T* bbuf = nullptr;                   // device copies of host b / c for the C ABI
   T* cbuf = nullptr;
   // row-partitioned (multi-GPU) state; world == 1 means single GPU
