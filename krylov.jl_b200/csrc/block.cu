@@ -129,8 +129,11 @@ __global__ void __launch_bounds__(kTileThreads, 3) spmm_tma_kernel(Csr<T> A, con
           for (int u = 0; u < RU; u++)
 #pragma unroll
             for (int d = 0; d < D; d++) {
-              const int idx = max(kb[u], min(kb[u] + kk + d, ke[u] - 1));      // an empty row reads a valid, ignored slot
-              xv[u][d] = __ldg(&X[(size_t)crow[idx] * P + c]);
+              const int idx = max(kb[u], min(kb[u] + kk + d, ke[u] - 1));
+              // an EMPTY row (also the rows past n of the last tile) has no slot of its own: whatever sits at
+              // `idx` in shared memory is not a column index -- gather row 0 of the panel instead (value ignored)
+              const int cc = crow[idx];
+              xv[u][d] = __ldg(&X[(size_t)(kb[u] < ke[u] ? cc : 0) * P + c]);
             }
           asm volatile("" ::: "memory");
 #pragma unroll
