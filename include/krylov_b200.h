@@ -102,7 +102,8 @@ int krylov_warm_start(void *ws, const void *x0, int n);
 int krylov_warm_start2(void *ws, const void *x0, const void *y0, int nx, int ny); /* -2 here */
 int krylov_workspace_free(void *ws); /* 0 | 1 if the handle is unknown (double free is safe) */
 
-/* Block solvers (krylov.h:250-285) are outside this library's path: create returns -2. */
+/* Block solvers (krylov.h:250-285): KRYLOV_BLOCK_GMRES is implemented (p <= 32, Float32 / Float64; the tall-skinny
+ * panel products of Float64 p = 8 / 16 / 32 run on the FP64 tensor cores); KRYLOV_BLOCK_MINRES answers -2. */
 int krylov_block_workspace_create(KrylovBlockSolverType solver, int m, int n, int p, KrylovDataType dtype,
                                   KrylovDeviceType device, const KrylovWorkspaceOptions *wopts, void **ws_out);
 int krylov_block_solve(void *ws, KrylovBlockMatvec matvec_A, KrylovBlockMatvec matvec_M, KrylovBlockMatvec matvec_N,
