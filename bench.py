@@ -5,8 +5,8 @@ Metric (BASELINE.json): CG iterations/s on the 3-D 7-point Poisson matrix
 get_div_grad(N,N,N), N = 215 (n = 9 938 375, nnz = 69 291 275), Float64, b = ones,
 and the achieved fraction of the HBM roofline.
 
-A "step" is one cg!(ws, A, b; atol=0, rtol=0, itmax=ITERS) solve = ITERS fused
-iterations (2 kernel launches each).  `value` is timed with CUDA events on the
+A "step" is one cg!(ws, A, b; atol=0, rtol=0, itmax=ITERS) solve = ITERS = 200 fused
+iterations (one persistent cooperative launch per 32 iterations).  `value` is timed with CUDA events on the
 workspace's own stream with A and b resident in HBM; `e2e` times the same solve
 through the reference-facing C ABI (krylov_solve / krylov_get_x) with pinned HOST
 buffers for b and x.  The matrix (871 MB) is far larger than L2 (126 MB), so
@@ -33,8 +33,8 @@ import numpy as np  # noqa: E402
 
 WORKLOADS = {
     # name: (N, iterations per step)
-    "poisson215": (215, 100),     # BASELINE config 2  (n ~ 1e7)
-    "poisson464": (464, 50),      # BASELINE config 5  (n ~ 1e8)
+    "poisson215": (215, 200),     # BASELINE config 2  (n ~ 1e7); SURVEY.md 8(d): timing run atol = rtol = 0, itmax = 200
+    "poisson464": (464, 100),     # BASELINE config 5  (n ~ 1e8); SURVEY.md 8(d): 100 iterations at 1, 2, 4, 8 GPUs
     "poisson32": (32, 79),        # BASELINE config 1  (CPU-runnable reference case)
 }
 FALLBACK_HBM_GBS = 6650.0         # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
@@ -414,7 +414,7 @@ def main():
     kernels = dict(phase_a=dict(ms=k1_ms, bytes=B_k1, GBs=B_k1 / (k1_ms * 1e-3) / 1e9 if k1_ms else None),
                    phase_b=dict(ms=k2_ms, bytes=B_k2, GBs=B_k2 / (k2_ms * 1e-3) / 1e9 if k2_ms else None),
                    timed_iterations=timed, share_a=k1_ms / (k1_ms + k2_ms) if k1_ms else None,
-                   kernel="cg_persist (one cooperative launch per 16 iterations)")
+                   kernel="cg_persist (one cooperative launch per 32 iterations)")
     # history of the same solve for the parity block (not timed)
     ws.solve(None, b, history=True, **solve_kw)
     gpu_hist = list(ws.stats.residuals)

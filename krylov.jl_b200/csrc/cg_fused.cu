@@ -311,8 +311,7 @@ __device__ __forceinline__ bool grid_reduce_barrier(GridBar* gb, T v, T* part, T
       fin(tot);
       __syncwarp();
       if (threadIdx.x == 0) {
-        gb->count = 0u;
-        __threadfence();
+        gb->count = 0u;                      // ordered before the release below (st.release covers this thread's prior writes)
         st_release_gpu_u32(&gb->gen, g + 1u);
       }
     }

@@ -290,11 +290,18 @@ class KrylovWorkspace:
         self._op_id = other._op_id
 
     def _set_diag(self, which: int, d):
+        attached = getattr(self, "_precond_attached", None)
+        if attached is None:
+            attached = self._precond_attached = [False, False]
         if d is None:
+            if not attached[which]:             # nothing to detach: no library call on the per-solve path
+                return
             lib().krylov_b200_set_preconditioner_diag(self._h, which, None, 0)
             if not isinstance(self, BlockGmresWorkspace):
                 lib().krylov_b200_set_preconditioner_blockdiag(self._h, which, 0, None, 0)
+            attached[which] = False
             return
+        attached[which] = True
         if getattr(d, "ndim", 1) == 3:      # block-Jacobi: (nblocks, bs, bs) dense diagonal blocks
             nb, bs, bs2 = d.shape
             if bs != bs2 or nb != (self.n + bs - 1) // bs:

@@ -109,7 +109,10 @@ def test_persistent_cg_register_budget_and_coherent_loads():
         assert regs <= 72 and spill == 0, (name, regs, spill)
     for mode in (0, 1):
         body = _sass_of("cg_fused", f"cg_persistIdLi{mode}ELi3ELi8")
-        assert not any("LDG.E.64.CONSTANT" in l for l in body), "a Float64 vector is read through the read-only path"
+        # row-partitioned variant: the communicator's constants (mailbox pointer, spin budget; dist.cuh) are 64-bit
+        # read-only loads, two per barrier -- nothing else may be
+        allowed = 0 if mode == 0 else 4
+        assert sum("LDG.E.64.CONSTANT" in l for l in body) <= allowed, "a Float64 vector is read through the read-only path"
 
 
 def test_gather_batches_keep_loads_in_flight():
