@@ -753,7 +753,8 @@ void cg_fused_loop(Workspace<T>& ws, const Csr<T>& A, const SolveOpts& o, T gamm
     }
   }
 
-  int batch = o.batch > 0 ? o.batch : (single_step ? 1 : 32);   // iterations per launch (persistent) / per host poll
+  static const char* ebatch = getenv("KB200_BATCH");            // A/B measurements of the per-launch fixed cost
+  int batch = o.batch > 0 ? o.batch : (single_step ? 1 : (ebatch && atoi(ebatch) > 0 ? atoi(ebatch) : 32));   // iterations per launch / host poll
   if (batch > kHist / 2) batch = kHist / 2;
   if (single_step) batch = 1;
 
