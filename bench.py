@@ -40,6 +40,12 @@ WORKLOADS = {
 FALLBACK_HBM_GBS = 6650.0         # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
+def workload_name(N, iters):
+    """The SAME string in both arms (ours / --impl reference) and at every N: the driver compares `config.workload`."""
+    return (f"cg! on get_div_grad({N},{N},{N}) Float64 CSR (n = {N ** 3}, nnz = {7 * N ** 3 - 6 * N ** 2}), b = ones, "
+            f"atol = rtol = 0, itmax = {iters} per step")
+
+
 def algorithmic_bytes_cg(n, nnz, v=8, i=4):
     """B_cg = nnz(v+i) + (n+1)i + 9nv per fused CG iteration."""
     return nnz * (v + i) + (n + 1) * i + 9 * n * v
@@ -273,8 +279,9 @@ def extra_records(kb, torch, dev, peak):
                     value=its, unit="it/s", launches_per_iteration=launches / niter, matrix_generate_s=round(gen_s, 2),
                     roofline=dict(bound="hbm", bytes_per_iteration=B, achieved=B * its / 1e9, peak=peak, unit="GB/s",
                                   frac=B * its / 1e9 / peak,
-                                  note="2 x matrix + 20 n v; the x gather of a RANDOM matrix is L2-sector bound "
-                                       "(profiles/README.md)")))
+                                  note="2 x matrix + 20 n v; the x gather of a uniformly RANDOM matrix is bound by the L1 "
+                                       "sector rate (one 32-B sector per nonzero: 118 M sectors per SpMV, l1tex 84 % of "
+                                       "peak, DRAM 30 %): profiles/r2_ncu_bicgstab_spmv.txt")))
     del rp, ci, va, b
     torch.cuda.empty_cache()
     return out
@@ -335,9 +342,10 @@ def run_reference(args):
     line = dict(metric="CG iterations/s", value=v, unit="it/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * total_t / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
                 dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload=f"cg! on get_div_grad({N},{N},{N}) Float64 CSR, b=ones, fixed iterations", n=n, nnz=nnz,
-                            note="Julia absent: CPU restatement (oracle port) of src/cg.jl:195-268, OpenMP; thread count = "
-                                 "fastest of a 2-iteration sweep", thread_sweep_it_per_s=sweep),
+                config=dict(workload=workload_name(N, iters), n=n, nnz=nnz, iters_per_step=iters,
+                            implementation="Julia absent: CPU restatement (oracle port) of src/cg.jl:195-268, OpenMP; thread count = "
+                                           "fastest of a 2-iteration sweep; each step is a bounded sample of the workload's iterations",
+                            thread_sweep_it_per_s=sweep),
                 cpu_baseline=dict(leg, value=v),
                 e2e=dict(value=v, unit="it/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
@@ -364,7 +372,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from krylov_b200 import dist
-        return dist.bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler, parity_block, golden_parity)
+        return dist.bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler, parity_block, golden_parity, workload_name)
     if kb.device_count() < 1:
         raise SystemExit("bench.py needs a B200: libkrylov_b200 has no CPU path")
     torch.cuda.set_device(local)
@@ -449,8 +457,8 @@ def main():
     line = dict(metric="CG iterations/s", value=value, unit="it/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
                 data="synthetic",
-                config=dict(workload=f"cg! fused (persistent cooperative kernel) on get_div_grad({N},{N},{N}) Float64 int32-CSR, b=ones, "
-                                     f"atol=rtol=0, itmax={iters} per step", n=n, nnz=nnz, iters_per_step=iters,
+                config=dict(workload=workload_name(N, iters), n=n, nnz=nnz, iters_per_step=iters,
+                            implementation="cg! fused: persistent cooperative kernel (32 iterations per launch), int32 CSR resident in HBM",
                             l2="inputs larger than L2 (matrix 0.87 GB vs 126 MB): no flush needed",
                             matrix_upload_s=round(upload_s, 3), matrix_generate_s=round(gen_s, 3)),
                 roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,

@@ -279,7 +279,7 @@ def _run_workload(N, iters, steps, warmup, rank, world, local, dev, torch, dist,
                             note="rank 0, measured inside cg_persist (%globaltimer), grid barrier + cross-GPU all-reduce included"))
 
 
-def bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler, parity_block=None, golden_parity=None):
+def bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler, parity_block=None, golden_parity=None, workload_name=None):
     import torch
     import torch.distributed as dist
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
@@ -317,8 +317,8 @@ def bench_main(args, WORKLOADS, algorithmic_bytes_cg, hbm_peak, ClockSampler, pa
         line = dict(metric="CG iterations/s", value=value, unit="it/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
                     data="synthetic",
-                    config=dict(workload=f"cg! fused (persistent cooperative kernel), get_div_grad({N},{N},{N}) Float64 int32-CSR "
-                                         f"row-partitioned in z-slabs over {world} GPUs, b=ones, atol=rtol=0, itmax={iters} per step",
+                    config=dict(workload=workload_name(N, iters) if workload_name else f"cg! on get_div_grad({N},{N},{N})",
+                                implementation=f"cg! fused: persistent cooperative kernel, int32 CSR row-partitioned in z-slabs over {world} GPUs",
                                 n=n, nnz=nnz, iters_per_step=iters,
                                 parallelism=f"rows/{world}: halo staged over NVLink P2P inside the kernel + in-kernel all-reduce",
                                 l2="per-rank matrix slab %.0f MB" % (nnz * 12 / world / 1e6), status=res["status"]),
