@@ -287,8 +287,21 @@ __device__ __forceinline__ float ld_sys(const float* p) {
 // Grid-wide barrier that also sums one value per thread over the whole grid.  `fin(total)` runs in warp 0 of the
 // LAST CTA to arrive (total valid in every lane of that warp) before anyone is released.  Returns false (in every
 // thread) if the wait timed out: the caller must leave the kernel.
+// The iteration scalars every thread needs after a barrier, broadcast through shared memory: ONE thread per CTA
+// reads them from the device block (four independent loads, one L2 round trip) instead of every thread doing four or
+// five dependent volatile reads per iteration.
+template <class T> struct CgScal { T alpha, beta; int iter, done; };
+template <class T>
+__device__ __forceinline__ void cg_load_scal(const CgState<T>* st, CgScal<T>* sc) {
+  const volatile CgState<T>* v = st;
+  const T al = v->alpha, be = v->beta;
+  const int it = v->iter, dn = v->done;
+  sc->alpha = al; sc->beta = be; sc->iter = it; sc->done = dn;
+}
+
 template <class T, class Fin>
-__device__ __forceinline__ bool grid_reduce_barrier(GridBar* gb, T v, T* part, T* sm, unsigned* sflag, Fin fin) {
+__device__ __forceinline__ bool grid_reduce_barrier(GridBar* gb, T v, T* part, T* sm, unsigned* sflag, const CgState<T>* st,
+                                                    CgScal<T>* sc, Fin fin) {
   const T mine = block_sum(v, sm);
   if (threadIdx.x == 0) {
     const unsigned g = *(volatile unsigned*)&gb->gen;      // read BEFORE arriving
@@ -303,14 +316,17 @@ __device__ __forceinline__ bool grid_reduce_barrier(GridBar* gb, T v, T* part, T
   const unsigned g = sflag[1];
   bool ok = true;
   if (last) {
-    __threadfence();
-    T acc = T(0);
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) acc += __ldcg(&part[i]);
-    const T tot = block_sum(acc, sm);       // valid in every lane of warp 0
     if (threadIdx.x < 32) {
+      // warp 0 alone re-reduces the partials (fixed order: lane-strided, then the shuffle tree): no CTA-wide
+      // synchronisation on the critical path of the release
+      __threadfence();
+      T acc = T(0);
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) acc += __ldcg(&part[i]);
+      const T tot = warp_sum(acc);          // valid in every lane
       fin(tot);
       __syncwarp();
       if (threadIdx.x == 0) {
+        cg_load_scal<T>(st, sc);             // after this thread's own finalize
         gb->count = 0u;                      // ordered before the release below (st.release covers this thread's prior writes)
         st_release_gpu_u32(&gb->gen, g + 1u);
       }
@@ -320,6 +336,7 @@ __device__ __forceinline__ bool grid_reduce_barrier(GridBar* gb, T v, T* part, T
     while (ld_acquire_gpu_u32(&gb->gen) == g) {
       if (clock64() - t0 > 120000000000LL) { sflag[0] = 2; break; }     // ~1 minute: the grid is wedged
     }
+    cg_load_scal<T>(st, sc);
   }
   __syncthreads();
   if (sflag[0] == 2) ok = false;
@@ -429,8 +446,10 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPer
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ T sm[32];
   __shared__ unsigned sflag[2];
+  __shared__ CgScal<T> sc;
   volatile CgState<T>* vst = st;
   if (vst->done) { cg_report_to_host<T>(a, st); return; }    // uniform: st only changes inside the barriers below
+  if (threadIdx.x == 0) cg_load_scal<T>(st, &sc);            // published by the __syncthreads of P.init below
   TilePipe<T> P;
   P.init(A, smem);
   const int G = gridDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -447,8 +466,8 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPer
   int passes = 0;
   const int n = A.n;
   for (int k = 0; k < a.max_iters; k++) {
-    const int iter = vst->iter;
-    const T beta = vst->beta, alpha_prev = vst->alpha;
+    const int iter = sc.iter;
+    const T beta = sc.beta, alpha_prev = sc.alpha;
     const bool xup = iter > 0;                 // x += alpha_{k-1} p_{k-1} rides in phase A (cg.jl:239)
     T* p_old = (iter & 1) ? a.P1 : a.P0;
     T* p_new = (iter & 1) ? a.P0 : a.P1;
@@ -503,18 +522,18 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPer
       }
     }
     passes = k + 1;
-    bool ok = grid_reduce_barrier<T>(gb, dacc, part, sm, sflag, [&](T tot) {
+    bool ok = grid_reduce_barrier<T>(gb, dacc, part, sm, sflag, st, &sc, [&](T tot) {
       if (MODE == kDist) {
         tot = (T)dist_allreduce_sum_warp<T>(dc, (double)tot);
         if (*(volatile int*)&dc->error) { if (lane == 0) { st->comm_error = 1; st->done = 1; } return; }
       }
       if (lane == 0) cg_k1_finalize(st, tot);
     });
-    if (!ok || vst->done) break;
+    if (!ok || sc.done) break;
     if (timing) t1 = globaltimer_ns();
     // ------------------------------ phase B (= K2) ------------------------------
     {
-      const T alpha = vst->alpha, nalpha = -alpha;
+      const T alpha = sc.alpha, nalpha = -alpha;
       T* r = a.r;
       const T* Ap = a.Ap;
       const T* mdiag = a.mdiag;
@@ -545,7 +564,7 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPer
         r[i] = rn;
         acc += rn * (MODE == kJacobi ? mul_rn(__ldg(&mdiag[i]), rn) : rn);
       }
-      ok = grid_reduce_barrier<T>(gb, acc, part, sm, sflag, [&](T tot) {
+      ok = grid_reduce_barrier<T>(gb, acc, part, sm, sflag, st, &sc, [&](T tot) {
         if (MODE == kDist) {
           tot = (T)dist_allreduce_sum_warp<T>(dc, (double)tot);
           if (*(volatile int*)&dc->error) { if (lane == 0) { st->comm_error = 1; st->done = 1; } return; }
@@ -559,7 +578,7 @@ __global__ void __launch_bounds__(kTileThreads, MINB) cg_persist(Csr<T> A, CgPer
         const unsigned long long t2 = globaltimer_ns();
         gb->ns_a += t1 - t0; gb->ns_b += t2 - t1; gb->timed_iters += 1;
       }
-      if (!ok || vst->done) break;
+      if (!ok || sc.done) break;
     }
   }
   if (warp == kConsumerWarps && lane == 0) tile_drain<T>(P, (unsigned)passes * (unsigned)cnt, ppos);
