@@ -77,28 +77,28 @@ void cgs_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const T* c_in, c
       iter = iter + 1;
       rNorm = std::sqrt(rr);
     } else {
-    if (!NisI) op_apply(c, N, p, y, ldiv);
-    op_apply(c, A, y, t);
-    if (!MisI) op_apply(c, M, t, v, ldiv);
-    const T sigma = k_dot<T>(c, n, cvec, v);
-    alpha = rho / sigma;
-    k_copy<T>(c, n, q, u);
-    k_axpy<T>(c, n, -alpha, v, q);
-    k_axpy<T>(c, n, T(1), q, u);
-    if (!NisI) op_apply(c, N, u, z, ldiv);
-    k_axpy<T>(c, n, alpha, z, x);
-    op_apply(c, A, z, s);
-    if (!MisI) op_apply(c, M, s, w, ldiv);
-    k_axpy<T>(c, n, -alpha, w, r);
-    rho_next = k_dot<T>(c, n, cvec, r);
-    const T beta = rho_next / rho;
-    k_copy<T>(c, n, u, r);
-    k_axpy<T>(c, n, beta, q, u);
-    k_axpby<T>(c, n, T(1), q, beta, p);
-    k_axpby<T>(c, n, T(1), u, beta, p);
-    rho = rho_next;
-    iter = iter + 1;
-    rNorm = k_nrm2<T>(c, n, r);
+      if (!NisI) op_apply(c, N, p, y, ldiv);
+      op_apply(c, A, y, t);
+      if (!MisI) op_apply(c, M, t, v, ldiv);
+      const T sigma = k_dot<T>(c, n, cvec, v);
+      alpha = rho / sigma;
+      k_copy<T>(c, n, q, u);
+      k_axpy<T>(c, n, -alpha, v, q);
+      k_axpy<T>(c, n, T(1), q, u);
+      if (!NisI) op_apply(c, N, u, z, ldiv);
+      k_axpy<T>(c, n, alpha, z, x);
+      op_apply(c, A, z, s);
+      if (!MisI) op_apply(c, M, s, w, ldiv);
+      k_axpy<T>(c, n, -alpha, w, r);
+      rho_next = k_dot<T>(c, n, cvec, r);
+      const T beta = rho_next / rho;
+      k_copy<T>(c, n, u, r);
+      k_axpy<T>(c, n, beta, q, u);
+      k_axpby<T>(c, n, T(1), q, beta, p);
+      k_axpby<T>(c, n, T(1), u, beta, p);
+      rho = rho_next;
+      iter = iter + 1;
+      rNorm = k_nrm2<T>(c, n, r);
     }
     if (history) stats.residuals.push_back(rNorm);
     const bool resid_decrease_mach = (rNorm + T(1) <= T(1));
@@ -185,10 +185,10 @@ void cg_lanczos_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const Lin
     if (fusedL) {
       beta = lanczos_fused_recur<T>(ws, delta, beta, iter > 0);
     } else {
-    k_axpy<T>(c, n, -delta, Mv, Mv_next);
-    if (iter > 0) {
-      k_axpy<T>(c, n, -beta, Mv_prev, Mv_next);
-      k_copy<T>(c, n, Mv_prev, Mv);
+      k_axpy<T>(c, n, -delta, Mv, Mv_next);
+      if (iter > 0) {
+        k_axpy<T>(c, n, -beta, Mv_prev, Mv_next);
+        k_copy<T>(c, n, Mv_prev, Mv);
     }
     k_copy<T>(c, n, Mv, Mv_next);
     if (!MisI) op_apply(c, M, Mv, v, ldiv);
@@ -530,13 +530,13 @@ static void truncated_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, con
       fused_orth_chain<T>(ws, *A.csr, z, w, vecs, cnt, hbuf, &Haux);
       for (int i = lo; i <= iter; i++) H[iter - i] = hbuf[i - lo];
     } else {
-    if (!NisI) op_apply(cx, N, V[pos - 1], z, ldiv);
-    op_apply(cx, A, z, t);
-    if (!MisI) op_apply(cx, M, t, w, ldiv);
-    for (int i = lo; i <= iter; i++) {          // incomplete orthogonalization
-      const int ipos = (i - 1) % mem + 1, diag = iter - i + 1;
-      H[diag - 1] = k_dot<T>(cx, n, w, V[ipos - 1]);
-      k_axpy<T>(cx, n, -H[diag - 1], V[ipos - 1], w);
+      if (!NisI) op_apply(cx, N, V[pos - 1], z, ldiv);
+      op_apply(cx, A, z, t);
+      if (!MisI) op_apply(cx, M, t, w, ldiv);
+      for (int i = lo; i <= iter; i++) {          // incomplete orthogonalization
+        const int ipos = (i - 1) % mem + 1, diag = iter - i + 1;
+        H[diag - 1] = k_dot<T>(cx, n, w, V[ipos - 1]);
+        k_axpy<T>(cx, n, -H[diag - 1], V[ipos - 1], w);
     }
     if (reorth) {
       for (int i = lo; i <= iter; i++) {
@@ -597,9 +597,9 @@ static void truncated_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, con
       // the whole direction update + x update in one pass per 8 stack vectors (trunc_fused_direction)
       trunc_fused_direction<T>(ws, P[ppos - 1], ndir, dvec, dcoef, z, H[0], step);
     } else {
-    k_axpy<T>(cx, n, T(1), z, P[ppos - 1]);
-    k_scal<T>(cx, n, T(1) / H[0], P[ppos - 1]);   // kdiv!(n, P[pos], H[1])
-    k_axpy<T>(cx, n, step, P[ppos - 1], x);
+      k_axpy<T>(cx, n, T(1), z, P[ppos - 1]);
+      k_scal<T>(cx, n, T(1) / H[0], P[ppos - 1]);   // kdiv!(n, P[pos], H[1])
+      k_axpy<T>(cx, n, step, P[ppos - 1], x);
     }
     if (history) stats.residuals.push_back(rNorm);
     const bool resid_decrease_mach = (rNorm + T(1) <= T(1));
@@ -811,15 +811,15 @@ void cr_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
       xNorm = std::sqrt(xx); rNorm = std::sqrt(rNorm2); ArNorm = std::sqrt(ArAr);
       if (history) { stats.residuals.push_back(rNorm); stats.Aresiduals.push_back(ArNorm); }
     } else {
-    k_axpy<T>(c, n, alpha, p, x);
-    xNorm = k_nrm2<T>(c, n, x);
-    if (radius > 0 && std::fabs(xNorm - radius) <= sqeps * std::max(std::fabs(xNorm), std::fabs(radius))) on_boundary = true;   // xNorm ≈ radius
-    k_axpy<T>(c, n, -alpha, Mq, r);
-    if (MisI) { rNorm2 = k_dot<T>(c, n, r, r); rNorm = std::sqrt(rNorm2); }
-    else {
-      const T omega = std::sqrt(alpha) * std::sqrt(rho);
-      rNorm = std::sqrt(std::fabs(rNorm + omega)) * std::sqrt(std::fabs(rNorm - omega));
-      rNorm2 = rNorm * rNorm;
+      k_axpy<T>(c, n, alpha, p, x);
+      xNorm = k_nrm2<T>(c, n, x);
+      if (radius > 0 && std::fabs(xNorm - radius) <= sqeps * std::max(std::fabs(xNorm), std::fabs(radius))) on_boundary = true;   // xNorm ≈ radius
+      k_axpy<T>(c, n, -alpha, Mq, r);
+      if (MisI) { rNorm2 = k_dot<T>(c, n, r, r); rNorm = std::sqrt(rNorm2); }
+      else {
+        const T omega = std::sqrt(alpha) * std::sqrt(rho);
+        rNorm = std::sqrt(std::fabs(rNorm + omega)) * std::sqrt(std::fabs(rNorm - omega));
+        rNorm2 = rNorm * rNorm;
     }
     if (history) stats.residuals.push_back(rNorm);
     op_apply(c, A, r, Ar);
@@ -844,8 +844,8 @@ void cr_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
     const T beta = rho / rhobar;
     if (fusedC) { qq = cr_fused_directions<T>(ws, beta); have_qq = true; }   // p, q updates + ||q||^2 for the next alpha
     else {
-    k_axpby<T>(c, n, T(1), r, beta, p);
-    k_axpby<T>(c, n, T(1), Ar, beta, q);
+      k_axpby<T>(c, n, T(1), r, beta, p);
+      k_axpby<T>(c, n, T(1), Ar, beta, q);
     }
     pNorm2 = rNorm2 + 2 * beta * pr - 2 * beta * alpha * pAp + beta * beta * pNorm2;
     if (pNorm2 > sqeps) pNorm = std::sqrt(pNorm2);

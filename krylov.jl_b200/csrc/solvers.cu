@@ -137,17 +137,17 @@ void cg_solve(Workspace<T>& ws, const LinOp<T>& A, const T* b, const LinOp<T>& M
   if (!warm_start && MisI && ws.dist.npush == 0) {
     gamma = k_cg_prologue<T>(c, n, b, x, r, ws.p);          // x = 0, r = b, p = z = r, gamma = <r, z> in one pass
   } else {
-  k_fill<T>(c, n, x, T(0));
-  if (warm_start) {
-    op_apply(c, A, dx, r);
-    k_axpby<T>(c, n, T(1), b, T(-1), r);
-  } else {
-    k_copy<T>(c, n, r, b);
-  }
-  cg_dist_push_r<T>(ws);                                    // row-partitioned push mode: neighbours' halo copy of r_0
-  if (!MisI) op_apply(c, M, r, z, ldiv);
-  k_copy<T>(c, n, ws.p, z);
-  gamma = k_dot<T>(c, n, r, z);
+    k_fill<T>(c, n, x, T(0));
+    if (warm_start) {
+      op_apply(c, A, dx, r);
+      k_axpby<T>(c, n, T(1), b, T(-1), r);
+    } else {
+      k_copy<T>(c, n, r, b);
+    }
+    cg_dist_push_r<T>(ws);                                  // row-partitioned push mode: neighbours' halo copy of r_0
+    if (!MisI) op_apply(c, M, r, z, ldiv);
+    k_copy<T>(c, n, ws.p, z);
+    gamma = k_dot<T>(c, n, r, z);
   }
   if (!(gamma >= 0)) throw std::runtime_error("The linear operator `A` or the preconditioner `M` is not symmetric positive definite.");
   T rNorm = std::sqrt(gamma);
