@@ -140,6 +140,41 @@ struct B200Diagonal{T<:BlasT}
 end
 Base.size(D::B200Diagonal) = (D.d.n, D.d.n)
 Base.eltype(::B200Diagonal{T}) where T = T
+# M = B200BlockDiagonal(bs, blocks): block-Jacobi, ceil(n / bs) dense bs x bs row-major blocks of the operator the
+# solver applies (P^-1 with ldiv = false); cg! runs it inside the persistent fused kernel (include/krylov_b200.h)
+struct B200BlockDiagonal{T<:BlasT}
+  bs::Int
+  blocks::B200Vector{T}
+  n::Int
+end
+Base.size(D::B200BlockDiagonal) = (D.n, D.n)
+Base.eltype(::B200BlockDiagonal{T}) where T = T
+
+# ---- dense n x p block of right-hand sides / solutions resident in HBM (column-major, like Matrix) --------------
+mutable struct B200Matrix{T<:BlasT} <: AbstractMatrix{T}
+  ptr::Ptr{Cvoid}
+  n::Int
+  p::Int
+  function B200Matrix{T}(::UndefInitializer, n::Integer, p::Integer) where T
+    q = n * p == 0 ? C_NULL : ccall((:kb200_alloc, lib), Ptr{Cvoid}, (Clonglong,), n * p * sizeof(T))
+    v = new{T}(q, n, p)
+    finalizer(x -> (x.ptr != C_NULL && ccall((:kb200_free, lib), Cint, (Ptr{Cvoid},), x.ptr); x.ptr = C_NULL), v)
+    v
+  end
+end
+function B200Matrix(h::Matrix{T}) where T<:BlasT
+  v = B200Matrix{T}(undef, size(h)...)
+  check(ccall((:kb200_h2d, lib), Cint, (Ptr{Cvoid}, Ptr{T}, Clonglong), v.ptr, h, sizeof(h)))
+  v
+end
+Base.size(v::B200Matrix) = (v.n, v.p)
+Base.similar(v::B200Matrix{T}) where T = B200Matrix{T}(undef, v.n, v.p)
+Base.getindex(v::B200Matrix, i::Int, j::Int) = error("scalar indexing of a B200Matrix is disabled")
+function Base.Matrix(v::B200Matrix{T}) where T
+  h = Matrix{T}(undef, v.n, v.p)
+  check(ccall((:kb200_d2h, lib), Cint, (Ptr{T}, Ptr{Cvoid}, Clonglong), h, v.ptr, sizeof(h)))
+  h
+end
 
 # ---- solver level: one C call per solve (fused kernels) ------------------------------------------------
 # The workspace keeps Krylov.jl's type (CgWorkspace{T,T,B200Vector{T}}) for its stats and public fields; the
@@ -165,6 +200,7 @@ end
 mutable struct Handle
   ptr::Ptr{Cvoid}
   op::Ptr{Cvoid}          # CSR object currently attached
+  block::Bool             # krylov_block_* handle (block_gmres!)
 end
 const HANDLES = IdDict{Any,Handle}()
 function handle_for(method::Symbol, ws, A::B200CSR{T}, memory::Int, window::Int) where T
@@ -175,7 +211,7 @@ function handle_for(method::Symbol, ws, A::B200CSR{T}, memory::Int, window::Int)
     rc = ccall((:krylov_workspace_create, lib), Cint, (Cint, Cint, Cint, Cint, Cint, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
                SOLVER_ID[method], A.m, A.n, dtype_id(T), 1, wo, out)
     rc == 0 || error("krylov_workspace_create -> $rc: " * unsafe_string(ccall((:krylov_b200_last_error, lib), Cstring, ())))
-    h = Handle(out[], C_NULL)
+    h = Handle(out[], C_NULL, false)
     finalizer(x -> (x.ptr != C_NULL && ccall((:krylov_workspace_free, lib), Cint, (Ptr{Cvoid},), x.ptr); x.ptr = C_NULL), h)
     HANDLES[ws] = h
   end
@@ -194,10 +230,17 @@ function _cb_tramp(_c_ws::Ptr{Cvoid}, user::Ptr{Cvoid})::Cint
   Cint(r)
 end
 
-set_precond!(h::Handle, which::Int, ::UniformScaling) =
+function set_precond!(h::Handle, which::Int, ::UniformScaling)
   check(ccall((:krylov_b200_set_preconditioner_diag, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint), h.ptr, which, C_NULL, 0))
+  h.block || check(ccall((:krylov_b200_set_preconditioner_blockdiag, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Cint), h.ptr, which, 0, C_NULL, 0))
+  nothing
+end
 set_precond!(h::Handle, which::Int, D::B200Diagonal) =
   check(ccall((:krylov_b200_set_preconditioner_diag, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint), h.ptr, which, D.d.ptr, 1))
+function set_precond!(h::Handle, which::Int, D::B200BlockDiagonal)
+  check(ccall((:krylov_b200_set_preconditioner_diag, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint), h.ptr, which, C_NULL, 0))
+  check(ccall((:krylov_b200_set_preconditioner_blockdiag, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Cint), h.ptr, which, D.bs, D.blocks.ptr, 1))
+end
 set_precond!(::Handle, ::Int, P) = error("libkrylov_b200: preconditioners must be I or a B200Diagonal (got $(typeof(P))); " *
                                          "any other operator runs through the primitive overloads (generic Krylov.jl method)")
 
@@ -284,5 +327,61 @@ Krylov.minres!(ws::Krylov.MinresWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::
   fused_solve!(:minres, ws, A, b; window = length(ws.err_vec), kw...)
 Krylov.minres!(ws::Krylov.MinresWorkspace{T,T,B200Vector{T}}, A::B200CSR{T}, b::B200Vector{T}, x0::B200Vector{T}; kw...) where T =
   fused_solve!(:minres, ws, A, b, x0; window = length(ws.err_vec), kw...)
+
+# ---- block_gmres! (src/block_gmres.jl:78-110; C ABI krylov.h:250-285): one krylov_block_solve per solve ------------------
+# B, X, X0 are column-major n x p device matrices; the library keeps row-major panels internally and runs the
+# tall-skinny products of Float64 p = 8 / 16 / 32 on the FP64 tensor cores.
+function block_handle_for(ws, A::B200CSR{T}, p::Int, memory::Int) where T
+  h = get(HANDLES, ws, nothing)
+  if h === nothing
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    wo = Ref((Cint(memory), Cint(0)))
+    rc = ccall((:krylov_block_workspace_create, lib), Cint, (Cint, Cint, Cint, Cint, Cint, Cint, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
+               0, A.m, A.n, p, dtype_id(T), 1, wo, out)             # KRYLOV_BLOCK_GMRES = 0, KRYLOV_CUDA = 1
+    rc == 0 || error("krylov_block_workspace_create -> $rc: " * unsafe_string(ccall((:krylov_b200_last_error, lib), Cstring, ())))
+    h = Handle(out[], C_NULL, true)
+    finalizer(x -> (x.ptr != C_NULL && ccall((:krylov_block_workspace_free, lib), Cint, (Ptr{Cvoid},), x.ptr); x.ptr = C_NULL), h)
+    HANDLES[ws] = h
+  end
+  if h.op != A.handle
+    check(ccall((:krylov_b200_attach_csr, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h.ptr, A.handle))
+    h.op = A.handle
+  end
+  h
+end
+
+function Krylov.block_gmres!(ws::Krylov.BlockGmresWorkspace{T,T,B200Vector{T},B200Matrix{T}}, A::B200CSR{T}, B::B200Matrix{T};
+                             M = I, N = I, ldiv::Bool = false, restart::Bool = false, reorthogonalization::Bool = false,
+                             atol::T = √eps(T), rtol::T = √eps(T), itmax::Int = 0, timemax::Float64 = Inf, verbose::Int = 0,
+                             history::Bool = false, callback = workspace -> false, iostream::IO = stdout) where T
+  A.m == A.n || error("System must be square")
+  size(B, 1) == A.n || error("Inconsistent problem size")
+  p = size(B, 2)
+  h = block_handle_for(ws, A, p, length(ws.V))
+  set_precond!(h, 0, M)
+  set_precond!(h, 1, N)
+  user = Ref{Any}((callback, ws))
+  cb = @cfunction(_cb_tramp, Cint, (Ptr{Cvoid}, Ptr{Cvoid}))
+  ext = Ref(CExt(history, ldiv, NaN, NaN, 1, 0, cb, Base.unsafe_convert(Ptr{Cvoid}, user), 0, 0, NaN))
+  o = Ref(COpts(atol, rtol, itmax, verbose, 0.0, NaN, NaN, isinf(timemax) ? NaN : timemax, 0.0, restart, reorthogonalization, false))
+  GC.@preserve user ext o begin
+    check(ccall((:krylov_b200_set_options, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h.ptr, ext))
+    if ws.warm_start                      # warm_start!(ws, X0) stored X0 in ws.ΔX
+      check(ccall((:krylov_block_warm_start, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint), h.ptr, ws.ΔX.ptr, A.n, p))
+      ws.warm_start = false
+    end
+    rc = ccall((:krylov_block_solve, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+               h.ptr, C_NULL, C_NULL, C_NULL, B.ptr, C_NULL, o)
+    rc == 0 || error(unsafe_string(ccall((:krylov_b200_last_error, lib), Cstring, ())))
+    check(ccall((:krylov_block_get_X, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint), h.ptr, ws.X.ptr, A.n, p))
+  end
+  fill_stats!(ws, h, T)
+  ws
+end
+function Krylov.block_gmres!(ws::Krylov.BlockGmresWorkspace{T,T,B200Vector{T},B200Matrix{T}}, A::B200CSR{T}, B::B200Matrix{T},
+                             X0::B200Matrix{T}; kw...) where T
+  Krylov.warm_start!(ws, X0)
+  Krylov.block_gmres!(ws, A, B; kw...)
+end
 
 end # module

@@ -169,3 +169,10 @@ def test_solver_methods_accept_the_reference_kwargs():
     assert JL.count("(:krylov_workspace_create, lib)") == 1 and "krylov_b200_attach_csr" in JL
     for solver in ("cg!", "minres!", "gmres!", "bicgstab!", "cr!", "cgs!", "cg_lanczos!", "fom!", "fgmres!", "dqgmres!", "diom!"):
         assert solver.rstrip("!") in JL, solver
+    # block solver and block-Jacobi preconditioner are bound too
+    assert "function Krylov.block_gmres!(" in JL and "(:krylov_block_solve, lib)" in JL and "struct B200Matrix" in JL
+    assert "(:krylov_b200_set_preconditioner_blockdiag, lib)" in JL and "struct B200BlockDiagonal" in JL
+    m2 = re.search(r"function Krylov\.block_gmres!\(ws::.*?;(.*?)\) where T", JL, flags=re.S)
+    bk = set(re.findall(r"(\w+)(?:::[^=]+?)?\s*=(?!=)", m2.group(1)))
+    for kw in ("M", "N", "ldiv", "restart", "reorthogonalization", "atol", "rtol", "itmax", "timemax", "verbose", "history", "callback", "iostream"):
+        assert kw in bk, kw                      # src/block_gmres.jl:85-97
