@@ -1,25 +1,27 @@
-// cg_fused.cu -- the CG hot loop (src/cg.jl:195-268) as two launches per
-// iteration with every scalar recurrence on the device.
+// cg_fused.cu -- the CG hot loop (src/cg.jl:195-268) with every scalar recurrence on the device.
 //
-//   K1  p <- z + beta p   (cg.jl:259, applied on the fly while gathering)
-//       Ap <- A p         (cg.jl:196)
-//       pAp <- <p, Ap>    (cg.jl:197)   -> curvature test + alpha (cg.jl:198-213)
-//   K2  x += alpha p ; r -= alpha Ap    (cg.jl:239-240)
-//       gamma' <- <r, r>  (cg.jl:242)   -> rNorm, stop tests, beta, pNorm2 (cg.jl:244-258)
+//   phase A / K1  p <- z + beta p   (cg.jl:259, applied on the fly while gathering)
+//                 Ap <- A p         (cg.jl:196)
+//                 pAp <- <p, Ap>    (cg.jl:197)   -> curvature test + alpha (cg.jl:198-213)
+//                 x += alpha_prev p_prev          (cg.jl:239 of the PREVIOUS iteration; p_prev is in a register here)
+//   phase B / K2  r -= alpha Ap                   (cg.jl:240)
+//                 gamma' <- <r, r>  (cg.jl:242)   -> rNorm, stop tests, beta, pNorm2 (cg.jl:244-258)
 //
-// The host only enqueues launches and polls a pinned copy of the scalar block
-// (one read-back per *batch* of iterations); kernels of iterations enqueued
-// past the stopping point see `done` and return immediately, so niter, x, r, p
-// at exit are those of the reference loop.  p is double-buffered because K1
-// reads the old direction of neighbouring rows while writing the new one.
+// Two implementations of the same arithmetic:
+//   * cg_persist (default): ONE cooperative, co-resident kernel runs a batch of 32 iterations; the phases are
+//     separated by grid-wide barriers that carry the dot-product reductions, the TMA producer prefetches the next
+//     iteration's first tiles across the barrier, the kernel reports its scalar block into pinned host memory when
+//     it ends.  Row-partitioned (MODE = kDist): the halo of r and p is staged over NVLink into the tails of the
+//     local vectors at the start of phase A and both barriers end in a warp-parallel cross-GPU all-reduce
+//     (dist.cuh).  Block-Jacobi M (MODE = kBlockJac): z = M r is formed block by block in phase B.
+//   * cg_k1_tma / cg_k1_rows + cg_k2: two launches per iteration, used when x must be current after every
+//     iteration (callbacks, verbose, timemax), when the operator has no TMA tile plan, and as the A/B reference
+//     (fused = 2, KB200_PERSIST=0).  Their row-partitioned variant pulls halo entries nonzero by nonzero.
 //
-// Row-partitioned (multi-GPU) variant, template DIST: same two kernels; K1
-// additionally gathers the halo entries of r and p straight from the peers'
-// HBM over NVLink and both kernels finish their dot product with the in-kernel
-// cross-GPU all-reduce of dist.cuh.  Hazards: a peer's r is rewritten only in
-// its K2, which starts after the pAp all-reduce that needs MY K1's partial
-// (published after all my halo reads); a peer's p buffer read here (p_k) is
-// rewritten only in its K1 two iterations later.
+// The host only enqueues launches and polls the scalar block (one read-back per batch of iterations); launches
+// enqueued past the stopping point see `done` and return immediately, so niter, x, r, p at exit are those of the
+// reference loop.  p is double-buffered because phase A reads the old direction of neighbouring rows while
+// writing the new one.
 #include "solver_common.h"
 #include "spmv_tiles.cuh"
 

@@ -4,15 +4,20 @@
 // Two mechanisms, both executed INSIDE the compute kernels (no separate
 // communication launch, no host involvement):
 //
-//  * halo gather: the SpMV reads the few x entries owned by other ranks with
-//    plain loads from the peers' vectors (P2P over NVLink), row by row, while
-//    the interior rows stream from local HBM -- the exchange overlaps the math.
-//  * scalar all-reduce: the CTA that finalises a grid-wide dot product writes
-//    its rank's partial into every peer's mailbox (P2P stores + system fence +
-//    sequence flag) and spins on its own mailbox until all ranks have arrived;
-//    every rank sums the same values in rank order, so alpha/beta/stop flags
-//    are bit-identical everywhere.  The all-reduce doubles as the inter-GPU
-//    barrier that orders halo reads against the peers' vector updates.
+//  * halo: the persistent CG kernel STAGES the x entries owned by other ranks
+//    into the tails of its local vectors (coalesced system-scope loads from
+//    the peers' vectors, one NVLink round trip per iteration, hidden behind
+//    the interior tiles); the two-launch CG kernels pull them nonzero by
+//    nonzero; every other product is preceded by halo_exchange_kernel, which
+//    pushes the entries into the peers' x-halo buffers (spmv.cu).
+//  * scalar all-reduce: the CTA that finalises a grid-wide dot product sends
+//    its rank's partial to every peer's mailbox -- value and sequence number
+//    in ONE 8-byte store per half (no fence between data and flag) -- and
+//    polls its own mailbox until all ranks have arrived; every rank sums the
+//    same values in rank order, so alpha/beta/stop flags are bit-identical
+//    everywhere.  A full warp does it in parallel in the persistent kernel.
+//    The all-reduce doubles as the inter-GPU barrier that orders halo reads
+//    against the peers' vector updates.
 //
 // The reference has no distributed code; its documentation recipe
 // (docs/src/custom_workspaces.md:464-637) does local dot + MPI.Allreduce and a
