@@ -47,3 +47,34 @@ def test_committed_bench_lines_carry_green_parity_and_cfg5(fn, n):
         assert {e["solver"] for e in d["extra"]} == {"gmres(30)", "bicgstab"}
     else:
         assert d["parity"]["ranks_agree"] is True and d["cfg5"]["parity"]["ranks_agree"] is True
+
+
+def test_bench_helpers_on_cpu():
+    """The pieces of bench.py that do not need a GPU: the config-4 matrix assembled with torch ops (here on the CPU
+    device) equals the SciPy assembly entry by entry; the parity block is green for the oracle's own history and red
+    for a perturbed one; the golden parity reads the committed cfg5 history."""
+    import numpy as np
+    import torch
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "krylov.jl_b200")]
+    import bench
+    from krylov_b200 import problems as P
+    from krylov_b200.problems import div_grad_csr
+    from oracle import oracle as O
+    n = 5000
+    rp, ci, va = P.random_csr(n, 20, seed=1234, dtype=np.float32)
+    drp, dci, dva = bench.device_random_csr(torch, torch.device("cpu"), n)
+    assert np.array_equal(drp.numpy(), rp) and np.array_equal(dci.numpy(), ci) and np.array_equal(dva.numpy(), va)
+    N, iters = 12, 30
+    rp, ci, va = div_grad_csr(N)
+    _, _, _, hist = O.cg_timed(rp, ci, va, np.ones(N ** 3), iters, 1, history=True)
+    ok = bench.parity_block(list(hist), N, iters)
+    assert ok["ok"] and ok["niter_equal"] and ok["iters_compared"] == iters and ok["max_rel_dev"] <= 1e-10      # OpenMP reduction order differs between thread counts
+    bad = bench.parity_block(list(hist * (1 + 1e-5)), N, iters)
+    assert bad["ok"] is False and bad["max_rel_dev"] > 1e-6
+    short = bench.parity_block(list(hist[:-3]), N, iters)
+    assert short["ok"] is False and short["niter_equal"] is False
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_cg_poisson464.json")))
+    g = bench.golden_parity(gold["residuals"], "bench_cg_poisson464")
+    assert g["ok"] and g["iters_compared"] == bench.WORKLOADS["poisson464"][1]
+    assert bench.golden_parity([1.0, 2.0], "no_such_file")["ok"] is None
+    assert bench.algorithmic_bytes_cg(215 ** 3, 7 * 215 ** 3 - 6 * 215 ** 2) == 1586811804        # SURVEY.md 8(d)
