@@ -269,7 +269,9 @@ static T read_slot(Ctx& c, int slot) {
   KB_CUDA(cudaMemcpyAsync(reinterpret_cast<double*>(c.hscal) + slot, reinterpret_cast<double*>(c.dscal) + slot,
                           sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   c.sync();
-  return *reinterpret_cast<T*>(reinterpret_cast<double*>(c.hscal) + slot);
+  const T v = *reinterpret_cast<T*>(reinterpret_cast<double*>(c.hscal) + slot);
+  dist_nan_guard(c, (double)v);
+  return v;
 }
 
 template <class T> void k_dot_dev(Ctx& c, int n, const T* x, const T* y, int slot) { dot_launch<T>(c, n, x, y, slot, 0); }
@@ -291,6 +293,7 @@ template <class T> void k_dot2(Ctx& c, int n, const T* a, const T* b, const T* u
   c.sync();
   *r1 = reinterpret_cast<T*>(c.hscal)[0];
   *r2 = reinterpret_cast<T*>(c.hscal)[1];
+  dist_nan_guard(c, (double)*r1 + (double)*r2);
 }
 
 // ---------------------------------------------------------------------------

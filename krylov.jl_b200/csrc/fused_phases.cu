@@ -221,6 +221,7 @@ void bicgstab_fused_iteration(Workspace<T>& ws, const Csr<T>& A, const T* cvec, 
   launch_stream<T, 0>(c, n, BicgK5Body<T>{ws.p, ws.r, ws.v, S}, NoFin(), 5);
   c.sync();
   *alpha = H[1].alpha; *omega = H[1].omega; *next_rho = H[1].next_rho; *rNorm = H[1].rNorm;
+  dist_nan_guard(c, (double)*rNorm);
 }
 
 // ===========================================================================
@@ -313,6 +314,7 @@ void minres_fused_lanczos(Workspace<T>& ws, const Csr<T>& A, int iter, T lambda,
   KB_CUDA(cudaMemcpyAsync(H, S, sizeof(St), cudaMemcpyDeviceToHost, c.stream));
   c.sync();
   *alpha = H->alpha; *beta2 = H->beta2;
+  dist_nan_guard(c, (double)*alpha + (double)*beta2);
   T* old_r1 = ws.r1;          // r1 <- r2 ; r2 <- y   (minres.jl:309-310) by rotating the bindings
   ws.r1 = ws.r2; ws.r2 = ws.y; ws.y = old_r1;
 }
@@ -327,6 +329,7 @@ T minres_fused_update(Workspace<T>& ws, T* w, T gamma, T phi) {
   launch_stream<T, 1>(c, ws.n, MinresK3Body<T>{w, ws.x, T(1) / gamma, phi}, MinresK3Fin<T>{S}, 5);
   KB_CUDA(cudaMemcpyAsync(H, S, sizeof(St), cudaMemcpyDeviceToHost, c.stream));
   c.sync();
+  dist_nan_guard(c, (double)H->xx);
   return std::sqrt(H->xx);
 }
 
@@ -376,6 +379,7 @@ void fused_orth_chain(Workspace<T>& ws, const Csr<T>& A, const T* xin, T* q, con
   c.sync();
   for (int i = 0; i < cnt; i++) h_out[i] = H->h[i];
   *Hbis = std::sqrt(H->hbis2);
+  dist_nan_guard(c, (double)H->hbis2);
 }
 
 // Arnoldi step k (1-based inner_iter): w = A V[k]; MGS against V[1..k]; returns h[0..k-1] and Hbis.
@@ -433,6 +437,7 @@ template <class T, int K> static void sib_read(Ctx& c, T* out) {
   KB_CUDA(cudaMemcpyAsync(h, sib_slots<T>(c), sizeof(T) * K, cudaMemcpyDeviceToHost, c.stream));
   c.sync();
   for (int k = 0; k < K; k++) out[k] = h[k];
+  dist_nan_guard(c, (double)out[0]);
 }
 
 // ---- dqgmres! / diom!: direction update (dqgmres.jl:279-289, diom.jl:279-289) in one pass per 8 stack vectors ----

@@ -70,6 +70,9 @@ template <class T> void k_blockdiag_invert(Ctx& c, int n, int bs, const T* block
 double k_dist_sum(Ctx& c, double v);                                   // sum of a host scalar over all ranks
 void dist_agree_on_exit(Ctx& c, bool& user_exit, bool& overtimed);     // OR the exit flags over the ranks
 void dist_check_alive(Ctx& c);                                         // throws once a reduction has timed out
+// A NaN scalar read back on a row-partitioned workspace may be the mark of a dead communicator (every reduction
+// returns NaN from then on): raise at once instead of iterating on NaNs until itmax.
+inline void dist_nan_guard(Ctx& c, double v) { if (c.dcomm && v != v) dist_check_alive(c); }
 
 // ---------------------------------------------------------------------------
 // CSR operator resident in HBM (int32 indices, 0-based, columns ascending).
